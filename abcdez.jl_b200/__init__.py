@@ -1,0 +1,9 @@
+"""abcdez.jl_b200 -- B200-native implementation of the ABCdeZ.jl particle hot path.
+
+The directory name contains a dot, so import it through the alias module at the repo root:
+``import abcdez_b200`` (abcdez_b200.py registers this package under that name).
+"""
+from .host import *  # noqa: F401,F403
+from .host import (ABCdeZError, Context, Factored, Model, Population, abcdesmc, abcdemc, lib, model_names,
+                   wsample_stratified, default_context, EXPORTS, LIB_PATH)
+from . import host, build  # noqa: F401

@@ -1,0 +1,68 @@
+"""Builds libabcdez_cuda.so for sm_100a in-tree (abcdez.jl_b200/libabcdez_cuda.so).
+
+nvcc cross-compiles without a GPU; the translation units are compiled in parallel.
+-fmad=false: the reference's arithmetic never contracts a*b+c and accept decisions must match
+the CPU oracle bit for bit (DESIGN.md "Numerics").
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libabcdez_cuda.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers_mtime():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "abcdez_cuda.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src: str, verbose: bool) -> str:
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = _sources()
+    hm = _headers_mtime()
+    todo, objs = [], []
+    for s in srcs:
+        obj = os.path.join(OBJ, s[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(os.path.join(CSRC, s)), hm):
+            todo.append(s)
+    if todo:
+        with cf.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            list(ex.map(lambda s: _compile(s, verbose), todo))
+    if todo or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

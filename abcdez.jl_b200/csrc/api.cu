@@ -1,0 +1,909 @@
+// api.cu -- the C ABI of libabcdez_cuda.so (include/abcdez_cuda.h): contexts, priors, models,
+// device-resident populations, the stage-level entry points used by the parity tests, and the
+// two run loops abcdez_smc_run (abcdesmc!, src/abcdez_smc.jl:215-394 of the reference) and
+// abcdez_mc_run (abcdemc!, src/abcdez_mc.jl:102-172).
+#include "internal.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace abcdez;
+
+// ---------------------------------------------------------------------------------------
+// errors: status codes + a thread-local message, never an exception across the ABI
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ABCDEZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+#define CHECK_ARG(cond, msg)                                                                       \
+    do {                                                                                           \
+        if (!(cond)) return fail(ABCDEZ_ERR_BAD_ARG, msg);                                         \
+    } while (0)
+
+extern "C" const char* abcdez_last_error(void) { return g_err.c_str(); }
+extern "C" int abcdez_version(void) { return ABCDEZ_VERSION; }
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int abcdez_init(int device, void* stream, abcdez_ctx** out)
+{
+    CHECK_ARG(out != nullptr, "abcdez_init: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(ABCDEZ_ERR_CUDA, std::string("abcdez_init: no CUDA device (") + cudaGetErrorString(e) +
+                    "); libabcdez_cuda has no CPU fallback");
+    CHECK_ARG(device >= 0 && device < n, "abcdez_init: device index out of range");
+    CU(cudaSetDevice(device));
+    abcdez_ctx* c = new (std::nothrow) abcdez_ctx();
+    if (!c) return fail(ABCDEZ_ERR_CUDA, "abcdez_init: out of host memory");
+    c->device = device;
+    c->rank = 0; c->world = 1; c->nccl_comm = nullptr;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) { delete c; return fail(ABCDEZ_ERR_CUDA, cudaGetErrorString(e2)); }
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_destroy(abcdez_ctx* ctx)
+{
+    if (!ctx) return ABCDEZ_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_sync(abcdez_ctx* ctx)
+{
+    CHECK_ARG(ctx != nullptr, "abcdez_sync: ctx is NULL");
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_nccl_unique_id(void*) { return fail(ABCDEZ_ERR_UNSUPPORTED, "NCCL sharding: see abcdez.jl_b200/dist.py (round 1 shards by independent sub-populations)"); }
+extern "C" int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void*)
+{
+    CHECK_ARG(ctx != nullptr, "abcdez_comm_init: ctx is NULL");
+    CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "abcdez_comm_init: bad rank/world");
+    ctx->rank = rank; ctx->world = world;
+    return ABCDEZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// prior
+// ---------------------------------------------------------------------------------------
+extern "C" int abcdez_prior_create(abcdez_ctx* ctx, int d, const int32_t* family, const double* params,
+                                   abcdez_prior** out)
+{
+    CHECK_ARG(ctx && family && params && out, "abcdez_prior_create: NULL argument");
+    CHECK_ARG(d >= 1 && d <= ABCDEZ_MAXD, "abcdez_prior_create: length(prior) must be in 1..16");
+    abcdez_prior* p = new (std::nothrow) abcdez_prior();
+    if (!p) return fail(ABCDEZ_ERR_CUDA, "out of host memory");
+    memset(&p->dev, 0, sizeof(p->dev));
+    p->dev.d = d;
+    for (int k = 0; k < d; ++k) {
+        const double* q = params + 4 * k;
+        p->dev.family[k] = family[k];
+        for (int j = 0; j < 4; ++j) p->dev.p[k][j] = q[j];
+        bool ok = true; double c = 0.0;
+        switch (family[k]) {
+        case ABCDEZ_NORMAL: ok = q[1] > 0.0; c = log(q[1]); break;
+        case ABCDEZ_UNIFORM: ok = q[0] < q[1]; c = -log(q[1] - q[0]); break;
+        case ABCDEZ_DISCRETE_UNIFORM: ok = q[0] <= q[1] && q[0] == rint(q[0]) && q[1] == rint(q[1]);
+            c = log(1.0 / (q[1] - q[0] + 1.0)); break;
+        case ABCDEZ_LOGNORMAL: ok = q[1] > 0.0; c = log(q[1]); break;
+        case ABCDEZ_EXPONENTIAL: ok = q[0] > 0.0; c = log(q[0]); break;
+        case ABCDEZ_GAMMA: ok = q[0] > 0.0 && q[1] > 0.0; c = lgamma(q[0]) + q[0] * log(q[1]); break;
+        case ABCDEZ_BETA: ok = q[0] > 0.0 && q[1] > 0.0; c = lgamma(q[0]) + lgamma(q[1]) - lgamma(q[0] + q[1]); break;
+        case ABCDEZ_NEGBIN: ok = q[0] > 0.0 && q[1] > 0.0 && q[1] <= 1.0; c = q[0] * log(q[1]) - lgamma(q[0]); break;
+        default: delete p; return fail(ABCDEZ_ERR_UNSUPPORTED, "abcdez_prior_create: unsupported marginal family");
+        }
+        if (!ok) { delete p; return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_prior_create: invalid marginal parameters"); }
+        p->dev.c[k] = c;
+    }
+    *out = p;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_prior_destroy(abcdez_prior* p) { delete p; return ABCDEZ_OK; }
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
+
+static int prior_op(abcdez_ctx* ctx, const abcdez_prior* p, int64_t N, int op, const double* in, double* out,
+                    uint64_t seed, uint32_t epoch, int64_t id0)
+{
+    CHECK_ARG(ctx && p && out, "prior op: NULL argument");
+    CHECK_ARG(N >= 0, "prior op: N < 0");
+    if (N == 0) return ABCDEZ_OK;
+    CU(cudaSetDevice(ctx->device));
+    int d = p->dev.d;
+    size_t nin = (size_t)N * d * 8, nout = (op == PRIOR_OP_LOGPDF ? (size_t)N : (size_t)N * d) * 8;
+    DevBuf din, dout;
+    CU(din.alloc(nin)); CU(dout.alloc(nout));
+    if (op != PRIOR_OP_SAMPLE) { CHECK_ARG(in != nullptr, "prior op: theta is NULL"); CU(cudaMemcpyAsync(din.p, in, nin, cudaMemcpyHostToDevice, ctx->stream)); }
+    launch_prior_op(ctx->stream, d, p->dev, N, op, din.as<double>(), dout.as<double>(), seed, epoch, (uint32_t)id0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, nout, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_prior_sample(abcdez_ctx* ctx, const abcdez_prior* p, int64_t N, uint64_t seed, uint32_t epoch,
+                                   int64_t id0, double* theta_out)
+{
+    return prior_op(ctx, p, N, PRIOR_OP_SAMPLE, nullptr, theta_out, seed, epoch, id0);
+}
+extern "C" int abcdez_prior_logpdf(abcdez_ctx* ctx, const abcdez_prior* p, int64_t N, const double* theta, double* out)
+{
+    return prior_op(ctx, p, N, PRIOR_OP_LOGPDF, theta, out, 0, 0, 0);
+}
+extern "C" int abcdez_prior_push(abcdez_ctx* ctx, const abcdez_prior* p, int64_t N, const double* theta, double* out)
+{
+    return prior_op(ctx, p, N, PRIOR_OP_PUSH, theta, out, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// models
+// ---------------------------------------------------------------------------------------
+extern "C" int abcdez_model_count(void) { return model_count(); }
+extern "C" const char* abcdez_model_name(int id) { const ModelOps* o = model_ops(id); return o ? o->name : nullptr; }
+extern "C" int abcdez_model_lookup(const char* name, int* id)
+{
+    CHECK_ARG(name && id, "abcdez_model_lookup: NULL argument");
+    for (int i = 0; i < model_count(); ++i)
+        if (strcmp(model_ops(i)->name, name) == 0) { *id = i; return ABCDEZ_OK; }
+    return fail(ABCDEZ_ERR_BAD_ARG, std::string("abcdez_model_lookup: no registered model named '") + name + "'");
+}
+extern "C" int abcdez_model_info(int id, int* d, int* blob_bytes)
+{
+    const ModelOps* o = model_ops(id);
+    CHECK_ARG(o != nullptr, "abcdez_model_info: bad model id");
+    if (d) *d = o->d;
+    if (blob_bytes) *blob_bytes = o->blob;
+    return ABCDEZ_OK;
+}
+extern "C" int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, size_t ndata, abcdez_model** out)
+{
+    CHECK_ARG(ctx && out, "abcdez_model_bind: NULL argument");
+    const ModelOps* o = model_ops(id);
+    CHECK_ARG(o != nullptr, "abcdez_model_bind: bad model id");
+    if (!o->smc_sweep) return fail(ABCDEZ_ERR_UNSUPPORTED, std::string("model '") + o->name + "' has no device functor in this build");
+    CHECK_ARG(ndata <= ABCDEZ_MAXDATA, "abcdez_model_bind: more than ABCDEZ_MAXDATA doubles of data");
+    CHECK_ARG(ndata == 0 || data != nullptr, "abcdez_model_bind: data is NULL");
+    abcdez_model* m = new (std::nothrow) abcdez_model();
+    if (!m) return fail(ABCDEZ_ERR_CUDA, "out of host memory");
+    m->id = id; m->ops = o;
+    memset(&m->data, 0, sizeof(m->data));
+    for (size_t i = 0; i < ndata; ++i) m->data.v[i] = data[i];
+    *out = m;
+    return ABCDEZ_OK;
+}
+extern "C" int abcdez_model_destroy(abcdez_model* m) { delete m; return ABCDEZ_OK; }
+
+extern "C" int abcdez_simulate(abcdez_ctx* ctx, const abcdez_model* m, int64_t N, const double* theta_pushed,
+                               uint64_t seed, uint32_t epoch, uint32_t tag, int64_t id0, double* dist_out,
+                               uint8_t* blobs_out)
+{
+    CHECK_ARG(ctx && m && theta_pushed && dist_out, "abcdez_simulate: NULL argument");
+    CHECK_ARG(N >= 0, "abcdez_simulate: N < 0");
+    if (N == 0) return ABCDEZ_OK;
+    CU(cudaSetDevice(ctx->device));
+    int d = m->ops->d, B = m->ops->blob;
+    DevBuf dth, dd, db;
+    CU(dth.alloc((size_t)N * d * 8)); CU(dd.alloc((size_t)N * 8)); CU(db.alloc((size_t)N * (B ? B : 8)));
+    CU(cudaMemcpyAsync(dth.p, theta_pushed, (size_t)N * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    m->ops->simulate(ctx->stream, nullptr, m->data, N, dth.as<double>(), seed, epoch, tag, (uint32_t)id0,
+                     dd.as<double>(), B ? db.as<double>() : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dist_out, dd.p, (size_t)N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (B && blobs_out) CU(cudaMemcpyAsync(blobs_out, db.p, (size_t)N * B, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ABCDEZ_OK;
+}
+
+extern "C" double abcdez_kernel_logpdf(int kernel, double eps, double x) { return abck_logpdf(kernel, eps, x); }
+extern "C" double abcdez_kernel_pdf(int kernel, double eps, double x)
+{
+    if (!abck_insupport(kernel, eps, x)) return 0.0;
+    if (abck_is_indicator(kernel)) return 1.0;
+    double q = x / eps;
+    return 1.0 - q * q;
+}
+
+// ---------------------------------------------------------------------------------------
+// population
+// ---------------------------------------------------------------------------------------
+__global__ void fill_f64_kernel(double* p, int64_t n, double v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static int push_ctrl(abcdez_pop* pop)
+{
+    CU(cudaMemcpyAsync(pop->dev.ctrl, pop->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, pop->ctx->stream));
+    return ABCDEZ_OK;
+}
+static int pull_ctrl(abcdez_pop* pop)
+{
+    CU(cudaMemcpyAsync(pop->h_ctrl, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, pop->ctx->stream));
+    CU(cudaStreamSynchronize(pop->ctx->stream));
+    return ABCDEZ_OK;
+}
+
+static int ensure_scratch(abcdez_pop* pop, size_t bytes)
+{
+    if (bytes <= pop->scratch_bytes) return ABCDEZ_OK;
+    if (pop->scratch) cudaFree(pop->scratch);
+    pop->scratch = nullptr; pop->scratch_bytes = 0;
+    CU(cudaMalloc(&pop->scratch, bytes));
+    pop->scratch_bytes = bytes;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
+{
+    if (!pop) return ABCDEZ_OK;
+    cudaSetDevice(pop->ctx->device);
+    cudaStreamSynchronize(pop->ctx->stream);
+    PopDev& P = pop->dev;
+    for (int b = 0; b < 2; ++b) { cudaFree(P.theta[b]); cudaFree(P.logpi[b]); cudaFree(P.delta[b]); cudaFree(P.blob[b]); }
+    cudaFree(P.W); cudaFree(P.alive); cudaFree(P.alive_list); cudaFree(P.ctrl); cudaFree(P.partial);
+    cudaFree(P.tile_cnt); cudaFree(P.sel_hist); cudaFree(P.cumsum); cudaFree(P.inds); cudaFree(P.hist); cudaFree(P.tabs);
+    if (pop->scratch) cudaFree(pop->scratch);
+    if (pop->sorted_delta) cudaFree(pop->sorted_delta);
+    if (pop->order) cudaFree(pop->order);
+    if (pop->sort_tmp) cudaFree(pop->sort_tmp);
+    if (pop->h_ctrl) cudaFreeHost(pop->h_ctrl);
+    if (pop->ev0) cudaEventDestroy(pop->ev0);
+    if (pop->ev1) cudaEventDestroy(pop->ev1);
+    delete pop;
+    return ABCDEZ_OK;
+}
+
+static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, int64_t N,
+                           int64_t id0, int hist_cap, abcdez_pop** out)
+{
+    CHECK_ARG(ctx && prior && model && out, "abcdez_pop_create: NULL argument");
+    CHECK_ARG(N >= 1 && N < (int64_t)0x7fffffff, "abcdez_pop_create: N must be in 1..2^31-2 per GPU");
+    CHECK_ARG(prior->dev.d == model->ops->d, "abcdez_pop_create: length(prior) != model dimension");
+    CHECK_ARG(id0 >= 0 && id0 + N <= (int64_t)0xffffffffll, "abcdez_pop_create: global particle ids must fit 32 bits");
+    CU(cudaSetDevice(ctx->device));
+    abcdez_pop* pop = new (std::nothrow) abcdez_pop();
+    if (!pop) return fail(ABCDEZ_ERR_CUDA, "out of host memory");
+    memset(static_cast<void*>(pop), 0, sizeof(*pop));
+    pop->ctx = ctx; pop->prior = prior->dev; pop->ops = model->ops; pop->data = model->data;
+    pop->N = N; pop->D = model->ops->d; pop->DS = row_stride(pop->D); pop->NB = model->ops->blob / 8;
+    pop->hist_cap = hist_cap;
+    PopDev& P = pop->dev;
+    P.N = (uint32_t)N; P.id0 = (uint32_t)id0; P.ntiles = (uint32_t)((N + TILE - 1) / TILE);
+    size_t n = (size_t)N;
+#define ALLOC(ptr, bytes)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes) ? (bytes) : 8);                        \
+        if (e_ != cudaSuccess) { abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); } \
+    } while (0)
+    for (int b = 0; b < 2; ++b) {
+        ALLOC(P.theta[b], n * pop->DS * 8); ALLOC(P.logpi[b], n * 8); ALLOC(P.delta[b], n * 8);
+        ALLOC(P.blob[b], n * pop->NB * 8);
+    }
+    ALLOC(P.W, n * 8); ALLOC(P.alive, n + 4); ALLOC(P.alive_list, n * 4); ALLOC(P.ctrl, sizeof(Ctrl));
+    ALLOC(P.partial, (size_t)P.ntiles * 2 * 8 + 64); ALLOC(P.tile_cnt, (size_t)P.ntiles * 4 + 64);
+    ALLOC(P.sel_hist, SEL_BINS * 4); ALLOC(P.cumsum, n * 8); ALLOC(P.inds, n * 4);
+    ALLOC(P.hist, (size_t)(hist_cap > 0 ? hist_cap : 1) * 8 * 8); ALLOC(P.tabs, 2 * sizeof(SeqTab));
+#undef ALLOC
+    CU(cudaMallocHost((void**)&pop->h_ctrl, sizeof(Ctrl)));
+    CU(cudaEventCreate(&pop->ev0)); CU(cudaEventCreate(&pop->ev1));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(P.sel_hist, 0, SEL_BINS * 4, st));
+    CU(cudaMemsetAsync(P.alive, 1, n, st));
+    CU(cudaMemsetAsync(P.theta[0], 0, n * pop->DS * 8, st));
+    CU(cudaMemsetAsync(P.theta[1], 0, n * pop->DS * 8, st));
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.W, N, 1.0 / (double)N);
+    Ctrl* c = pop->h_ctrl;
+    memset(c, 0, sizeof(Ctrl));
+    c->eps = INFINITY; c->eps_k = INFINITY; c->eps_target = 0.0;
+    c->facc = 1.0; c->gamma0 = 2.38 / sqrt(2.0 * (double)pop->D); c->gsig = 1e-5;     // src/abcdez_smc.jl:280-281
+    c->alpha = 0.95; c->Kmcmc_min = 1.0; c->facc_tune = 0.975;
+    c->nsims_max = (long long)10000000; c->kind = ABCDEZ_INDICATOR_STRICT; c->Kmcmc = 3; c->Ki = 3;
+    c->N = (uint32_t)N; c->n_alive = (uint32_t)N; c->ess_min = 0.5 * (double)N;
+    c->hist_cap = hist_cap;
+    c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull; c->acc.min_gt_key = ~0ull;
+    c->acc.w_alive = 1.0 / (double)N;
+    int rc = push_ctrl(pop);
+    if (rc) { abcdez_pop_destroy(pop); return rc; }
+    CU(cudaStreamSynchronize(st));
+    *out = pop;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_create(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, int64_t N,
+                                 int64_t id0, abcdez_pop** out)
+{
+    return pop_create_impl(ctx, prior, model, N, id0, 0, out);
+}
+
+extern "C" int abcdez_pop_upload(abcdez_pop* pop, const double* theta, const double* logpi, const double* delta,
+                                 const uint8_t* blobs, const double* W, const uint8_t* alive)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_upload: pop is NULL");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    cudaStream_t st = pop->ctx->stream;
+    PopDev& P = pop->dev; int cur = pop->h_ctrl->cur; size_t n = (size_t)pop->N;
+    if (theta) {
+        if (pop->DS == pop->D) CU(cudaMemcpyAsync(P.theta[cur], theta, n * pop->D * 8, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpy2DAsync(P.theta[cur], (size_t)pop->DS * 8, theta, (size_t)pop->D * 8, (size_t)pop->D * 8, n,
+                                  cudaMemcpyHostToDevice, st));
+    }
+    if (logpi) CU(cudaMemcpyAsync(P.logpi[cur], logpi, n * 8, cudaMemcpyHostToDevice, st));
+    if (delta) CU(cudaMemcpyAsync(P.delta[cur], delta, n * 8, cudaMemcpyHostToDevice, st));
+    if (blobs && pop->NB) CU(cudaMemcpyAsync(P.blob[cur], blobs, n * pop->NB * 8, cudaMemcpyHostToDevice, st));
+    if (W) CU(cudaMemcpyAsync(P.W, W, n * 8, cudaMemcpyHostToDevice, st));
+    if (alive) {
+        CU(cudaMemcpyAsync(P.alive, alive, n, cudaMemcpyHostToDevice, st));
+        // keep the control block and the compacted list consistent with the uploaded flags
+        uint32_t na = 0; double wal = 0.0;
+        for (size_t i = 0; i < n; ++i) if (alive[i]) { na++; if (W && wal == 0.0) wal = W[i]; }
+        std::vector<uint32_t> list; list.reserve(na);
+        for (size_t i = 0; i < n; ++i) if (alive[i]) list.push_back((uint32_t)i);
+        if (na) CU(cudaMemcpyAsync(P.alive_list, list.data(), (size_t)na * 4, cudaMemcpyHostToDevice, st));
+        pop->h_ctrl->n_alive = na;
+        if (W) pop->h_ctrl->acc.w_alive = wal;
+        CU(cudaStreamSynchronize(st));
+        rc = push_ctrl(pop); if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(st));
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_download(abcdez_pop* pop, double* theta, double* logpi, double* delta, uint8_t* blobs,
+                                   double* W, uint8_t* alive)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_download: pop is NULL");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    cudaStream_t st = pop->ctx->stream;
+    PopDev& P = pop->dev; int cur = pop->h_ctrl->cur; size_t n = (size_t)pop->N;
+    if (theta) {
+        if (pop->DS == pop->D) CU(cudaMemcpyAsync(theta, P.theta[cur], n * pop->D * 8, cudaMemcpyDeviceToHost, st));
+        else CU(cudaMemcpy2DAsync(theta, (size_t)pop->D * 8, P.theta[cur], (size_t)pop->DS * 8, (size_t)pop->D * 8, n,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    if (logpi) CU(cudaMemcpyAsync(logpi, P.logpi[cur], n * 8, cudaMemcpyDeviceToHost, st));
+    if (delta) CU(cudaMemcpyAsync(delta, P.delta[cur], n * 8, cudaMemcpyDeviceToHost, st));
+    if (blobs && pop->NB) CU(cudaMemcpyAsync(blobs, P.blob[cur], n * pop->NB * 8, cudaMemcpyDeviceToHost, st));
+    if (W) CU(cudaMemcpyAsync(W, P.W, n * 8, cudaMemcpyDeviceToHost, st));
+    if (alive) CU(cudaMemcpyAsync(alive, P.alive, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_set(abcdez_pop* pop, double eps, double eps_kernel_prev, int32_t kernel, double gamma0,
+                              double gamma_sigma, uint64_t seed, uint32_t sweep_epoch)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_set: pop is NULL");
+    CHECK_ARG(kernel >= 0 && kernel <= 3, "abcdez_pop_set: unknown ABC kernel");
+    CHECK_ARG(eps >= 0.0 && eps_kernel_prev >= 0.0, "Expected \xcf\xb5 \xe2\x89\xa5 0.0");   // src/abcdez_types.jl:30
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    Ctrl* c = pop->h_ctrl;
+    c->eps = eps; c->eps_k = eps_kernel_prev; c->kind = kernel; c->gamma0 = gamma0; c->gsig = gamma_sigma;
+    c->seed = seed; c->sweep_epoch = sweep_epoch;
+    c->stop = 0; c->sweeps_done = 0; c->sweep_idx = 0; c->Kmcmc = 0x7fffffff; c->Ki = 1;
+    c->Kmcmc_min = INFINITY; c->naccs_iter = 0; c->err = 0; c->acc.err = 0;
+    rc = push_ctrl(pop); if (rc) return rc;
+    CU(cudaStreamSynchronize(pop->ctx->stream));
+    return ABCDEZ_OK;
+}
+
+static int check_dev_err(abcdez_pop* pop, const char* where)
+{
+    int e = pop->h_ctrl->err ? pop->h_ctrl->err : pop->h_ctrl->acc.err;
+    if (!e) return ABCDEZ_OK;
+    const char* what = e == ABCDEZ_ERR_NAN_DISTANCE ? "NaN distance among alive particles (quantile undefined)"
+                     : e == ABCDEZ_ERR_NO_ALIVE ? "No alive particles"
+                     : e == ABCDEZ_ERR_INIT_RETRY ? "abcde_init!: redraw limit reached without a finite distance/log-prior"
+                     : e == ABCDEZ_ERR_PARTNER_RETRY ? "partner draw did not terminate (fewer than 3 alive particles?)"
+                     : "device-side error";
+    return fail(e, std::string(where) + ": " + what);
+}
+
+#define TIME_BEGIN(pop) CU(cudaEventRecord((pop)->ev0, (pop)->ctx->stream))
+#define TIME_END(pop, nl)                                                                          \
+    do {                                                                                           \
+        CU(cudaEventRecord((pop)->ev1, (pop)->ctx->stream));                                       \
+        CU(cudaEventSynchronize((pop)->ev1));                                                      \
+        float ms_ = 0.f; CU(cudaEventElapsedTime(&ms_, (pop)->ev0, (pop)->ev1));                   \
+        (pop)->last_ms = ms_; (pop)->last_launches = (nl);                                         \
+    } while (0)
+
+extern "C" int abcdez_pop_last_timing(abcdez_pop* pop, double* ms, int64_t* launches)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_last_timing: pop is NULL");
+    if (ms) *ms = pop->last_ms;
+    if (launches) *launches = pop->last_launches;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_init(abcdez_pop* pop, uint64_t seed, int draw_prior, int64_t* nredraws)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_init: pop is NULL");
+    CU(cudaSetDevice(pop->ctx->device));
+    TIME_BEGIN(pop);
+    pop->ops->init(pop->ctx->stream, pop->dev, pop->prior, pop->data, seed, draw_prior);
+    CU(cudaGetLastError());
+    TIME_END(pop, 1);
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    if (nredraws) *nredraws = pop->h_ctrl->redraws;
+    return check_dev_err(pop, "abcdez_pop_init");
+}
+
+// copy optional injected host arrays into the scratch buffer; returns device pointers
+static int stage_inject(abcdez_pop* pop, const int32_t* s, const int32_t* a, const int32_t* b, const double* z,
+                        const double* u, bool want_flags, SweepInj* inj)
+{
+    size_t n = (size_t)pop->N;
+    size_t bytes = 3 * n * 4 + 2 * n * 8 + n + 64;
+    int rc = ensure_scratch(pop, bytes); if (rc) return rc;
+    char* base = (char*)pop->scratch;
+    double* dz = (double*)base; double* du = dz + n;
+    int32_t* ds = (int32_t*)(du + n); int32_t* da = ds + n; int32_t* db = da + n;
+    uint8_t* df = (uint8_t*)(db + n);
+    cudaStream_t st = pop->ctx->stream;
+    memset(inj, 0, sizeof(*inj));
+    if (z) { CU(cudaMemcpyAsync(dz, z, n * 8, cudaMemcpyHostToDevice, st)); inj->z = dz; }
+    if (u) { CU(cudaMemcpyAsync(du, u, n * 8, cudaMemcpyHostToDevice, st)); inj->u = du; }
+    if (s) { CU(cudaMemcpyAsync(ds, s, n * 4, cudaMemcpyHostToDevice, st)); inj->s = ds; }
+    if (a && b) {
+        CU(cudaMemcpyAsync(da, a, n * 4, cudaMemcpyHostToDevice, st)); inj->a = da;
+        CU(cudaMemcpyAsync(db, b, n * 4, cudaMemcpyHostToDevice, st)); inj->b = db;
+    }
+    if (want_flags) { CU(cudaMemsetAsync(df, 0, n, st)); inj->flags = df; }
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_smc_sweep(abcdez_pop* pop, const int32_t* inj_a, const int32_t* inj_b, const double* inj_z,
+                                    const double* inj_u, uint8_t* flags_out, int64_t* nsims, int64_t* naccs)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_smc_sweep: pop is NULL");
+    CHECK_ARG((inj_a == nullptr) == (inj_b == nullptr), "abcdez_pop_smc_sweep: inject both partners or neither");
+    CU(cudaSetDevice(pop->ctx->device));
+    SweepInj inj;
+    int rc = stage_inject(pop, nullptr, inj_a, inj_b, inj_z, inj_u, flags_out != nullptr, &inj); if (rc) return rc;
+    TIME_BEGIN(pop);
+    pop->ops->smc_sweep(pop->ctx->stream, pop->dev, pop->prior, pop->data, inj);
+    CU(cudaGetLastError());
+    TIME_END(pop, 1);
+    if (flags_out) CU(cudaMemcpyAsync(flags_out, inj.flags, (size_t)pop->N, cudaMemcpyDeviceToHost, pop->ctx->stream));
+    rc = pull_ctrl(pop); if (rc) return rc;
+    if (nsims) *nsims = (int64_t)pop->h_ctrl->last_nsims;
+    if (naccs) *naccs = (int64_t)pop->h_ctrl->last_naccs;
+    return check_dev_err(pop, "abcdez_pop_smc_sweep");
+}
+
+static int mc_prepare(abcdez_pop* pop)
+{
+    size_t n = (size_t)pop->N;
+    if (!pop->sorted_delta) {
+        CU(cudaMalloc((void**)&pop->sorted_delta, n * 8));
+        CU(cudaMalloc((void**)&pop->order, n * 4));
+        pop->sort_tmp_bytes = mc_sort_tmp_bytes(pop->N);
+        CU(cudaMalloc(&pop->sort_tmp, pop->sort_tmp_bytes));
+    }
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_mc_sweep(abcdez_pop* pop, double eps_pop, double eps_target, const int32_t* inj_s,
+                                   const int32_t* inj_a, const int32_t* inj_b, const double* inj_z, const double* inj_u,
+                                   uint8_t* flags_out, int64_t* nsims)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_mc_sweep: pop is NULL");
+    CHECK_ARG((inj_a == nullptr) == (inj_b == nullptr), "abcdez_pop_mc_sweep: inject both partners or neither");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    rc = mc_prepare(pop); if (rc) return rc;
+    SweepInj inj;
+    rc = stage_inject(pop, inj_s, inj_a, inj_b, inj_z, inj_u, flags_out != nullptr, &inj); if (rc) return rc;
+    cudaStream_t st = pop->ctx->stream;
+    TIME_BEGIN(pop);
+    int nl = 1;
+    if (!inj_s) nl += launch_mc_prepare(st, pop->dev.N, pop->dev.delta[pop->h_ctrl->cur], pop->sorted_delta, pop->order,
+                                        pop->sort_tmp, pop->sort_tmp_bytes);
+    McArgs mc{ eps_pop, eps_target, pop->sorted_delta, pop->order };
+    pop->ops->mc_sweep(st, pop->dev, pop->prior, pop->data, inj, mc);
+    CU(cudaGetLastError());
+    TIME_END(pop, nl);
+    if (flags_out) CU(cudaMemcpyAsync(flags_out, inj.flags, (size_t)pop->N, cudaMemcpyDeviceToHost, st));
+    rc = pull_ctrl(pop); if (rc) return rc;
+    if (nsims) *nsims = (int64_t)pop->h_ctrl->last_nsims;
+    return check_dev_err(pop, "abcdez_pop_mc_sweep");
+}
+
+extern "C" int abcdez_pop_eps_quantile(abcdez_pop* pop, double alpha, double* q, double* v_lo, double* v_hi)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_eps_quantile: pop is NULL");
+    CHECK_ARG(alpha >= 0.0 && alpha <= 1.0, "abcdez_pop_eps_quantile: alpha out of [0,1]");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    Ctrl* c = pop->h_ctrl;
+    CHECK_ARG(c->n_alive >= 1, "abcdez_pop_eps_quantile: no alive particles");
+    double eps_keep = c->eps, tgt_keep = c->eps_target;
+    c->alpha = alpha; c->stop = 0; c->err = 0; c->acc.err = 0;
+    c->eps = INFINITY; c->eps_target = -INFINITY;      // the stage call returns the raw quantile
+    {   // host-side select_setup (same arithmetic as ctrl.cuh)
+        unsigned long long n = c->n_alive;
+        double m = 1.0 - alpha, aleph = fma((double)n, alpha, m);
+        long long j = (long long)trunc(aleph);
+        if (j > (long long)n - 1) j = (long long)n - 1;
+        if (j < 1) j = 1;
+        double g = aleph - (double)j; g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+        c->sel_j = (unsigned long long)j; c->sel_rank = (unsigned long long)(j - 1); c->sel_prefix = 0; c->q_gamma = g;
+        c->acc.cnt_le = 0; c->acc.min_gt_key = ~0ull;
+    }
+    rc = push_ctrl(pop); if (rc) return rc;
+    TIME_BEGIN(pop);
+    int nl = launch_eps_quantile(pop->ctx->stream, pop->dev);
+    CU(cudaGetLastError());
+    TIME_END(pop, nl);
+    rc = pull_ctrl(pop); if (rc) return rc;
+    if (q) *q = c->q;
+    if (v_lo) *v_lo = c->q_a;
+    if (v_hi) *v_hi = c->q_b;
+    rc = check_dev_err(pop, "abcdez_pop_eps_quantile");
+    c->eps = eps_keep; c->eps_target = tgt_keep;
+    int rc2 = push_ctrl(pop); if (rc2) return rc2;
+    CU(cudaStreamSynchronize(pop->ctx->stream));
+    return rc;
+}
+
+extern "C" int abcdez_pop_reweight(abcdez_pop* pop, double eps_new, double* wnorm, double* ess, int64_t* n_alive)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_reweight: pop is NULL");
+    CHECK_ARG(eps_new >= 0.0, "Expected \xcf\xb5 \xe2\x89\xa5 0.0");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    Ctrl* c = pop->h_ctrl;
+    c->eps = eps_new; c->stop = 0; c->ess_min = -1.0;       // stage call: never triggers the resample flag
+    rc = push_ctrl(pop); if (rc) return rc;
+    TIME_BEGIN(pop);
+    int nl = launch_reweight(pop->ctx->stream, pop->dev);
+    nl += launch_compact(pop->ctx->stream, pop->dev);
+    CU(cudaGetLastError());
+    TIME_END(pop, nl);
+    rc = pull_ctrl(pop); if (rc) return rc;
+    c->eps_k = eps_new;                                     // src/abcdez_smc.jl:360
+    rc = push_ctrl(pop); if (rc) return rc;
+    CU(cudaStreamSynchronize(pop->ctx->stream));
+    if (wnorm) *wnorm = c->wnorm;
+    if (ess) *ess = c->ess;
+    if (n_alive) *n_alive = c->n_alive;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_resample(abcdez_pop* pop, const double* uniforms, uint32_t epoch, int mode, int32_t* inds_out)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_resample: pop is NULL");
+    CHECK_ARG(mode >= 0 && mode <= 2, "abcdez_pop_resample: mode must be 0, 1 or 2");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    Ctrl* c = pop->h_ctrl;
+    CHECK_ARG(c->n_alive >= 1, "abcdez_pop_resample: no alive particles");
+    int use_mode = mode;
+    if (mode == 0 && !abck_is_indicator(c->kind)) use_mode = 1;
+    size_t n = (size_t)pop->N;
+    const double* du = nullptr;
+    if (uniforms) {
+        rc = ensure_scratch(pop, n * 8); if (rc) return rc;
+        CU(cudaMemcpyAsync(pop->scratch, uniforms, n * 8, cudaMemcpyHostToDevice, pop->ctx->stream));
+        du = (const double*)pop->scratch;
+    }
+    c->stop = 0;
+    rc = push_ctrl(pop); if (rc) return rc;
+    TIME_BEGIN(pop);
+    int nl = launch_resample(pop->ctx->stream, pop->dev, pop->DS, pop->NB, du, epoch, use_mode, 1);
+    CU(cudaGetLastError());
+    TIME_END(pop, nl);
+    if (inds_out) CU(cudaMemcpyAsync(inds_out, pop->dev.inds, n * 4, cudaMemcpyDeviceToHost, pop->ctx->stream));
+    rc = pull_ctrl(pop); if (rc) return rc;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_wsample_stratified(abcdez_ctx* ctx, int64_t N, const double* weights, const double* uniforms,
+                                         int mode, int64_t* inds_out)
+{
+    CHECK_ARG(ctx && weights && uniforms && inds_out, "abcdez_wsample_stratified: NULL argument");
+    CHECK_ARG(N >= 1 && N < (int64_t)0x7fffffff, "abcdez_wsample_stratified: N out of range");
+    CHECK_ARG(mode >= 0 && mode <= 2, "abcdez_wsample_stratified: mode must be 0, 1 or 2");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = (size_t)N; unsigned nt = (unsigned)((N + TILE - 1) / TILE);
+    DevBuf dw, du, dc, dp, dt, di;
+    CU(dw.alloc(n * 8)); CU(du.alloc(n * 8)); CU(dc.alloc(n * 8)); CU(dp.alloc((size_t)nt * 8 + 64));
+    CU(dt.alloc(2 * sizeof(SeqTab))); CU(di.alloc(n * 8));
+    CU(cudaMemcpyAsync(dw.p, weights, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(du.p, uniforms, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // tabs[1] holds the strata edges; strat_indices_kernel reads &tabs[0] + 1 -> pass the base
+    launch_strat_indices(ctx->stream, N, dw.as<double>(), du.as<double>(), dc.as<double>(), dp.as<double>(),
+                         dt.as<SeqTab>(), mode == 2 ? 2 : 1, di.as<long long>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(inds_out, di.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_pop_bench_sweeps(abcdez_pop* pop, int sweeps, int64_t* nsims, int64_t* naccs, double* ms)
+{
+    CHECK_ARG(pop != nullptr && sweeps >= 1, "abcdez_pop_bench_sweeps: bad argument");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    Ctrl* c = pop->h_ctrl;
+    Ctrl keep = *c;
+    c->stop = 0; c->sweeps_done = 0; c->sweep_idx = 0; c->Kmcmc = 0x7fffffff; c->Kmcmc_min = INFINITY;
+    long long ns0 = c->nsims_total; unsigned long long na0 = c->naccs_iter;
+    rc = push_ctrl(pop); if (rc) return rc;
+    SweepInj inj; memset(&inj, 0, sizeof(inj));
+    TIME_BEGIN(pop);
+    for (int s = 0; s < sweeps; ++s) pop->ops->smc_sweep(pop->ctx->stream, pop->dev, pop->prior, pop->data, inj);
+    CU(cudaGetLastError());
+    TIME_END(pop, sweeps);
+    rc = pull_ctrl(pop); if (rc) return rc;
+    if (nsims) *nsims = c->nsims_total - ns0;
+    if (naccs) *naccs = (int64_t)(c->naccs_iter - na0);
+    if (ms) *ms = pop->last_ms;
+    // restore the schedule scalars but keep the evolved particle state (cur, epoch)
+    keep.cur = c->cur; keep.sweep_epoch = c->sweep_epoch; keep.nsims_total = c->nsims_total; keep.n_sweeps = c->n_sweeps;
+    keep.dmin = c->dmin; keep.dmax = c->dmax;
+    *c = keep;
+    rc = push_ctrl(pop); if (rc) return rc;
+    CU(cudaStreamSynchronize(pop->ctx->stream));
+    return check_dev_err(pop, "abcdez_pop_bench_sweeps");
+}
+
+// ---------------------------------------------------------------------------------------
+// abcdesmc!  (src/abcdez_smc.jl:215-394)
+// ---------------------------------------------------------------------------------------
+extern "C" void abcdez_smc_opts_default(abcdez_smc_opts* o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->nparticles = 100; o->alpha = 0.95; o->delta_ess = 0.5; o->nsims_max = 10000000; o->Kmcmc = 3;
+    o->Kmcmc_min = 1.0; o->kernel = ABCDEZ_INDICATOR_STRICT; o->facc_stop = 0.0; o->facc_min = 0.0;
+    o->facc_tune = 0.975; o->seed = 1; o->verboseout = 1; o->max_iters = 0; o->exact_scan = 0; o->profile = 0;
+    o->sync_every = 1;
+}
+
+extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                              const abcdez_smc_opts* o, abcdez_smc_result* res)
+{
+    CHECK_ARG(ctx && prior && model && o && res, "abcdez_smc_run: NULL argument");
+    // argument validation with the reference's messages, src/abcdez_smc.jl:223-235
+    CHECK_ARG(0.0 <= o->alpha && o->alpha < 1.0, "\xce\xb1 must be in 0 <= \xce\xb1 < 1");
+    CHECK_ARG(0.0 <= o->delta_ess && o->delta_ess <= 1.0, "\xce\xb4""ess must be in 0 <= \xce\xb4""ess <= 1");
+    CHECK_ARG(0.0 <= o->facc_stop && o->facc_stop <= 1.0, "facc_stop must be in 0 <= facc_stop <= 1");
+    CHECK_ARG(0.0 <= o->facc_min && o->facc_min <= 1.0, "facc_min must be in 0 <= facc_min <= 1");
+    CHECK_ARG(0.0 <= o->facc_tune && o->facc_tune <= 1.0, "facc_tune must be in 0 <= facc_tune <= 1");
+    CHECK_ARG(0.0 <= eps_target, "\xcf\xb5_target must be non-negative");
+    CHECK_ARG(1 <= o->Kmcmc, "Kmcmc must be at least 1");
+    CHECK_ARG(0.0 <= o->Kmcmc_min, "Kmcmc_min must be in 0 <= Kmcmc_min <= Inf");
+    CHECK_ARG(1 <= o->nsims_max, "nsims_max must be at least 1");
+    CHECK_ARG(o->kernel >= 0 && o->kernel <= 3, "unknown ABC kernel");
+    {
+        double mn = o->alpha < o->delta_ess ? o->alpha : o->delta_ess;
+        double nmin = ceil(3.0 * (double)prior->dev.d / mn);                 // :234
+        if (!((double)o->nparticles >= nmin)) {
+            char buf[96]; snprintf(buf, sizeof buf, "nparticles must be at least %.0f", nmin);
+            return fail(ABCDEZ_ERR_BAD_ARG, buf);
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    const int64_t N = o->nparticles;
+    int hist_cap = o->verboseout ? (res->hist_cap > 0 ? res->hist_cap : 0) : 0;
+    int dev_hist = hist_cap > 0 ? hist_cap : 1;
+    abcdez_pop* pop = nullptr;
+    int rc = pop_create_impl(ctx, prior, model, N, 0, dev_hist, &pop);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    Ctrl* c = pop->h_ctrl;
+    c->eps_target = eps_target; c->alpha = o->alpha; c->ess_min = (double)N * o->delta_ess;   // :259
+    c->nsims_max = o->nsims_max; c->Kmcmc = o->Kmcmc; c->Ki = o->Kmcmc; c->Kmcmc_min = o->Kmcmc_min;
+    c->kind = o->kernel; c->facc_stop = o->facc_stop; c->facc_min = o->facc_min; c->facc_tune = o->facc_tune;
+    c->seed = o->seed; c->max_iters = o->max_iters; c->hist_cap = hist_cap;
+    rc = push_ctrl(pop);
+    std::vector<cudaEvent_t> evs;
+    cudaEvent_t e_init0 = nullptr, e_loop0 = nullptr, e_loop1 = nullptr;
+    int64_t launches = 0;
+    int64_t host_iters = 0;
+    const int sync_every = o->sync_every > 0 ? o->sync_every : 1;
+    const int mode = abck_is_indicator(o->kernel) ? 0 : (o->exact_scan ? 2 : 1);
+    SweepInj noinj; memset(&noinj, 0, sizeof(noinj));
+#define RUN_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ABCDEZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); goto done; } } while (0)
+    if (rc) goto done;
+    RUN_CU(cudaEventCreate(&e_init0)); RUN_CU(cudaEventCreate(&e_loop0)); RUN_CU(cudaEventCreate(&e_loop1));
+    RUN_CU(cudaEventRecord(e_init0, st));
+    pop->ops->init(st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :242-252
+    launches += 1 + launch_begin_run(st, pop->dev);                          // :255-292
+    RUN_CU(cudaEventRecord(e_loop0, st));
+    for (;;) {                                                               // :295
+        host_iters++;
+        launches += launch_eps_quantile(st, pop->dev);                       // :301
+        launches += launch_reweight(st, pop->dev);                           // :305-324
+        launches += launch_compact(st, pop->dev);
+        launches += launch_resample(st, pop->dev, pop->DS, pop->NB, nullptr, (uint32_t)host_iters, mode, 0);   // :324-326
+        for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
+            if (o->profile) {
+                cudaEvent_t a, b; RUN_CU(cudaEventCreate(&a)); RUN_CU(cudaEventCreate(&b));
+                evs.push_back(a); evs.push_back(b);
+                RUN_CU(cudaEventRecord(a, st));
+                pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
+                RUN_CU(cudaEventRecord(b, st));
+            } else {
+                pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
+            }
+            launches++;
+        }
+        if (host_iters % sync_every == 0) {
+            RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+            RUN_CU(cudaStreamSynchronize(st));
+            if (c->stop || c->err || c->acc.err) break;
+        }
+        if (host_iters > 10000000) break;
+    }
+    RUN_CU(cudaEventRecord(e_loop1, st));
+    RUN_CU(cudaGetLastError());
+    RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    RUN_CU(cudaStreamSynchronize(st));
+    rc = check_dev_err(pop, "abcdez_smc_run");
+    if (rc == ABCDEZ_ERR_NO_ALIVE) rc = ABCDEZ_OK;       // a warning in the reference (:375); reported in status
+    if (rc) goto done;
+    {
+        float ms = 0.f;
+        RUN_CU(cudaEventElapsedTime(&ms, e_init0, e_loop0)); res->init_ms = ms;
+        RUN_CU(cudaEventElapsedTime(&ms, e_loop0, e_loop1)); res->total_ms = ms;
+        double sw = 0.0;
+        for (size_t i = 0; i + 1 < evs.size(); i += 2) { RUN_CU(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); sw += ms; }
+        res->sweep_ms = sw;
+    }
+    res->eps = c->eps; res->logZ = c->logZ; res->iters = c->iters; res->nsims = c->nsims_total;
+    res->status = c->status; res->n_resamples = c->n_resamples; res->n_sweeps = c->n_sweeps; res->n_launches = launches;
+    res->hist_len = hist_cap > 0 ? c->hist_len : 0;
+    // results, :382-393
+    if (res->P) {
+        rc = ensure_scratch(pop, (size_t)N * pop->D * 8); if (rc) goto done;
+        launch_push_rows(st, pop->dev, pop->prior, pop->D, (double*)pop->scratch);
+        RUN_CU(cudaMemcpyAsync(res->P, pop->scratch, (size_t)N * pop->D * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (res->Wns) RUN_CU(cudaMemcpyAsync(res->Wns, pop->dev.W, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    if (res->C) RUN_CU(cudaMemcpyAsync(res->C, pop->dev.delta[c->cur], (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    if (res->blobs && pop->NB) RUN_CU(cudaMemcpyAsync(res->blobs, pop->dev.blob[c->cur], (size_t)N * pop->NB * 8, cudaMemcpyDeviceToHost, st));
+    RUN_CU(cudaStreamSynchronize(st));
+    if (res->hist_len > 0) {
+        std::vector<double> h((size_t)res->hist_len * 8);
+        RUN_CU(cudaMemcpy(h.data(), pop->dev.hist, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < res->hist_len; ++i) {
+            const double* r = &h[(size_t)i * 8];
+            if (res->h_eps) res->h_eps[i] = r[0];
+            if (res->h_dmin) res->h_dmin[i] = r[1];
+            if (res->h_dmax) res->h_dmax[i] = r[2];
+            if (res->h_logZ) res->h_logZ[i] = r[3];
+            if (res->h_ess) res->h_ess[i] = r[4];
+            if (res->h_facc) res->h_facc[i] = r[5];
+            if (res->h_gamma0) res->h_gamma0[i] = r[6];
+            if (res->h_Kmcmc) res->h_Kmcmc[i] = (int32_t)r[7];
+        }
+    }
+done:
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    if (e_init0) cudaEventDestroy(e_init0);
+    if (e_loop0) cudaEventDestroy(e_loop0);
+    if (e_loop1) cudaEventDestroy(e_loop1);
+    abcdez_pop_destroy(pop);
+    return rc;
+#undef RUN_CU
+}
+
+// ---------------------------------------------------------------------------------------
+// abcdemc!  (src/abcdez_mc.jl:102-172)
+// ---------------------------------------------------------------------------------------
+extern "C" void abcdez_mc_opts_default(abcdez_mc_opts* o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->nparticles = 50; o->generations = 20; o->seed = 1;
+}
+
+extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                             const abcdez_mc_opts* o, abcdez_mc_result* res)
+{
+    CHECK_ARG(ctx && prior && model && o && res, "abcdez_mc_run: NULL argument");
+    CHECK_ARG(0.0 <= eps_target, "\xcf\xb5_target must be non-negative");      // src/abcdez_mc.jl:108
+    CHECK_ARG(5 <= o->nparticles, "nparticles must be at least 5");          // :109
+    CHECK_ARG(1 <= o->generations, "generations must be at least 1");        // :110
+    CU(cudaSetDevice(ctx->device));
+    const int64_t N = o->nparticles;
+    abcdez_pop* pop = nullptr;
+    int rc = pop_create_impl(ctx, prior, model, N, 0, 1, &pop);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    Ctrl* c = pop->h_ctrl;
+    c->seed = o->seed; c->eps_target = eps_target;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int64_t launches = 0;
+    SweepInj noinj; memset(&noinj, 0, sizeof(noinj));
+#define RUN_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ABCDEZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); goto done; } } while (0)
+    rc = push_ctrl(pop); if (rc) goto done;
+    rc = mc_prepare(pop); if (rc) goto done;
+    RUN_CU(cudaEventCreate(&e0)); RUN_CU(cudaEventCreate(&e1));
+    pop->ops->init(st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :117-125
+    launches++;
+    RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    RUN_CU(cudaStreamSynchronize(st));
+    rc = check_dev_err(pop, "abcdez_mc_run"); if (rc) goto done;
+    RUN_CU(cudaEventRecord(e0, st));
+    for (int it = 0; it < o->generations; ++it) {                            // :134
+        // extrema(delta) of the live generation come from the previous kernel's epilogue (:146)
+        double eps_pop = fmax(eps_target, c->dmin + 0.0 * (c->dmax - c->dmin));   // :147, alpha = 0 (:107)
+        if (c->dmax > eps_target)         // only particles above eps need the sorted order (:20-24)
+            launches += launch_mc_prepare(st, pop->dev.N, pop->dev.delta[c->cur], pop->sorted_delta, pop->order,
+                                          pop->sort_tmp, pop->sort_tmp_bytes);
+        McArgs mc{ eps_pop, eps_target, pop->sorted_delta, pop->order };
+        pop->ops->mc_sweep(st, pop->dev, pop->prior, pop->data, noinj, mc);   // :149
+        launches++;
+        RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        RUN_CU(cudaStreamSynchronize(st));
+        if (c->err || c->acc.err) break;
+    }
+    RUN_CU(cudaEventRecord(e1, st));
+    RUN_CU(cudaGetLastError());
+    RUN_CU(cudaStreamSynchronize(st));
+    rc = check_dev_err(pop, "abcdez_mc_run"); if (rc) goto done;
+    { float ms = 0.f; RUN_CU(cudaEventElapsedTime(&ms, e0, e1)); res->total_ms = ms; res->sweep_ms = ms; }
+    res->reached_eps = (c->dmax <= eps_target) ? 1 : 0;                      // :163
+    res->nsims = c->nsims_total; res->dmin = c->dmin; res->dmax = c->dmax; res->n_launches = launches;
+    if (res->P) {
+        rc = ensure_scratch(pop, (size_t)N * pop->D * 8); if (rc) goto done;
+        launch_push_rows(st, pop->dev, pop->prior, pop->D, (double*)pop->scratch);   // :166
+        RUN_CU(cudaMemcpyAsync(res->P, pop->scratch, (size_t)N * pop->D * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (res->C) RUN_CU(cudaMemcpyAsync(res->C, pop->dev.delta[c->cur], (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    if (res->blobs && pop->NB) RUN_CU(cudaMemcpyAsync(res->blobs, pop->dev.blob[c->cur], (size_t)N * pop->NB * 8, cudaMemcpyDeviceToHost, st));
+    RUN_CU(cudaStreamSynchronize(st));
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    abcdez_pop_destroy(pop);
+    return rc;
+#undef RUN_CU
+}

@@ -1,0 +1,762 @@
+// bookkeeping.cu -- the SMC bookkeeping of abcdesmc! (src/abcdez_smc.jl:301-326,357-376) as
+// HBM-streaming sm_100a kernels:
+//   eps schedule   quantile(delta[alive], alpha)   :301      radix select on order-preserving keys
+//   reweighting    abcdesmc_update_ws! + :305-315  :59-83    two fused passes (unnormalised, normalise)
+//   ESS / logZ     get_ess :8, :315,:323                     deterministic two-level reductions
+//   alive list     (replaces the O(N) wsample scans :121,125) tile scan + compaction
+//   resampling     wsample_stratified! :15-56, abcdesmc_resample! :85-104
+// All schedule decisions are taken on the device by the last CTA of the kernel that
+// produces their inputs ("last block done" tickets), so one SMC iteration is a fixed list of
+// launches with no host round trip; skipped stages read their flag and return.
+#include "internal.h"
+#include "seqsum.cuh"
+#include "ctrl.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace abcdez {
+
+static inline unsigned tiles_for(int64_t N) { return (unsigned)((N + TILE - 1) / TILE); }
+
+__global__ void end_iter_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop) return;
+    ctrl_end_iter(P, c);
+}
+
+// pre-loop state, src/abcdez_smc.jl:255-292
+__global__ void begin_run_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    double N = (double)P.N;
+    double w = 1.0 / N;
+    push_hist(P, c, c->eps, 1.0 / (N * (w * w)), c->facc, c->Kmcmc);
+    select_setup(c);
+}
+
+// ---------------------------------------------------------------------------------------
+// radix select of v[j] among the alive distances: 11-bit digits, MSB first
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4_f64(const double* __restrict__ p, size_t i0, uint32_t N, double v[4])
+{
+    if (i0 + 3 < N) {
+        double2 a = *reinterpret_cast<const double2*>(p + i0), b = *reinterpret_cast<const double2*>(p + i0 + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < N) ? p[i0 + k] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void store4_f64(double* __restrict__ p, size_t i0, uint32_t N, const double v[4])
+{
+    if (i0 + 3 < N) {
+        *reinterpret_cast<double2*>(p + i0) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(p + i0 + 2) = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i0 + k < N) p[i0 + k] = v[k];
+    }
+}
+
+__device__ __forceinline__ uint32_t load4_u8(const uint8_t* __restrict__ p, size_t i0, uint32_t N)
+{
+    if (i0 + 3 < N) return *reinterpret_cast<const uint32_t*>(p + i0);
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i0 + k < N) r |= (uint32_t)p[i0 + k] << (8 * k);
+    return r;
+}
+
+// pick the bin holding rank sel_rank; all BK_THREADS threads of the calling CTA participate
+__device__ void select_pick(const PopDev& P, Ctrl* c, int shift, int nbins, bool final_pass)
+{
+    __shared__ unsigned s_part[BK_THREADS];
+    __shared__ unsigned s_found_bin, s_found_before;
+    const int per = SEL_BINS / BK_THREADS;     // 8 bins per thread
+    unsigned loc[per], tot = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+        int b = threadIdx.x * per + k;
+        loc[k] = (b < nbins) ? __ldcg(&P.sel_hist[b]) : 0u;
+        tot += loc[k];
+    }
+    s_part[threadIdx.x] = tot;
+    if (threadIdx.x == 0) { s_found_bin = 0xffffffffu; s_found_before = 0; }
+    __syncthreads();
+    // exclusive prefix over the 256 partials (short serial loop per thread is fine: 256 adds)
+    unsigned before = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) before += s_part[t];
+    unsigned long long rank = c->sel_rank;
+    unsigned cum = before;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+        if (loc[k] && rank >= cum && rank < (unsigned long long)cum + loc[k]) {
+            s_found_bin = threadIdx.x * per + k; s_found_before = cum;
+        }
+        cum += loc[k];
+    }
+    __syncthreads();
+    // clear the histogram for the next pass
+#pragma unroll
+    for (int k = 0; k < per; ++k) P.sel_hist[threadIdx.x * per + k] = 0u;
+    if (threadIdx.x == 0) {
+        if (s_found_bin == 0xffffffffu) {
+            if (!c->err) c->err = ABCDEZ_ERR_NO_ALIVE;      // empty alive set
+        } else {
+            c->sel_prefix |= ((unsigned long long)s_found_bin) << shift;
+            c->sel_rank = rank - s_found_before;
+            if (final_pass) c->q_a = key_f64(c->sel_prefix);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+select_hist_kernel(PopDev P, int shift, int nbins, unsigned long long himask, int first, int final_pass)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop) return;
+    __shared__ unsigned sh[SEL_BINS];
+    for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = c->sel_prefix;
+    const double* __restrict__ dl = P.delta[c->cur];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double v[4];
+    load4_f64(dl, i0, P.N, v);
+    uint32_t al = load4_u8(P.alive, i0, P.N);
+    int nan_seen = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        bool ok = (al >> (8 * k)) & 0xff;
+        unsigned long long key = f64_key(v[k]);
+        if (ok && first && isnan(v[k])) nan_seen = 1;
+        ok = ok && ((key & himask) == prefix);
+        unsigned digit = ok ? (unsigned)((key >> shift) & (unsigned long long)(nbins - 1)) : 0xffffffffu;
+        // warp-aggregated shared-memory atomics: the leading digits of distances are highly
+        // concentrated, a plain atomicAdd would serialise 32-way
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[digit], (unsigned)__popc(peers));
+    }
+    if (nan_seen) atomicMax(&c->acc.err, (int)ABCDEZ_ERR_NAN_DISTANCE);
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+        unsigned cnt = sh[b];
+        if (cnt) atomicAdd(&P.sel_hist[b], cnt);
+    }
+    if (last_block(&c->acc.ticket[1], gridDim.x)) select_pick(P, c, shift, nbins, final_pass != 0);
+}
+
+// v[j+1]: count of keys <= v[j] and the smallest key above it; then the type-7 interpolation
+// and the clamp eps = max(min(q, eps), eps_target)  (src/abcdez_smc.jl:301)
+__global__ void __launch_bounds__(BK_THREADS) select_next_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop) return;
+    const unsigned long long akey = c->sel_prefix;
+    const double* __restrict__ dl = P.delta[c->cur];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double v[4];
+    load4_f64(dl, i0, P.N, v);
+    uint32_t al = load4_u8(P.alive, i0, P.N);
+    unsigned cnt = 0; unsigned long long mn = ~0ull;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        bool ok = (al >> (8 * k)) & 0xff;
+        unsigned long long key = f64_key(v[k]);
+        if (ok) { if (key <= akey) cnt++; else mn = key < mn ? key : mn; }
+    }
+    __shared__ unsigned s_cnt[32]; __shared__ unsigned long long s_mn[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    cnt = warp_sum_u(cnt); mn = warp_min_u64(mn);
+    if (lane == 0) { s_cnt[w] = cnt; s_mn[w] = mn; }
+    __syncthreads();
+    if (w == 0) {
+        cnt = lane < nw ? s_cnt[lane] : 0u; mn = lane < nw ? s_mn[lane] : ~0ull;
+        cnt = warp_sum_u(cnt); mn = warp_min_u64(mn);
+        if (lane == 0) {
+            if (cnt) atomicAdd(&c->acc.cnt_le, (unsigned long long)cnt);
+            if (mn != ~0ull) atomicMin(&c->acc.min_gt_key, mn);
+        }
+    }
+    if (last_block(&c->acc.ticket[1], gridDim.x)) {
+        if (threadIdx.x == 0) {
+            double a = c->q_a, b;
+            if (c->n_alive <= 1 || __ldcg(&c->acc.cnt_le) >= c->sel_j + 1) b = a;
+            else b = key_f64(__ldcg(&c->acc.min_gt_key));
+            c->q_b = b;
+            double g = c->q_gamma;
+            double q = (isfinite(a) && isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
+            c->q = q;
+            c->eps = fmax(fmin(q, c->eps), c->eps_target);                   // :301
+        }
+    }
+}
+
+int launch_eps_quantile(cudaStream_t st, const PopDev& P)
+{
+    unsigned g = tiles_for(P.N);
+    // 64-bit keys: digits at shifts 53,42,31,20,9 (11 bits) and 0 (9 bits)
+    const int shifts[6] = { 53, 42, 31, 20, 9, 0 };
+    for (int p = 0; p < 6; ++p) {
+        int nbins = (p == 5) ? 512 : 2048;
+        unsigned long long himask = (p == 0) ? 0ull : (~0ull << (shifts[p - 1]));
+        select_hist_kernel<<<g, BK_THREADS, 0, st>>>(P, shifts[p], nbins, himask, p == 0, p == 5);
+    }
+    select_next_kernel<<<g, BK_THREADS, 0, st>>>(P);
+    return 7;
+}
+
+// ---------------------------------------------------------------------------------------
+// reweighting, src/abcdez_smc.jl:59-83 and :305-326
+// ---------------------------------------------------------------------------------------
+// pass A: ws (alive only), wprod = Wns .* ws kept unnormalised in W; wnorm = sum(wprod); logZ += log(wnorm)
+__global__ void __launch_bounds__(BK_THREADS) reweight_a_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop) return;
+    __shared__ double s_red[32];
+    const double eps_new = c->eps, eps_old = c->eps_k;
+    const int kind = c->kind;
+    const double* __restrict__ dl = P.delta[c->cur];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double v[4], w[4];
+    load4_f64(dl, i0, P.N, v);
+    load4_f64(P.W, i0, P.N, w);
+    uint32_t al = load4_u8(P.alive, i0, P.N);
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        bool ok = ((al >> (8 * k)) & 0xff) && (i0 + k < P.N);
+        double ws = 0.0;
+        if (ok) ws = exp(abck_logpdf(kind, eps_new, v[k]) - abck_logpdf(kind, eps_old, v[k]));   // :75
+        w[k] = ok ? w[k] * ws : 0.0;                                                              // :308
+        acc += w[k];
+    }
+    store4_f64(P.W, i0, P.N, w);
+    double t = block_sum(acc, s_red);
+    if (threadIdx.x == 0) P.partial[blockIdx.x] = t;
+    if (last_block(&c->acc.ticket[2], gridDim.x)) {
+        double a = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) a += __ldcg(&P.partial[b]);
+        a = block_sum(a, s_red);
+        if (threadIdx.x == 0) {
+            c->wnorm = a;                                                   // :309
+            c->logZ += log(a);                                              // :315
+        }
+    }
+}
+
+// reweight pass B + the decisions of :318-324.  Builds the sequential-sum tables for the
+// closed-form resampling when it will be needed.
+__device__ void ctrl_after_reweight(const PopDev& P, Ctrl* c, double sumsq, unsigned n_alive)
+{
+    c->n_alive = n_alive;
+    c->ess = 1.0 / sumsq;                                                   // :8,:323
+    c->naccs_iter = 0ull; c->Ki = c->Kmcmc;                                 // :318-319
+    c->sweep_idx = 0; c->sweeps_done = 0;
+    if (c->facc < c->facc_min) c->gamma0 *= c->facc_tune;                   // :320
+    c->do_resample = (c->ess < c->ess_min) ? 1 : 0;                         // :324
+    if (c->do_resample && abck_is_indicator(c->kind)) {
+        seqtab_build(&P.tabs[0], __ldcg(&c->acc.w_alive), (unsigned long long)n_alive);
+        seqtab_build(&P.tabs[1], 1.0 / (double)P.N, (unsigned long long)P.N);
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS) reweight_b_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop) return;
+    __shared__ double s_red[32];
+    __shared__ unsigned s_cnt[32];
+    const double wnorm = c->wnorm;
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double w[4];
+    load4_f64(P.W, i0, P.N, w);
+    double acc = 0.0; unsigned cnt = 0; uint32_t al = 0; double wal = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < P.N) {
+            w[k] = w[k] / wnorm;                                            // :310
+            bool a = (w[k] > 0.0);                                          // :311
+            if (a) { al |= 1u << (8 * k); cnt++; wal = w[k]; }
+            acc += w[k] * w[k];
+        }
+    }
+    store4_f64(P.W, i0, P.N, w);
+    if (i0 + 3 < P.N) *reinterpret_cast<uint32_t*>(P.alive + i0) = al;
+    else { for (int k = 0; k < 4; ++k) if (i0 + k < P.N) P.alive[i0 + k] = (al >> (8 * k)) & 0xff; }
+    if (cnt) c->acc.w_alive = wal;     // indicator kernels: every alive weight is this same double
+    double t = block_sum(acc, s_red);
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    cnt = warp_sum_u(cnt);
+    if (lane == 0) s_cnt[wp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tc = 0;
+        for (int q = 0; q < nw; ++q) tc += s_cnt[q];
+        P.partial[blockIdx.x] = t;
+        P.tile_cnt[blockIdx.x] = tc;
+    }
+    if (last_block(&c->acc.ticket[2], gridDim.x)) {
+        double a = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) a += __ldcg(&P.partial[b]);
+        a = block_sum(a, s_red);
+        // exclusive scan of the tile counts -> tile offsets (chunked: each thread owns a contiguous chunk)
+        __shared__ unsigned s_chunk[BK_THREADS];
+        unsigned nt = gridDim.x, per = (nt + blockDim.x - 1) / blockDim.x;
+        unsigned lo = threadIdx.x * per, hi = lo + per < nt ? lo + per : nt, sum = 0;
+        for (unsigned b = lo; b < hi; ++b) sum += __ldcg(&P.tile_cnt[b]);
+        s_chunk[threadIdx.x] = sum;
+        __syncthreads();
+        unsigned off = 0;
+        for (int q = 0; q < (int)threadIdx.x; ++q) off += s_chunk[q];
+        for (unsigned b = lo; b < hi; ++b) { unsigned tcnt = __ldcg(&P.tile_cnt[b]); P.tile_cnt[b] = off; off += tcnt; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_cnt[0] = off;   // total alive (last chunk's end)
+        __syncthreads();
+        if (threadIdx.x == 0) ctrl_after_reweight(P, c, a, s_cnt[0]);
+    }
+}
+
+int launch_reweight(cudaStream_t st, const PopDev& P)
+{
+    unsigned g = tiles_for(P.N);
+    reweight_a_kernel<<<g, BK_THREADS, 0, st>>>(P);
+    reweight_b_kernel<<<g, BK_THREADS, 0, st>>>(P);
+    return 2;
+}
+
+// ---------------------------------------------------------------------------------------
+// compaction of the alive flags into alive_list (the O(1) replacement of wsample's scans)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS) compact_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || c->n_alive == P.N) return;       // identity list is implicit
+    __shared__ unsigned s_w[32];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    uint32_t al = load4_u8(P.alive, i0, P.N);
+    unsigned cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt += ((al >> (8 * k)) & 0xff) ? 1u : 0u;
+    // block exclusive scan of cnt
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int q = 0; q < w; ++q) woff += s_w[q];
+    (void)nw;
+    unsigned pos = P.tile_cnt[blockIdx.x] + woff + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if ((al >> (8 * k)) & 0xff) P.alive_list[pos++] = (uint32_t)(i0 + k);
+}
+
+int launch_compact(cudaStream_t st, const PopDev& P)
+{
+    compact_kernel<<<tiles_for(P.N), BK_THREADS, 0, st>>>(P);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// stratified resampling, src/abcdez_smc.jl:15-56 and :85-104
+// ---------------------------------------------------------------------------------------
+__device__ void ctrl_after_resample(const PopDev& P, Ctrl* c)
+{
+    double N = (double)P.N, w = 1.0 / N;
+    c->cur ^= 1;                     // the gathered generation is the live one
+    c->n_alive = P.N;                // :102-103
+    c->ess = 1.0 / (N * (w * w));    // get_ess(Wns) after the reset, :326
+    c->n_resamples += 1;
+}
+
+// stratum draw r_si = rand(Uniform(unif0, unif1)) = unif0 + (unif1 - unif0) * u   (:46-47)
+__device__ __forceinline__ double stratum_draw(const SeqTab* edges, double sval, uint32_t si, double u)
+{
+    double unif0 = seqtab_value(edges, si);         // running sum of sval, si steps (:46,:52)
+    double unif1 = unif0 + sval;
+    return unif0 + (unif1 - unif0) * u;
+}
+
+__device__ __forceinline__ void gather_particle(const PopDev& P, int cur, int DS, int NB, uint32_t dst, uint32_t src)
+{
+    const double* s = P.theta[cur] + (size_t)src * DS;
+    double* d = P.theta[cur ^ 1] + (size_t)dst * DS;
+    if (DS & 1) { for (int k = 0; k < DS; ++k) d[k] = s[k]; }
+    else { for (int k = 0; k < DS; k += 2) *reinterpret_cast<double2*>(d + k) = *reinterpret_cast<const double2*>(s + k); }
+    P.logpi[cur ^ 1][dst] = P.logpi[cur][src];
+    P.delta[cur ^ 1][dst] = P.delta[cur][src];
+    for (int k = 0; k < NB; ++k) P.blob[cur ^ 1][(size_t)dst * NB + k] = P.blob[cur][(size_t)src * NB + k];
+}
+
+// closed-form path (indicator kernels): no scan at all
+__global__ void __launch_bounds__(BK_THREADS)
+resample_uniform_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj_u, uint32_t epoch, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ SeqTab s_w;        // weights table (the edges table is read through L1/L2)
+    {   // cooperative copy of the small table into shared memory
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.tabs[0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_w);
+        for (unsigned q = threadIdx.x; q < sizeof(SeqTab) / 4; q += blockDim.x) dst[q] = src[q];
+    }
+    __syncthreads();
+    const int cur = c->cur;
+    const uint32_t N = P.N, n_alive = c->n_alive;
+    const double sval = 1.0 / (double)N;                                     // :34
+    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si < N) {
+        double u, u2;
+        if (inj_u) u = inj_u[si];
+        else { Stream rs(c->seed, P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }
+        double r = stratum_draw(&P.tabs[1], sval, si, u);
+        unsigned long long k = seqtab_first_ge(&s_w, r);                     // :48-51 in closed form
+        uint32_t src;
+        if (k == 0) src = 0u;                                                // r == 0: the reference leaves i = 0
+        else {
+            if (k > n_alive) k = n_alive;
+            src = (n_alive == N) ? (uint32_t)(k - 1) : P.alive_list[k - 1];
+        }
+        gather_particle(P, cur, DS, NB, si, src);                            // :96-99
+        P.inds[si] = (int32_t)src;
+    }
+    __syncthreads();
+    if (si < N) { P.W[si] = sval; P.alive[si] = 1; }                         // :102-103
+    if (last_block(&c->acc.ticket[3], gridDim.x)) {
+        if (threadIdx.x == 0) ctrl_after_resample(P, c);
+    }
+}
+
+// general weights (Epanechnikov kernels): inclusive scan of W, then a search per stratum.
+// mode 1: parallel three-phase scan (tile sums, tile offsets, tile rescan) -- rounds differently
+// from the reference's sequential sum, documented in DESIGN.md; mode 2: sequential scan, exact.
+__global__ void __launch_bounds__(BK_THREADS) scan_tile_sums_kernel(const double* __restrict__ W, uint32_t N, double* partial)
+{
+    __shared__ double s_red[32];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double w[4];
+    load4_f64(W, i0, N, w);
+    double acc = ((w[0] + w[1]) + w[2]) + w[3];
+    double t = block_sum(acc, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+__global__ void scan_tile_offsets_kernel(double* partial, unsigned ntiles)
+{
+    // single thread: sequential exclusive scan of the tile sums (ntiles <= ~10^5)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (unsigned b = 0; b < ntiles; ++b) { double t = partial[b]; partial[b] = s; s += t; }
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+scan_apply_kernel(const double* __restrict__ W, uint32_t N, const double* __restrict__ partial, double* __restrict__ cumsum)
+{
+    __shared__ double s_w[32];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double w[4];
+    load4_f64(W, i0, N, w);
+    w[1] += w[0]; w[2] += w[1]; w[3] += w[2];
+    double incl = w[3];
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[wp] = incl;
+    __syncthreads();
+    double off = partial[blockIdx.x];
+    for (int q = 0; q < wp; ++q) off += s_w[q];
+    off += incl - w[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] += off;
+    store4_f64(cumsum, i0, N, w);
+}
+
+// exact mode: the reference's sequential FP64 cumsum (:50), staged through shared memory so
+// that the one adding thread never waits on HBM
+__global__ void __launch_bounds__(BK_THREADS) scan_sequential_kernel(const double* __restrict__ W, uint32_t N, double* __restrict__ cumsum)
+{
+    __shared__ double buf[2048];
+    double s = 0.0;
+    for (size_t base = 0; base < N; base += 2048) {
+        for (int q = threadIdx.x; q < 2048; q += blockDim.x) buf[q] = (base + q < N) ? W[base + q] : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int lim = (N - base) < 2048 ? (int)(N - base) : 2048;
+            for (int q = 0; q < lim; ++q) { s = __dadd_rn(s, buf[q]); buf[q] = s; }
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < 2048; q += blockDim.x) if (base + q < N) cumsum[base + q] = buf[q];
+        __syncthreads();
+    }
+}
+
+// first index (0-based) with cumsum[i] >= r; r <= 0 -> 0 ("i = 0" quirk, clamped); r > total -> N-1
+__device__ __forceinline__ uint32_t search_cumsum(const double* __restrict__ cs, uint32_t N, double r)
+{
+    if (!(r > 0.0)) return 0u;
+    uint32_t lo = 0, hi = N;      // find first i with cs[i] >= r
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (cs[m] < r) lo = m + 1; else hi = m; }
+    return lo >= N ? N - 1 : lo;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+resample_general_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj_u, uint32_t epoch, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    const int cur = c->cur;
+    const uint32_t N = P.N;
+    const double sval = 1.0 / (double)N;
+    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si < N) {
+        double u, u2;
+        if (inj_u) u = inj_u[si];
+        else { Stream rs(c->seed, P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }
+        double r = stratum_draw(&P.tabs[1], sval, si, u);
+        uint32_t src = search_cumsum(P.cumsum, N, r);
+        gather_particle(P, cur, DS, NB, si, src);
+        P.inds[si] = (int32_t)src;
+    }
+    __syncthreads();
+    if (si < N) { P.W[si] = sval; P.alive[si] = 1; }
+    if (last_block(&c->acc.ticket[3], gridDim.x)) {
+        if (threadIdx.x == 0) ctrl_after_resample(P, c);
+    }
+}
+
+// wrappers that respect the device-side do_resample flag for the scan kernels
+__global__ void __launch_bounds__(BK_THREADS) scan_tile_sums_pop_kernel(PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ double s_red[32];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double w[4];
+    load4_f64(P.W, i0, P.N, w);
+    double acc = ((w[0] + w[1]) + w[2]) + w[3];
+    double t = block_sum(acc, s_red);
+    if (threadIdx.x == 0) P.partial[blockIdx.x] = t;
+}
+
+__global__ void scan_tile_offsets_pop_kernel(PopDev P, int force, int build_edges)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (unsigned b = 0; b < P.ntiles; ++b) { double t = P.partial[b]; P.partial[b] = s; s += t; }
+        if (build_edges) seqtab_build(&P.tabs[1], 1.0 / (double)P.N, (unsigned long long)P.N);
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS) scan_apply_pop_kernel(PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ double s_w[32];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    double w[4];
+    load4_f64(P.W, i0, P.N, w);
+    w[1] += w[0]; w[2] += w[1]; w[3] += w[2];
+    double incl = w[3];
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[wp] = incl;
+    __syncthreads();
+    double off = P.partial[blockIdx.x];
+    for (int q = 0; q < wp; ++q) off += s_w[q];
+    off += incl - w[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] += off;
+    store4_f64(P.cumsum, i0, P.N, w);
+}
+
+__global__ void __launch_bounds__(BK_THREADS) scan_sequential_pop_kernel(PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ double buf[2048];
+    const uint32_t N = P.N;
+    double s = 0.0;
+    for (size_t base = 0; base < N; base += 2048) {
+        for (int q = threadIdx.x; q < 2048; q += blockDim.x) buf[q] = (base + q < N) ? P.W[base + q] : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int lim = (N - base) < 2048 ? (int)(N - base) : 2048;
+            for (int q = 0; q < lim; ++q) { s = __dadd_rn(s, buf[q]); buf[q] = s; }
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < 2048; q += blockDim.x) if (base + q < N) P.cumsum[base + q] = buf[q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seqtab_build(&P.tabs[1], 1.0 / (double)P.N, (unsigned long long)P.N);
+}
+
+// host-forced table build for the stage-level resample call (force=1 bypasses reweight)
+__global__ void build_tabs_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    seqtab_build(&P.tabs[0], __ldcg(&c->acc.w_alive), (unsigned long long)c->n_alive);
+    seqtab_build(&P.tabs[1], 1.0 / (double)P.N, (unsigned long long)P.N);
+}
+
+// mode: 0 auto, 1 parallel scan, 2 sequential scan.  kind_is_indicator decided on the host
+// from the control block mirror (the kernel type never changes during a run).
+int launch_resample(cudaStream_t st, const PopDev& P, int DS, int NB, const double* inj_u, uint32_t epoch,
+                    int mode, int force)
+{
+    unsigned gt = tiles_for(P.N), gp = (unsigned)((P.N + BK_THREADS - 1) / BK_THREADS);
+    if (mode == 0) {
+        if (force) build_tabs_kernel<<<1, 1, 0, st>>>(P);
+        resample_uniform_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, inj_u, epoch, force);
+        return force ? 2 : 1;
+    }
+    if (mode == 2) {
+        scan_sequential_pop_kernel<<<1, BK_THREADS, 0, st>>>(P, force);
+        resample_general_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, inj_u, epoch, force);
+        return 2;
+    }
+    scan_tile_sums_pop_kernel<<<gt, BK_THREADS, 0, st>>>(P, force);
+    scan_tile_offsets_pop_kernel<<<1, 32, 0, st>>>(P, force, 1);
+    scan_apply_pop_kernel<<<gt, BK_THREADS, 0, st>>>(P, force);
+    resample_general_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, inj_u, epoch, force);
+    return 4;
+}
+
+// wsample_stratified!(rng, weights, inds) on caller-supplied weights (test/runtests.jl:13-19)
+__global__ void __launch_bounds__(BK_THREADS)
+strat_indices_kernel(uint32_t N, const double* __restrict__ cumsum, const double* __restrict__ u,
+                     const SeqTab* __restrict__ edges, long long* __restrict__ inds)
+{
+    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= N) return;
+    double r = stratum_draw(edges, 1.0 / (double)N, si, u[si]);
+    inds[si] = (long long)search_cumsum(cumsum, N, r) + 1;     // 1-based like the reference
+}
+
+__global__ void build_edges_kernel(SeqTab* tabs, uint32_t N)
+{
+    seqtab_build(&tabs[1], 1.0 / (double)N, (unsigned long long)N);
+}
+
+int launch_strat_indices(cudaStream_t st, int64_t N, const double* W, const double* u, double* cumsum,
+                         double* partial, SeqTab* tabs, int mode, long long* inds)
+{
+    unsigned gt = tiles_for(N), gp = (unsigned)((N + BK_THREADS - 1) / BK_THREADS);
+    int n = 0;
+    build_edges_kernel<<<1, 1, 0, st>>>(tabs, (uint32_t)N); n++;
+    if (mode == 2) { scan_sequential_kernel<<<1, BK_THREADS, 0, st>>>(W, (uint32_t)N, cumsum); n++; }
+    else {
+        scan_tile_sums_kernel<<<gt, BK_THREADS, 0, st>>>(W, (uint32_t)N, partial);
+        scan_tile_offsets_kernel<<<1, 32, 0, st>>>(partial, gt);
+        scan_apply_kernel<<<gt, BK_THREADS, 0, st>>>(W, (uint32_t)N, partial, cumsum);
+        n += 3;
+    }
+    strat_indices_kernel<<<gp, BK_THREADS, 0, st>>>((uint32_t)N, cumsum, u, &tabs[1], inds); n++;
+    return n;
+}
+
+int launch_end_iter(cudaStream_t st, const PopDev& P) { end_iter_kernel<<<1, 1, 0, st>>>(P); return 1; }
+int launch_begin_run(cudaStream_t st, const PopDev& P) { begin_run_kernel<<<1, 1, 0, st>>>(P); return 1; }
+
+// ---------------------------------------------------------------------------------------
+// extrema(delta) over the live generation (abcdemc!, src/abcdez_mc.jl:146; stage calls)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS) minmax_kernel(PopDev P)
+{
+    Ctrl* c = P.ctrl;
+    const double* __restrict__ dl = P.delta[c->cur];
+    size_t i0 = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * 4;
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (int k = 0; k < 4; ++k) if (i0 + k < P.N) { unsigned long long key = f64_key(dl[i0 + k]); mn = key < mn ? key : mn; mx = key > mx ? key : mx; }
+    mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&c->acc.dmin_key, mn); atomicMax(&c->acc.dmax_key, mx); }
+    if (last_block(&c->acc.ticket[4], gridDim.x)) {
+        if (threadIdx.x == 0) {
+            c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
+            c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
+        }
+    }
+}
+
+int launch_minmax(cudaStream_t st, const PopDev& P)
+{
+    minmax_kernel<<<tiles_for(P.N), BK_THREADS, 0, st>>>(P);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// layout conversion and result assembly (push_p on every particle, src/abcdez_smc.jl:382)
+// ---------------------------------------------------------------------------------------
+__global__ void pack_rows_kernel(int D, int DS, int64_t N, const double* __restrict__ src, double* __restrict__ dst, int to_rows)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * D) return;
+    int64_t i = e / D; int k = (int)(e - i * D);
+    if (to_rows) dst[i * DS + k] = src[e]; else dst[e] = src[i * DS + k];
+}
+
+int launch_pack_rows(cudaStream_t st, int D, int64_t N, const double* dense, double* rows, int to_rows)
+{
+    int DS = row_stride(D);
+    int64_t n = N * D;
+    unsigned g = (unsigned)((n + 255) / 256);
+    if (to_rows) pack_rows_kernel<<<g, 256, 0, st>>>(D, DS, N, dense, rows, 1);
+    else pack_rows_kernel<<<g, 256, 0, st>>>(D, DS, N, rows, const_cast<double*>(dense), 0);
+    return 1;
+}
+
+__global__ void push_rows_kernel(PopDev P, PriorDev pr, int D, int DS, double* __restrict__ out)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)P.N * D) return;
+    int64_t i = e / D; int k = (int)(e - i * D);
+    double v = P.theta[P.ctrl->cur][i * DS + k];
+    out[e] = fam_is_discrete(pr.family[k]) ? rint(v) : v;
+}
+
+int launch_push_rows(cudaStream_t st, const PopDev& P, const PriorDev& pr, int D, double* out_dense)
+{
+    int64_t n = (int64_t)P.N * D;
+    push_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, pr, D, row_stride(D), out_dense);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// abcdemc!: (delta, index)-sorted order for the "better-or-equal particle" draw
+// (src/abcdez_mc.jl:23).  Library radix sort (CUB) -- plumbing, not a hot kernel: one sort per
+// generation and only while some particle is still above eps_target.
+// ---------------------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t* p, uint32_t N)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) p[i] = i;
+}
+
+size_t mc_sort_tmp_bytes(int64_t N)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const double*)nullptr, (double*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
+    return bytes + (size_t)N * sizeof(uint32_t);    // + iota input
+}
+
+int launch_mc_prepare(cudaStream_t st, uint32_t N, const double* delta_live, double* sorted_delta, uint32_t* order,
+                      void* tmp, size_t tmp_bytes)
+{
+    uint32_t* iota = reinterpret_cast<uint32_t*>(tmp);
+    void* cub_tmp = reinterpret_cast<char*>(tmp) + (size_t)N * sizeof(uint32_t);
+    size_t cub_bytes = tmp_bytes - (size_t)N * sizeof(uint32_t);
+    iota_kernel<<<(N + 255) / 256, 256, 0, st>>>(iota, N);
+    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, delta_live, sorted_delta,
+                                    (const uint32_t*)iota, order, (int)N, 0, 64, st);
+    return 3;
+}
+
+}  // namespace abcdez

@@ -1,0 +1,6 @@
+// inst_lv.cu -- instantiates the fused sweep kernels (sweep.cuh) for a group of registered models.
+#include "sweep.cuh"
+
+namespace abcdez {
+ABCDEZ_DEFINE_MODEL(ops_lotka_volterra, LotkaVolterra)
+}  // namespace abcdez

@@ -1,0 +1,134 @@
+// internal.h -- host-side objects behind the opaque handles of include/abcdez_cuda.h and the
+// launcher interface between api.cu, sweep.cu and bookkeeping.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "common.cuh"
+#include "models.cuh"
+
+namespace abcdez {
+
+constexpr int TILE = 1024;            // particles per CTA in the bookkeeping kernels (256 thr x 4)
+constexpr int BK_THREADS = 256;
+constexpr int SWEEP_THREADS = 256;    // thread-per-particle sweeps
+constexpr int SEL_BINS = 2048;        // 11-bit radix-select digits
+constexpr int SEQTAB_MAX = 256;       // segments of the sequential-sum closed form
+
+// closed form of the reference's sequential FP64 running sums (src/abcdez_smc.jl:46,50) for a
+// constant addend: S(0)=0, S(k)=fl(S(k-1)+c).  S(kst[j] + m) = sst[j] + m*inc[j] exactly.
+struct SeqTab {
+    int n;
+    unsigned long long kst[SEQTAB_MAX];
+    double sst[SEQTAB_MAX];
+    double inc[SEQTAB_MAX];
+    unsigned long long kmax;      // largest valid k
+};
+
+// device pointers of one population, passed to kernels by value
+struct PopDev {
+    double* theta[2];
+    double* logpi[2];
+    double* delta[2];
+    double* blob[2];              // N x (BLOB/8) doubles
+    double* W;
+    uint8_t* alive;
+    uint32_t* alive_list;         // compacted indices of alive particles (valid when n_alive < N)
+    Ctrl* ctrl;
+    double* partial;              // per-CTA reduction partials (2 x nblocks)
+    uint32_t* tile_cnt;           // per-tile alive counts -> exclusive offsets
+    uint32_t* sel_hist;           // SEL_BINS radix-select histogram
+    double* cumsum;               // N inclusive cumulative weights (general-weight resampling)
+    int32_t* inds;                // N resampling indices (0-based)
+    double* hist;                 // hist_cap x 8 history records
+    SeqTab* tabs;                 // [0]: weights, [1]: strata edges
+    uint32_t N;
+    uint32_t id0;
+    uint32_t ntiles;
+};
+
+struct SweepInj {
+    const int32_t* a; const int32_t* b; const int32_t* s;
+    const double* z; const double* u;
+    uint8_t* flags;
+};
+
+struct McArgs {
+    double eps_pop, eps_target;
+    const double* sorted_delta;   // delta sorted ascending
+    const uint32_t* order;        // particle index per sorted position
+};
+
+// per-model launchers (sweep.cu)
+struct ModelOps {
+    const char* name;
+    int d, blob;
+    void (*init)(cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, uint64_t seed, int draw_prior);
+    void (*smc_sweep)(cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, const SweepInj&);
+    void (*mc_sweep)(cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, const SweepInj&, const McArgs&);
+    void (*simulate)(cudaStream_t, const PriorDev*, const ModelData&, int64_t N, const double* theta_pushed,
+                     uint64_t seed, uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs);
+};
+const ModelOps* model_ops(int id);
+int model_count();
+
+// dimension-only launchers for the prior stage calls (sweep.cu)
+void launch_prior_op(cudaStream_t, int d, const PriorDev&, int64_t N, int op, const double* in, double* out,
+                     uint64_t seed, uint32_t epoch, uint32_t id0);
+enum { PRIOR_OP_SAMPLE = 0, PRIOR_OP_LOGPDF = 1, PRIOR_OP_PUSH = 2 };
+
+// bookkeeping launchers (bookkeeping.cu); each returns the number of kernel launches it issued
+int launch_eps_quantile(cudaStream_t, const PopDev&);                 // -> ctrl.q_a, q_b, q, eps (clamped)
+int launch_reweight(cudaStream_t, const PopDev&);                     // -> W, alive, wnorm, logZ, ess, flags
+int launch_compact(cudaStream_t, const PopDev&);                      // -> alive_list
+int launch_resample(cudaStream_t, const PopDev&, int D, int NB, const double* inj_u, uint32_t epoch,
+                    int mode, int force);
+int launch_end_iter(cudaStream_t, const PopDev&);
+int launch_begin_run(cudaStream_t, const PopDev&);
+int launch_minmax(cudaStream_t, const PopDev&);
+int launch_strat_indices(cudaStream_t, int64_t N, const double* W_dev, const double* u_dev, double* cumsum_dev,
+                         double* partial_dev, SeqTab* tabs_dev, int mode, long long* inds_dev);
+int launch_push_rows(cudaStream_t, const PopDev&, const PriorDev&, int D, double* out_dense);
+int launch_pack_rows(cudaStream_t, int D, int64_t N, const double* dense, double* rows, int to_rows);
+int launch_mc_prepare(cudaStream_t, uint32_t N, const double* delta_live, double* sorted_delta, uint32_t* order,
+                      void* tmp, size_t tmp_bytes);
+size_t mc_sort_tmp_bytes(int64_t N);
+
+}  // namespace abcdez
+
+struct abcdez_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int rank, world;
+    void* nccl_comm;
+    int sm_count;
+};
+
+struct abcdez_prior {
+    abcdez::PriorDev dev;
+};
+
+struct abcdez_model {
+    int id;
+    const abcdez::ModelOps* ops;
+    abcdez::ModelData data;
+};
+
+struct abcdez_pop {
+    abcdez_ctx* ctx;
+    abcdez::PriorDev prior;
+    const abcdez::ModelOps* ops;
+    abcdez::ModelData data;
+    abcdez::PopDev dev;
+    abcdez::Ctrl* h_ctrl;         // pinned mirror
+    int64_t N;
+    int D, DS, NB;
+    int hist_cap;
+    // scratch for injected arrays / flags
+    void* scratch; size_t scratch_bytes;
+    // abcdemc! sort buffers
+    double* sorted_delta; uint32_t* order; void* sort_tmp; size_t sort_tmp_bytes;
+    cudaEvent_t ev0, ev1;
+    double last_ms; int64_t last_launches;
+};

@@ -1,0 +1,221 @@
+// models.cuh -- the dist!(theta, ve) -> (d, blob) plugins as registered CUDA device functors.
+//
+// In the reference `dist!` is an arbitrary Julia closure (src/abcdez_smc.jl:215, contract in
+// docs/src/index.md:288-324).  Here a model is a struct with compile-time D (= length(prior)),
+// BLOB (bytes carried with the particle, multiple of 8) and a static
+//     __device__ double run(const double* theta /*push_p-ed*/, const double* data, SimRng&, double* blob)
+// instantiated into the fused sweep kernels (sweep.cuh).  `ve` (per-thread scratch,
+// src/abcdez_smc.jl:111) is the thread's registers.  Normative model definitions: DESIGN.md
+// "Models"; the CPU oracle restates them independently.
+#pragma once
+#include "common.cuh"
+
+namespace abcdez {
+
+struct ModelData { double v[ABCDEZ_MAXDATA]; };
+
+// examples/minimal_example.jl:17-24, test/runtests.jl:138: y ~ N(theta, sigma), d = |y - data|
+struct Gauss1D {
+    static constexpr int D = 1, BLOB = 0;
+    static constexpr const char* name = "gauss1d";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        return fabs(th[0] + data[1] * r.n() - data[0]);
+    }
+};
+
+// same simulator, the simulated y is carried as the particle's blob (docs/src/index.md:298-324)
+struct Gauss1DBlob {
+    static constexpr int D = 1, BLOB = 8;
+    static constexpr const char* name = "gauss1d_blob";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double* blob)
+    {
+        double y = th[0] + data[1] * r.n();
+        blob[0] = y;
+        return fabs(y - data[0]);
+    }
+};
+
+// config 2: y ~ N(theta, Sigma), Sigma_ij = rho^|i-j| (stationary AR(1) noise), d = ||y - y_obs||_2
+struct GaussCorr10 {
+    static constexpr int D = 10, BLOB = 0;
+    static constexpr const char* name = "gauss_corr10";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0, z[10];
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) r.n2(z[k], z[k + 1]);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            e = (k == 0) ? z[0] : rho * e + sr * z[k];
+            double dy = th[k] + e - data[k];
+            acc += dy * dy;
+        }
+        return sqrt(acc);
+    }
+};
+
+// test/runtests.jl:496-497
+struct Dirac {
+    static constexpr int D = 1, BLOB = 0;
+    static constexpr const char* name = "dirac";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng&, double*)
+    {
+        return fabs(th[0] * th[0] + 1.0 - data[0]);
+    }
+};
+
+// test/runtests.jl:524-525
+struct NormDU {
+    static constexpr int D = 2, BLOB = 0;
+    static constexpr const char* name = "normdu";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        return fabs((th[0] * th[0] + th[1]) * (th[0] + r.n() * 0.01) - data[0]);
+    }
+};
+
+// test/runtests.jl:603 (dist1!) and :614 (dist2!, returns Inf with probability 1/2)
+template <bool WITH_INF>
+struct TwoD {
+    static constexpr int D = 2, BLOB = 0;
+    static constexpr const char* name = WITH_INF ? "twod_inf" : "twod";
+    __device__ static __forceinline__ double run(const double* th, const double*, SimRng& r, double*)
+    {
+        double z1, z2;
+        r.n2(z1, z2);
+        double t1 = th[0] + z1 * 0.01 - th[1] * th[1];
+        double t2 = th[1] - 1.0 + z2 * 0.01;
+        double v = 50.0 * (t1 * t1) + t2 * t2;
+        if (WITH_INF) { double u1, u2; r.u2(u1, u2); if (!(u1 < 0.5)) v = INFINITY; }
+        return v;
+    }
+};
+
+// test/runtests.jl:582-583
+struct Mixture {
+    static constexpr int D = 1, BLOB = 0;
+    static constexpr const char* name = "mixture";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        double z1, z2, u1, u2;
+        r.n2(z1, z2);
+        r.u2(u1, u2);
+        double noise = (u1 < 0.5) ? z1 * 0.1 : z2;
+        return fabs(th[0] + noise - data[0]);
+    }
+};
+
+// test/runtests.jl:537-549: 31-point drifted-Wiener RMS summary, mean absolute difference
+struct Wiener {
+    static constexpr int D = 2, BLOB = 0;
+    static constexpr const char* name = "wiener";
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        // one scalar noise factor per simulation: the reference's `@.(...) .* (0.95 + 0.1 * rand())`
+        double acc = 0.0, f = 0.95 + 0.1 * r.u();
+        for (int t = 0; t <= 30; ++t) {
+            double tt = (double)t;
+            double v = sqrt(th[0] * th[0] * tt * tt + th[1] * th[1] * tt) * f;
+            acc += fabs(v - data[t]);
+        }
+        return acc / 31.0;
+    }
+};
+
+// config 4: Lotka-Volterra, fixed-step RK4 (see DESIGN.md for the data layout)
+struct LotkaVolterra {
+    static constexpr int D = 4, BLOB = 0;
+    static constexpr const char* name = "lotka_volterra";
+    __device__ static __forceinline__ void rhs(const double* th, double x, double y, double& dx, double& dy)
+    {
+        dx = th[0] * x - th[1] * x * y;
+        dy = th[2] * x * y - th[3] * y;
+    }
+    __device__ static double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        double x = data[0], y = data[1], dt = data[2];
+        int sub = (int)data[3], nobs = (int)data[4];
+        double sig = data[5], acc = 0.0;
+        for (int j = 0; j < nobs; ++j) {
+            for (int s = 0; s < sub; ++s) {
+                double k1x, k1y, k2x, k2y, k3x, k3y, k4x, k4y;
+                rhs(th, x, y, k1x, k1y);
+                rhs(th, x + 0.5 * dt * k1x, y + 0.5 * dt * k1y, k2x, k2y);
+                rhs(th, x + 0.5 * dt * k2x, y + 0.5 * dt * k2y, k3x, k3y);
+                rhs(th, x + dt * k3x, y + dt * k3y, k4x, k4y);
+                x = x + dt / 6.0 * (k1x + 2.0 * k2x + 2.0 * k3x + k4x);
+                y = y + dt / 6.0 * (k1y + 2.0 * k2y + 2.0 * k3y + k4y);
+            }
+            double z1, z2;
+            r.n2(z1, z2);
+            double rx = x + sig * z1 - data[6 + 2 * j];
+            double ry = y + sig * z2 - data[7 + 2 * j];
+            acc += rx * rx + ry * ry;
+        }
+        return sqrt(acc / (2.0 * nobs));
+    }
+};
+
+// config 5: linear birth-death process, Gillespie SSA (divergent trajectory lengths)
+struct BirthDeath {
+    static constexpr int D = 2, BLOB = 16;
+    static constexpr const char* name = "birth_death";
+    __device__ static double run(const double* th, const double* data, SimRng& r, double* blob)
+    {
+        double n = data[0];
+        int nobs = (int)data[1];
+        double dt = data[2], maxev = data[3];
+        double t = 0.0, acc = 0.0, events = 0.0;
+        double lam_mu = th[0] + th[1];
+        for (int j = 0; j < nobs; ++j) {
+            double tobs = dt * (double)(j + 1);
+            while (n > 0.0 && events < maxev) {
+                double rate = lam_mu * n, u1, u2;
+                r.u2(u1, u2);
+                double tn = t + (-log(1.0 - u1)) / rate;
+                if (tn > tobs) break;
+                t = tn;
+                n += (u2 * lam_mu < th[0]) ? 1.0 : -1.0;
+                events += 1.0;
+            }
+            t = tobs;
+            double dn = n - data[4 + j];
+            acc += dn * dn;
+        }
+        blob[0] = n; blob[1] = events;
+        return sqrt(acc / (double)nobs);
+    }
+};
+
+// test/runtests.jl:427-437 (socks): sequential picks without replacement
+struct Socks {
+    static constexpr int D = 2, BLOB = 0;
+    static constexpr const char* name = "socks";
+    __device__ static double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        double n_socks = th[0], prop = th[1];
+        double n_pairs = rint(prop * floor(n_socks / 2.0));
+        double n_odd = n_socks - 2.0 * n_pairs;
+        double n_pick = n_socks < 11.0 ? n_socks : 11.0;
+        double p2 = n_pairs, p1 = 0.0, o = n_odd, got_pairs = 0.0;
+        for (int t = 0; t < (int)n_pick; ++t) {
+            double tot = 2.0 * p2 + p1 + o;
+            double u = r.u() * tot;
+            if (u < 2.0 * p2) { p2 -= 1.0; p1 += 1.0; }
+            else if (u < 2.0 * p2 + p1) { p1 -= 1.0; got_pairs += 1.0; }
+            else { o -= 1.0; }
+        }
+        double sample_odds = n_pick - 2.0 * got_pairs;
+        return fabs(got_pairs - data[0]) + fabs(sample_odds - data[1]);
+    }
+};
+
+// model ids: keep in sync with MODEL_TABLE in registry.cu (and, independently, the oracle)
+enum {
+    M_GAUSS1D = 0, M_GAUSS1D_BLOB = 1, M_GAUSS_CORR10 = 2, M_DIRAC = 3, M_NORMDU = 4, M_TWOD = 5,
+    M_TWOD_INF = 6, M_MIXTURE = 7, M_WIENER = 8, M_LOTKA_VOLTERRA = 9, M_BIRTH_DEATH = 10, M_GK = 11,
+    M_SOCKS = 12, M_COUNT = 13
+};
+
+}  // namespace abcdez

@@ -527,18 +527,14 @@ static double simulate(int model, const double* th, const double* data, simrng_t
         double noise = (u1 < 0.5) ? z1 * 0.1 : z2;
         return fabs(th[0] + noise - data[0]);
     }
-    case M_WIENER: {          /* test/runtests.jl:537-549; data[0..30] = tdata */
-        double acc = 0.0;
-        for (int t = 0; t <= 30; t += 2) {
-            sim_u2(r, &u1, &u2);
+    case M_WIENER: {          /* test/runtests.jl:537-549; data[0..30] = tdata.  The reference's
+                               * `@.(sqrt(...)) .* (0.95 + 0.1 * rand())` draws ONE scalar factor per
+                               * simulation (the @. does not reach the rand()). */
+        double acc = 0.0, f = 0.95 + 0.1 * sim_u(r);
+        for (int t = 0; t <= 30; ++t) {
             double tt = (double)t;
-            double v = sqrt(th[0] * th[0] * tt * tt + th[1] * th[1] * tt) * (0.95 + 0.1 * u1);
+            double v = sqrt(th[0] * th[0] * tt * tt + th[1] * th[1] * tt) * f;
             acc += fabs(v - data[t]);
-            if (t + 1 <= 30) {
-                tt = (double)(t + 1);
-                v = sqrt(th[0] * th[0] * tt * tt + th[1] * th[1] * tt) * (0.95 + 0.1 * u2);
-                acc += fabs(v - data[t + 1]);
-            }
         }
         return acc / 31.0;
     }

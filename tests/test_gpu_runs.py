@@ -1,0 +1,237 @@
+"""GPU end-to-end tests of abcdesmc! / abcdemc! through the C ABI.
+
+Tier 1: same Philox seed -> the GPU run follows the oracle's run decision by decision
+(identical iteration count, simulation count, resampling events, Kmcmc history; eps / logZ /
+ESS histories within 1e-9).  Tier 2: the reference's own statistical tests
+(test/runtests.jl:110-624) with the reference's tolerances.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import MODEL_CASES, to_prior
+
+pytestmark = pytest.mark.gpu
+
+SQ10 = math.sqrt(10)
+
+
+def isaround(x, val, f=1.0):
+    """test/runtests.jl:9"""
+    x = np.asarray(x, dtype=float)
+    return x.mean() - f * x.std(ddof=1) <= val <= x.mean() + f * x.std(ddof=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# tier 1: decision-level parity of whole runs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,eps_target,N,kw", [
+    ("gauss1d", 0.3, 1000, {}),
+    ("gauss1d", 0.3, 3001, dict(kernel="indicator")),
+    ("gauss1d", 0.3, 2000, dict(kernel="epa", exact_scan=True)),
+    ("gauss1d_blob", 0.3, 1500, dict(Kmcmc=5, Kmcmc_min=2.0)),
+    ("gauss1d", 0.05, 2000, dict(nsims_max=20000)),
+    ("gauss1d", 0.3, 2000, dict(facc_min=0.3, facc_tune=0.9, alpha=0.8, delta_ess=0.3)),
+    ("gauss_corr10", 2.5, 4000, {}),
+    ("twod_inf", 0.05, 1000, {}),
+    ("normdu", 0.05, 500, {}),
+    ("lotka_volterra", 0.3, 1200, dict(nsims_max=40000)),
+])
+def test_smc_run_follows_oracle(A, oracle, gpu_ctx, name, eps_target, N, kw):
+    spec, data = MODEL_CASES[name]
+    kind = kw.pop("kernel", "indicator_strict")
+    exact = kw.pop("exact_scan", False)
+    okw = dict(nparticles=N, seed=4242, kind=kind, **kw)
+    want = oracle.smc_run(spec, name, data, eps_target, **okw)
+    gkw = {k: v for k, v in kw.items()}
+    got = A.abcdesmc(to_prior(A, spec), A.Model(name, data), eps_target, None, nparticles=N, rng=4242, ABCk=kind,
+                     exact_scan=exact, verbose=False, **gkw)
+    assert (got.iters, got.nsims, got.status) == (want.iters, want.nsims, want.status)
+    assert np.array_equal(got.Kmcmcs, want.hist["Kmcmc"])
+    np.testing.assert_allclose(got.eps_hist, want.hist["eps"], rtol=1e-9)
+    np.testing.assert_allclose(got.logZs, want.hist["logZ"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got.esss, want.hist["ess"], rtol=1e-9)
+    np.testing.assert_allclose(got.faccs, want.hist["facc"], rtol=1e-12)
+    np.testing.assert_allclose(got.gamma0s, want.hist["gamma0"], rtol=1e-15)
+    np.testing.assert_allclose(got.ranges_eps[:, 0], want.hist["dmin"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got.ranges_eps[:, 1], want.hist["dmax"], rtol=1e-9, atol=1e-12)
+    assert math.isclose(got.logZ, want.logZ, rel_tol=1e-9) and math.isclose(got.eps, want.eps, rel_tol=1e-9)
+    assert np.array_equal(got.Wns > 0, want.Wns > 0)
+    np.testing.assert_allclose(got.Wns, want.Wns, rtol=1e-9)
+    np.testing.assert_allclose(got.P, want.P, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got.C, want.C, rtol=1e-9, atol=1e-10)
+    if want.blobs.shape[1]:
+        np.testing.assert_allclose(got.blobs.view(np.float64), want.blobs.view(np.float64), rtol=1e-9, atol=1e-10)
+    if want.iters > 30:
+        assert got.stats["n_resamples"] >= 1
+
+
+@pytest.mark.parametrize("name,eps_target,N,gens", [("gauss1d", 0.3, 1000, 60), ("twod", 0.05, 500, 80), ("dirac", 0.1, 50, 20)])
+def test_mc_run_follows_oracle(A, oracle, gpu_ctx, name, eps_target, N, gens):
+    spec, data = MODEL_CASES[name]
+    want = oracle.mc_run(spec, name, data, eps_target, nparticles=N, generations=gens, seed=777)
+    got = A.abcdemc(to_prior(A, spec), A.Model(name, data), eps_target, None, nparticles=N, generations=gens, rng=777, verbose=False)
+    assert (got.nsims, got.reached_eps) == (want.nsims, want.reached_eps)
+    np.testing.assert_allclose(got.P, want.P, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got.C, want.C, rtol=1e-9, atol=1e-10)
+
+
+def test_sync_every_does_not_change_results(A, gpu_ctx):
+    """Running ahead of the host (several iterations enqueued per stop-flag poll) is invisible."""
+    spec, data = MODEL_CASES["gauss1d"]
+    r1 = A.abcdesmc(to_prior(A, spec), A.Model("gauss1d", data), 0.3, None, nparticles=2000, rng=5, verbose=False)
+    r2 = A.abcdesmc(to_prior(A, spec), A.Model("gauss1d", data), 0.3, None, nparticles=2000, rng=5, verbose=False, sync_every=8)
+    assert r1.iters == r2.iters and r1.logZ == r2.logZ and np.array_equal(r1.P, r2.P) and np.array_equal(r1.Wns, r2.Wns)
+
+
+def test_run_is_deterministic(A, gpu_ctx):
+    spec, data = MODEL_CASES["gauss_corr10"]
+    rs = [A.abcdesmc(to_prior(A, spec), A.Model("gauss_corr10", data), 2.0, None, nparticles=20000, rng=9, verbose=False) for _ in range(2)]
+    assert rs[0].logZ == rs[1].logZ and np.array_equal(rs[0].P, rs[1].P) and np.array_equal(rs[0].esss, rs[1].esss)
+
+
+# ---------------------------------------------------------------------------------------------
+# argument validation, src/abcdez_smc.jl:223-235, src/abcdez_mc.jl:108-110
+# ---------------------------------------------------------------------------------------------
+def test_argument_errors(A, gpu_ctx):
+    pr, m = A.host.Normal(0, SQ10), A.Model("gauss1d", [3.0, 1.0])
+    bad = [(dict(alpha=1.0), "α must be in 0 <= α < 1"), (dict(delta_ess=1.5), "δess must be in"),
+           (dict(facc_stop=-0.1), "facc_stop must be"), (dict(facc_min=2.0), "facc_min must be"),
+           (dict(facc_tune=1.5), "facc_tune must be"), (dict(Kmcmc=0), "Kmcmc must be at least 1"),
+           (dict(Kmcmc_min=-1.0), "Kmcmc_min must be"), (dict(nsims_max=0), "nsims_max must be at least 1"),
+           (dict(nparticles=5), "nparticles must be at least 6")]
+    for kw, msg in bad:
+        with pytest.raises(A.ABCdeZError, match=msg):
+            A.abcdesmc(pr, m, 0.3, None, verbose=False, **kw)
+    with pytest.raises(A.ABCdeZError, match="ϵ_target must be non-negative"):
+        A.abcdesmc(pr, m, -0.3, None, verbose=False)
+    with pytest.raises(A.ABCdeZError, match="nparticles must be at least 5"):
+        A.abcdemc(pr, m, 0.3, None, nparticles=4, verbose=False)
+    with pytest.raises(A.ABCdeZError, match="generations must be at least 1"):
+        A.abcdemc(pr, m, 0.3, None, generations=0, verbose=False)
+    # Greek keyword spellings of the reference
+    r = A.abcdesmc(pr, m, 0.3, None, nparticles=200, α=0.9, δess=0.4, rng=1, verbose=False)
+    assert r.ϵ == 0.3 and r.P.shape == (200,)
+
+
+# ---------------------------------------------------------------------------------------------
+# tier 2: the reference's statistical tests (independent Philox streams)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("xdata,Z,tol", [(3.0, 0.047940112540007955, 0.10), (7.0, 0.007781668367620676, 0.20)])
+def test_1d_normal_evidence(A, gpu_ctx, xdata, Z, tol):
+    """test/runtests.jl:110-218: abcdesmc! and abcdemc!, N = 5000."""
+    pr, m = A.host.Normal(0, SQ10), A.Model("gauss1d", [xdata, 1.0])
+    r = A.abcdesmc(pr, m, 0.3, None, nparticles=5000, verbose=False, rng=1001)
+    assert Z * (1 - tol) <= math.exp(r.logZ) <= Z * (1 + tol)
+    assert isaround(r.P[r.Wns > 0], 10 / 11 * xdata)
+    rmc = A.abcdemc(pr, m, 0.3, None, nparticles=5000, generations=500, verbose=False, rng=1002)
+    assert isaround(rmc.P, 10 / 11 * xdata)
+    assert rmc.reached_eps
+
+
+def test_evidence_tight_at_large_N(A, gpu_ctx):
+    """What the GPU buys: N = 10^6 brings the evidence estimate within 1 % of the analytic value."""
+    r = A.abcdesmc(A.host.Normal(0, SQ10), A.Model("gauss1d", [3.0, 1.0]), 0.3, None, nparticles=1_000_000,
+                   nsims_max=10**10, verbose=False, rng=31337)
+    assert abs(math.exp(r.logZ) / 0.047940112540007955 - 1.0) < 0.01
+    x = r.P[r.Wns > 0]
+    assert abs(x.mean() - 30 / 11) < 0.01 and abs(x.var() - 10 / 11) < 0.05
+
+
+def test_bayes_factor_uniform_priors(A, gpu_ctx):
+    """test/runtests.jl:220-266."""
+    m = A.Model("gauss1d", [3.0, 1.0])
+    r1 = A.abcdesmc(A.host.Uniform(-10, 10), m, 0.3, None, nparticles=5000, verbose=False, rng=11)
+    r2 = A.abcdesmc(A.host.Uniform(-20, 20), m, 0.3, None, nparticles=5000, verbose=False, rng=12)
+    Z1, Z2 = math.exp(r1.logZ), math.exp(r2.logZ)
+    assert 0.02998511 * 0.8 <= Z1 <= 0.02998511 * 1.2 and 0.01500489 * 0.8 <= Z2 <= 0.01500489 * 1.2
+    assert 1.6 <= Z1 / Z2 <= 2.4
+    assert isaround(r1.P[r1.Wns > 0], 3.0) and isaround(r2.P[r2.Wns > 0], 3.0)
+
+
+@pytest.mark.parametrize("kind,Z", [("indicator", 0.047940112540007955), ("epa", 0.03196007502667197),
+                                    ("epa_strict", 0.03196007502667197)])
+def test_kernel_variants(A, gpu_ctx, kind, Z):
+    """test/runtests.jl:268-423 incl. `weightinds` through the library's wsample_stratified."""
+    r = A.abcdesmc(A.host.Normal(0, SQ10), A.Model("gauss1d", [3.0, 1.0]), 0.3, None, ABCk=kind, nparticles=5000,
+                   verbose=False, rng=21)
+    assert Z * 0.9 <= math.exp(r.logZ) <= Z * 1.1
+    if kind == "indicator":
+        x = r.P[r.Wns > 0]
+    else:
+        assert math.isclose(r.Wns.sum(), 1.0, rel_tol=1e-9)
+        inds = A.wsample_stratified(r.Wns, np.random.default_rng(1).random(5000)) - 1
+        x = r.P[inds]
+    assert isaround(x, 10 / 11 * 3.0)
+
+
+def test_socks(A, gpu_ctx):
+    """test/runtests.jl:425-491."""
+    size = -30.0 ** 2 / (30.0 - 15.0 ** 2)
+    pr = A.Factored(A.host.NegativeBinomial(size, size / (30.0 + size)), A.host.Beta(15, 2))
+    m = A.Model("socks", [0.0, 11.0])
+    r = A.abcdesmc(pr, m, 0.01, None, nparticles=5000, verbose=False, rng=31)
+    al = r.Wns > 0
+    assert isaround(r.P[al, 0], 46.2) and isaround(r.P[al, 1], 0.866)
+    assert np.all(r.P[:, 0] == np.rint(r.P[:, 0]))
+    rmc = A.abcdemc(pr, m, 0.01, None, nparticles=5000, generations=500, verbose=False, rng=32)
+    assert isaround(rmc.P[:, 0], 46.2) and isaround(rmc.P[:, 1], 0.866)
+
+
+def test_dirac_normdu_wiener_mixture_2d(A, gpu_ctx):
+    """test/runtests.jl:493-624 (default nparticles where the reference uses defaults)."""
+    pr, m = A.host.Normal(1, 0.2), A.Model("dirac", [1.5])
+    assert isaround(A.abcdemc(pr, m, 0.1, None, verbose=False, rng=41).P, 0.707)
+    r = A.abcdesmc(pr, m, 0.1, None, verbose=False, rng=42)
+    assert isaround(r.P[r.Wns > 0], 0.707)
+
+    pr = A.Factored(A.host.Normal(1, 0.5), A.host.DiscreteUniform(1, 10)); m = A.Model("normdu", [5.5])
+    rm = A.abcdemc(pr, m, 0.01, None, nparticles=100, generations=1000, verbose=False, rng=43).P
+    assert isaround(rm[:, 0], 1) and isaround(rm[:, 1], 5)
+    r = A.abcdesmc(pr, m, 0.01, None, nparticles=100, verbose=False, rng=44)
+    al = r.Wns > 0
+    assert isaround(r.P[al, 0], 1) and isaround(r.P[al, 1], 5)
+
+    t = np.arange(31.0); tdata = np.sqrt(0.25 * t * t + 4.0 * t) * 1.003
+    pr = A.Factored(A.host.Uniform(0, 1), A.host.Uniform(0, 4)); m = A.Model("wiener", tdata)
+    rm = A.abcdemc(pr, m, 0.05, None, nparticles=1000, generations=300, verbose=False, rng=45).P
+    assert isaround(rm[:, 0], 0.5, 2.0) and isaround(rm[:, 1], 2.0, 2.0)
+    r = A.abcdesmc(pr, m, 0.05, None, nparticles=1000, verbose=False, rng=46)
+    al = r.Wns > 0
+    assert isaround(r.P[al, 0], 0.5, 2.0) and isaround(r.P[al, 1], 2.0, 2.0)
+
+    st_n = np.array([0.0, 0.04680825481526908, 0.1057221226763449, 0.2682111969397526, 0.8309228020477986])
+    def stv(x):
+        qs = np.quantile(x, np.arange(0.1, 0.95, 0.1)); return ((qs - qs[::-1]) / 2)[4:]
+    pr, m = A.host.Uniform(-10, 10), A.Model("mixture", [0.0])
+    rm = A.abcdemc(pr, m, 0.01, None, nparticles=2000, generations=1000, verbose=False, rng=47).P
+    r = A.abcdesmc(pr, m, 0.01, None, nparticles=2000, verbose=False, rng=48)
+    assert np.mean(np.abs(stv(rm) - st_n)) < 0.1 and np.mean(np.abs(stv(r.P[r.Wns > 0]) - st_n)) < 0.1
+
+    pr = A.Factored(A.host.Normal(0, 5), A.host.Normal(0, 5))
+    for name in ("twod", "twod_inf"):
+        m = A.Model(name, [])
+        rm = A.abcdemc(pr, m, 0.01, None, nparticles=500, generations=500, verbose=False, rng=49).P
+        assert isaround(rm[:, 0], 1) and isaround(rm[:, 1], 1)
+        r = A.abcdesmc(pr, m, 0.01, None, nparticles=500, verbose=False, rng=50)
+        al = r.Wns > 0
+        assert isaround(r.P[al, 0], 1) and isaround(r.P[al, 1], 1)
+
+
+def test_minimal_example_model_probabilities(A, gpu_ctx):
+    """examples/minimal_example.jl (config 1): two models differing in the prior, N = 1000 in the
+    reference; here averaged over 8 seeds to make the 0.678 / 0.322 check sharp."""
+    m = A.Model("gauss1d", [3.0, 1.0])
+    Z1 = np.mean([math.exp(A.abcdesmc(A.host.Normal(0, SQ10), m, 0.3, None, nparticles=1000, verbose=False, rng=s).logZ) for s in range(8)])
+    Z2 = np.mean([math.exp(A.abcdesmc(A.host.Normal(0, 10.0), m, 0.3, None, nparticles=1000, verbose=False, rng=100 + s).logZ) for s in range(8)])
+    assert abs(Z1 / 0.047940 - 1) < 0.1 and abs(Z2 / 0.022780 - 1) < 0.12
+    assert abs(Z1 / (Z1 + Z2) - 0.678) < 0.04
+
+
+def test_blobs_travel_with_particles(A, gpu_ctx):
+    """docs/src/index.md:298-324: the blob returned with a particle is the simulation that produced its distance."""
+    r = A.abcdesmc(A.host.Normal(0, SQ10), A.Model("gauss1d_blob", [3.0, 1.0]), 0.3, None, nparticles=3000, verbose=False, rng=77)
+    y = r.blobs.view(np.float64)[:, 0]
+    np.testing.assert_allclose(np.abs(y - 3.0), r.C, rtol=1e-12, atol=1e-12)
+    assert np.all(r.C[r.Wns > 0] < 0.3)
