@@ -173,7 +173,7 @@ struct BirthDeath {
             while (n > 0.0 && events < maxev) {
                 double rate = lam_mu * n, u1, u2;
                 r.u2(u1, u2);
-                double tn = t + (-log(1.0 - u1)) / rate;
+                double tn = t + (-plog(1.0 - u1)) / rate;
                 if (tn > tobs) break;
                 t = tn;
                 n += (u2 * lam_mu < th[0]) ? 1.0 : -1.0;

@@ -233,7 +233,7 @@ smc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj)
                     if (!acc) {                                            // :145, uniform only when w < 0
                         double u, u2;
                         if (inj.u) u = inj.u[i]; else ms.u2(1u, u, u2);
-                        acc = (log(u) < w);
+                        acc = (plog(u) < w);
                     }
                     if (acc) {                                             // :146-150
                         dli = dp; lpi = lp;
@@ -342,7 +342,7 @@ mc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj, McArgs mc)
             double w_prior = lp - lpi;                                     // :42 (logpi[i], not [s])
             double u, u2;
             if (inj.u) u = inj.u[i]; else ms.u2(1u, u, u2);                // :43, always drawn
-            if (!(log(u) > fmin(0.0, w_prior))) {
+            if (!(plog(u) > fmin(0.0, w_prior))) {
                 nsim = 1; flag |= ABCDEZ_FLAG_SIM;                         // :44
                 SimRng r(seed, pid, epoch, TAG_MODEL);
                 double blp[NB > 0 ? NB : 1];

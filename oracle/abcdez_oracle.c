@@ -82,6 +82,140 @@ void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
     philox4x32_10(ctr, key, out);
 }
 
+/* ------------------------------------------------------------------ */
+/* Portable math contract (DESIGN.md "Numerics"): log, exp, lgamma and  */
+/* sin/cos(2 pi u) defined operation by operation in IEEE-754 binary64  */
+/* with +,-,*,/ only (no FMA contraction).  The differential-evolution  */
+/* move amplifies a 1-ulp perturbation of theta by ~2.6x per accepted   */
+/* move, so two implementations whose libm differ in the last bit       */
+/* diverge within ~10 SMC iterations; with these definitions the CUDA   */
+/* library and this oracle produce bit-identical runs.  Accuracy is     */
+/* <= 2 ulp (checked against glibc in tests/test_oracle_golden.py).     */
+/* ------------------------------------------------------------------ */
+#define PM_LN2      0x1.62e42fefa39efp-1
+#define PM_LN2_HI   0x1.62e42fee00000p-1
+#define PM_LN2_LO   0x1.a39ef35793c76p-33
+#define PM_INV_LN2  0x1.71547652b82fep+0
+#define PM_SQRT2    0x1.6a09e667f3bcdp+0
+#define PM_TWO_PI   0x1.921fb54442d18p+2
+#define PM_HALF_LOG_2PI 0x1.d67f1c864beb5p-1
+
+static inline double plog(double x)
+{
+    if (x != x || x < 0.0) return NAN;
+    if (x == 0.0) return -INFINITY;
+    if (x == INFINITY) return x;
+    uint64_t b; memcpy(&b, &x, 8);
+    int e = (int)((b >> 52) & 0x7ff);
+    if (e == 0) { x = x * 0x1p54; memcpy(&b, &x, 8); e = (int)((b >> 52) & 0x7ff) - 54; }
+    e -= 1023;
+    b = (b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m; memcpy(&m, &b, 8);
+    if (m > PM_SQRT2) { m = m * 0.5; e += 1; }
+    double f = m - 1.0;
+    double s = f / (2.0 + f);
+    double z = s * s;
+    /* log(m) = 2 atanh(s) = 2s + s*z*(2/3 + z*(2/5 + ... + z*2/23)) */
+    double p = 2.0 / 23.0;
+    p = p * z + 2.0 / 21.0;
+    p = p * z + 2.0 / 19.0;
+    p = p * z + 2.0 / 17.0;
+    p = p * z + 2.0 / 15.0;
+    p = p * z + 2.0 / 13.0;
+    p = p * z + 2.0 / 11.0;
+    p = p * z + 2.0 / 9.0;
+    p = p * z + 2.0 / 7.0;
+    p = p * z + 2.0 / 5.0;
+    p = p * z + 2.0 / 3.0;
+    double r = (s * z) * p;
+    double lm = 2.0 * s + r;
+    return ((double)e * PM_LN2_HI + lm) + (double)e * PM_LN2_LO;
+}
+
+static inline double pexp(double x)
+{
+    if (x != x) return x;
+    if (x > 709.78) return INFINITY;
+    if (x < -745.2) return 0.0;
+    double k = floor(x * PM_INV_LN2 + 0.5);
+    double r = (x - k * PM_LN2_HI) - k * PM_LN2_LO;
+    double p = 1.0 / 6227020800.0;            /* 1/13! */
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r + 1.0;
+    /* scale by 2^k in two exact steps (k in [-1075, 1024]) */
+    int ki = (int)k, k1 = ki / 2, k2 = ki - k1;
+    uint64_t b1 = (uint64_t)(k1 + 1023) << 52, b2 = (uint64_t)(k2 + 1023) << 52;
+    double s1, s2; memcpy(&s1, &b1, 8); memcpy(&s2, &b2, 8);
+    return (p * s1) * s2;
+}
+
+/* sin and cos of 2*pi*u for u in [0, 1] */
+static inline void psincos2pi(double u, double* sn, double* cs)
+{
+    double q = floor(4.0 * u + 0.5);
+    double r = u - 0.25 * q;                   /* exact, |r| <= 1/8 */
+    double x = r * PM_TWO_PI;
+    double x2 = x * x;
+    double ps = -1.0 / 355687428096000.0;      /* -1/17! */
+    ps = ps * x2 + 1.0 / 1307674368000.0;
+    ps = ps * x2 - 1.0 / 6227020800.0;
+    ps = ps * x2 + 1.0 / 39916800.0;
+    ps = ps * x2 - 1.0 / 362880.0;
+    ps = ps * x2 + 1.0 / 5040.0;
+    ps = ps * x2 - 1.0 / 120.0;
+    ps = ps * x2 + 1.0 / 6.0;
+    double s = x - x * (x2 * ps);
+    double pc = 1.0 / 6402373705728000.0;      /* 1/18! */
+    pc = pc * x2 - 1.0 / 20922789888000.0;
+    pc = pc * x2 + 1.0 / 87178291200.0;
+    pc = pc * x2 - 1.0 / 479001600.0;
+    pc = pc * x2 + 1.0 / 3628800.0;
+    pc = pc * x2 - 1.0 / 40320.0;
+    pc = pc * x2 + 1.0 / 720.0;
+    pc = pc * x2 - 1.0 / 24.0;
+    pc = pc * x2 + 0.5;
+    double c = 1.0 - x2 * pc;
+    int k = (int)q & 3;
+    if (k == 0) { *sn = s; *cs = c; }
+    else if (k == 1) { *sn = c; *cs = -s; }
+    else if (k == 2) { *sn = -s; *cs = -c; }
+    else { *sn = -c; *cs = s; }
+}
+
+/* log Gamma(z), z > 0: upward recurrence to z >= 10, then Stirling's series */
+static inline double plgamma(double z)
+{
+    if (!(z > 0.0)) return (z == 0.0) ? INFINITY : NAN;
+    if (z == INFINITY) return z;
+    double prod = 1.0;
+    while (z < 10.0) { prod = prod * z; z = z + 1.0; }
+    double zi = 1.0 / z, z2 = zi * zi;
+    double t = -691.0 / 360360.0;
+    t = t * z2 + 1.0 / 1188.0;
+    t = t * z2 - 1.0 / 1680.0;
+    t = t * z2 + 1.0 / 1260.0;
+    t = t * z2 - 1.0 / 360.0;
+    t = t * z2 + 1.0 / 12.0;
+    double st = ((z - 0.5) * plog(z) - z) + PM_HALF_LOG_2PI + t * zi;
+    return st - plog(prod);
+}
+
+double orc_plog(double x) { return plog(x); }
+double orc_pexp(double x) { return pexp(x); }
+double orc_plgamma(double x) { return plgamma(x); }
+void orc_psincos2pi(double u, double* s, double* c) { psincos2pi(u, s, c); }
+
 /* Randomness contract: stream tags (DESIGN.md "Randomness contract"). */
 enum {
     TAG_PRIOR = 1,      /* prior draws; c3 = (dim<<16) | block              */
@@ -117,18 +251,17 @@ static inline void stream_u2(const stream_t* s, uint32_t block, double* u1, doub
     *u2 = (double)(b >> 11) * 0x1.0p-53;
 }
 
-#define ORC_TWO_PI 6.283185307179586476925286766559
 
 /* Box-Muller pair from one block: z1 = r cos(2 pi u2), z2 = r sin(2 pi u2),
- * r = sqrt(-2 log(1-u1)).  (1-u1) is in (0,1] and exactly representable. */
+ * r = sqrt(-2 plog(1-u1)).  (1-u1) is in (0,1] and exactly representable. */
 static inline void stream_n2(const stream_t* s, uint32_t block, double* z1, double* z2)
 {
     double u1, u2;
     stream_u2(s, block, &u1, &u2);
-    double r = sqrt(-2.0 * log(1.0 - u1));
-    double ang = ORC_TWO_PI * u2;
-    *z1 = r * cos(ang);
-    *z2 = r * sin(ang);
+    double r = sqrt(-2.0 * plog(1.0 - u1)), sn, cs;
+    psincos2pi(u2, &sn, &cs);
+    *z1 = r * cs;
+    *z2 = r * sn;
 }
 
 /* sequential RNG view handed to the simulators */
@@ -176,43 +309,57 @@ static inline void push_p(const prior_t* pr, const double* th, double* out)
 
 #define ORC_LOG2PI 1.8378770664093454835606594728112
 
+/* additive constant of the log density, evaluated once with the host libm (the CUDA library
+ * evaluates the same expressions with the same libm on the host side) */
+static double marginal_const(int fam, const double* p)
+{
+    switch (fam) {
+    case FAM_NORMAL: return log(p[1]);
+    case FAM_UNIFORM: return -log(p[1] - p[0]);
+    case FAM_DISCRETE_UNIFORM: return log(1.0 / (p[1] - p[0] + 1.0));
+    case FAM_LOGNORMAL: return log(p[1]);
+    case FAM_EXPONENTIAL: return log(p[0]);
+    case FAM_GAMMA: return lgamma(p[0]) + p[0] * log(p[1]);
+    case FAM_BETA: return lgamma(p[0]) + lgamma(p[1]) - lgamma(p[0] + p[1]);
+    case FAM_NEGBIN: return p[0] * log(p[1]) - lgamma(p[0]);
+    }
+    return NAN;
+}
+
 static double marginal_logpdf(int fam, const double* p, double x)
 {
+    double c = marginal_const(fam, p);
     switch (fam) {
     case FAM_NORMAL: {            /* Distributions normlogpdf: -(z^2+log2pi)/2 - log(sigma) */
         double z = (x - p[0]) / p[1];
-        return -(z * z + ORC_LOG2PI) / 2.0 - log(p[1]);
+        return -(z * z + ORC_LOG2PI) / 2.0 - c;
     }
     case FAM_UNIFORM:             /* insupport [a,b] ? -log(b-a) : -Inf */
-        return (x >= p[0] && x <= p[1]) ? -log(p[1] - p[0]) : -INFINITY;
-    case FAM_DISCRETE_UNIFORM: {  /* log(1/(b-a+1)) on integers a..b */
-        if (x >= p[0] && x <= p[1] && x == rint(x)) return log(1.0 / (p[1] - p[0] + 1.0));
-        return -INFINITY;
-    }
+        return (x >= p[0] && x <= p[1]) ? c : -INFINITY;
+    case FAM_DISCRETE_UNIFORM:    /* log(1/(b-a+1)) on integers a..b */
+        return (x >= p[0] && x <= p[1] && x == rint(x)) ? c : -INFINITY;
     case FAM_LOGNORMAL: {
         if (!(x > 0.0)) return -INFINITY;
-        double lx = log(x);
+        double lx = plog(x);
         double z = (lx - p[0]) / p[1];
-        return -(z * z + ORC_LOG2PI) / 2.0 - log(p[1]) - lx;
+        return -(z * z + ORC_LOG2PI) / 2.0 - c - lx;
     }
     case FAM_EXPONENTIAL:         /* scale parametrisation */
-        return (x >= 0.0) ? -x / p[0] - log(p[0]) : -INFINITY;
+        return (x >= 0.0) ? -x / p[0] - c : -INFINITY;
     case FAM_GAMMA: {
         if (!(x >= 0.0)) return -INFINITY;
-        if (x == 0.0) return p[0] == 1.0 ? -log(p[1]) : (p[0] < 1.0 ? INFINITY : -INFINITY);
-        return (p[0] - 1.0) * log(x) - x / p[1] - lgamma(p[0]) - p[0] * log(p[1]);
+        if (x == 0.0) return p[0] == 1.0 ? -plog(p[1]) : (p[0] < 1.0 ? INFINITY : -INFINITY);
+        return (p[0] - 1.0) * plog(x) - x / p[1] - c;
     }
     case FAM_BETA: {
         if (!(x >= 0.0 && x <= 1.0)) return -INFINITY;
-        double lb = lgamma(p[0]) + lgamma(p[1]) - lgamma(p[0] + p[1]);
-        double t1 = (p[0] == 1.0) ? 0.0 : (p[0] - 1.0) * log(x);
-        double t2 = (p[1] == 1.0) ? 0.0 : (p[1] - 1.0) * log1p(-x);
-        return t1 + t2 - lb;
+        double t1 = (p[0] == 1.0) ? 0.0 : (p[0] - 1.0) * plog(x);
+        double t2 = (p[1] == 1.0) ? 0.0 : (p[1] - 1.0) * plog(1.0 - x);
+        return t1 + t2 - c;
     }
     case FAM_NEGBIN: {            /* k failures before r successes, success prob p */
         if (!(x >= 0.0) || x != rint(x)) return -INFINITY;
-        double r = p[0], q = p[1];
-        return lgamma(x + r) - lgamma(r) - lgamma(x + 1.0) + r * log(q) + x * log1p(-q);
+        return plgamma(x + p[0]) - plgamma(x + 1.0) + c + x * plog(1.0 - p[1]);
     }
     }
     return NAN;
@@ -237,7 +384,7 @@ static double gamma_draw(const stream_t* s, uint32_t dimbase, uint32_t* blk, dou
     if (a < 1.0) {
         double u1, u2;
         stream_u2(s, dimbase | (*blk)++, &u1, &u2);
-        boost = pow(1.0 - u1, 1.0 / a);
+        boost = pexp(plog(1.0 - u1) / a);
         a += 1.0;
     }
     double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
@@ -248,7 +395,7 @@ static double gamma_draw(const stream_t* s, uint32_t dimbase, uint32_t* blk, dou
         if (v <= 0.0) continue;
         v = v * v * v;
         stream_u2(s, dimbase | (*blk)++, &u1, &u2);
-        if (log(1.0 - u1) < 0.5 * z * z + d - d * v + d * log(v)) return boost * d * v;
+        if (plog(1.0 - u1) < 0.5 * z * z + d - d * v + d * plog(v)) return boost * d * v;
     }
     return boost * d;
 }
@@ -270,9 +417,9 @@ static void prior_sample(const prior_t* pr, uint64_t seed, uint32_t particle, ui
         case FAM_DISCRETE_UNIFORM:
             stream_u2(&s, base, &u1, &u2); out[k] = p[0] + floor(u1 * (p[1] - p[0] + 1.0)); break;
         case FAM_LOGNORMAL:
-            stream_n2(&s, base, &z1, &z2); out[k] = exp(p[0] + p[1] * z1); break;
+            stream_n2(&s, base, &z1, &z2); out[k] = pexp(p[0] + p[1] * z1); break;
         case FAM_EXPONENTIAL:
-            stream_u2(&s, base, &u1, &u2); out[k] = -p[0] * log(1.0 - u1); break;
+            stream_u2(&s, base, &u1, &u2); out[k] = -p[0] * plog(1.0 - u1); break;
         case FAM_GAMMA:
             out[k] = p[1] * gamma_draw(&s, base, &blk, p[0]); break;
         case FAM_BETA: {
@@ -286,7 +433,7 @@ static void prior_sample(const prior_t* pr, uint64_t seed, uint32_t particle, ui
             double acc = 0.0; long cnt = -1;
             do {
                 stream_u2(&s, base | blk++, &u1, &u2);
-                acc += -log(1.0 - u1); cnt++;
+                acc += -plog(1.0 - u1); cnt++;
             } while (acc <= lam && cnt < 100000);
             out[k] = (double)cnt; break;
         }
@@ -319,7 +466,7 @@ double orc_kernel_logpdf(int kind, double eps, double x)
     if (!abck_insupport(kind, eps, x)) return -INFINITY;
     if (kind == K_INDICATOR || kind == K_INDICATOR_STRICT) return 0.0;
     double q = x / eps;
-    return log(1.0 - q * q);                                                   /* :61,:73 */
+    return plog(1.0 - q * q);                                                  /* :61,:73 */
 }
 
 /* ------------------------------------------------------------------ */
@@ -400,7 +547,7 @@ static double model_bd(const double* th, const double* data, simrng_t* r, double
         while (n > 0.0 && events < maxev) {
             double rate = lam_mu * n, u1, u2;
             sim_u2(r, &u1, &u2);
-            double tn = t + (-log(1.0 - u1)) / rate;
+            double tn = t + (-plog(1.0 - u1)) / rate;
             if (tn > tobs) break;            /* memoryless: pending event discarded at tobs */
             t = tn;
             n += (u2 * lam_mu < th[0]) ? 1.0 : -1.0;
@@ -766,7 +913,7 @@ int orc_smc_sweep(int d, const int32_t* family, const double* params, int model,
         if (!acc) {                                                        /* :145, uniform only if w<0 */
             double u, u2;
             if (inj_u) u = inj_u[i]; else stream_u2(&ms, 1, &u, &u2);
-            acc = (log(u) < w);
+            acc = (plog(u) < w);
         }
         if (acc) {                                                         /* :146-150 */
             ndelta[i] = dp;
@@ -842,7 +989,7 @@ int orc_reweight(int64_t N, const double* delta, double* W, uint8_t* alive,
     for (int64_t i = 0; i < N; ++i) {
         double ws = 0.0;
         if (alive[i])                                                      /* :71-76 */
-            ws = exp(orc_kernel_logpdf(kind, eps_new, delta[i]) - orc_kernel_logpdf(kind, eps_old, delta[i]));
+            ws = pexp(orc_kernel_logpdf(kind, eps_new, delta[i]) - orc_kernel_logpdf(kind, eps_old, delta[i]));
         wprod[i] = alive[i] ? W[i] * ws : 0.0;                              /* :308 */
     }
     double wnorm = pairwise_sum(wprod, N);                                  /* :309 */
@@ -990,7 +1137,7 @@ int orc_smc_run(int d, const int32_t* family, const double* params, int model, c
         eps = fmax(fmin(q, eps), eps_target);
         double wnorm;
         orc_reweight(N, dl, W, alive, eps_k, eps, o->kind, &wnorm, &ess, &n_alive);   /* :305-311,323 */
-        logZ += log(wnorm);                                                /* :315 */
+        logZ += plog(wnorm);                                               /* :315 */
         naccs = 0; Ki = o->Kmcmc;                                          /* :318-319 */
         if (facc < o->facc_min) gamma0 *= o->facc_tune;                    /* :320 */
         if (ess < ess_min) {                                               /* :324-326 */
@@ -1133,7 +1280,7 @@ int orc_mc_sweep(int d, const int32_t* family, const double* params, int model, 
         double w_prior = lp - logpi[i];                                    /* :42, logpi[i] not [s] */
         double u, u2;
         if (inj_u) u = inj_u[i]; else stream_u2(&ms, 1, &u, &u2);
-        if (log(u) > fmin(0.0, w_prior)) continue;                         /* :43, uniform always drawn */
+        if (plog(u) > fmin(0.0, w_prior)) continue;                        /* :43, uniform always drawn */
         nsims++;                                                           /* :44 */
         if (flags) flags[i] |= FLAG_SIM;
         simrng_t r; r.s = mk_stream(seed, pid, epoch, TAG_MODEL); r.blk = 0;

@@ -247,3 +247,36 @@ def test_wiener_and_socks_and_mixture(oracle):
     qs = np.quantile(x, np.arange(0.1, 0.95, 0.1))
     stv = ((qs - qs[::-1]) / 2)[4:]
     assert np.mean(np.abs(stv - st_n)) < 0.1
+
+
+# ---- portable math contract (DESIGN.md "Numerics"): accuracy vs libm ---------------------------
+def test_portable_math_accuracy(oracle):
+    import ctypes as C
+    from scipy.special import gammaln
+    L = oracle.lib()
+    for f in ("orc_plog", "orc_pexp", "orc_plgamma"):
+        getattr(L, f).restype = C.c_double; getattr(L, f).argtypes = [C.c_double]
+    rng = np.random.default_rng(0)
+
+    def ulps(got, want):
+        return np.max(np.abs(got - want) / np.spacing(np.abs(want)))
+
+    xs = np.concatenate([rng.random(20000), 10 ** rng.uniform(-300, 300, 20000), 1 - 2.0 ** -np.arange(1, 54), [2.0 ** -53, 0.5, 2.0, 1e-310]])
+    got = np.array([L.orc_plog(float(x)) for x in xs])
+    assert ulps(got, np.log(xs)) <= 2.0
+    assert L.orc_plog(1.0) == 0.0 and L.orc_plog(0.0) == -INF and math.isnan(L.orc_plog(-1.0))
+    xs = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-2, 2, 20000), [0.0, -745.0, 709.7]])
+    got = np.array([L.orc_pexp(float(x)) for x in xs])
+    assert ulps(got, np.exp(xs)) <= 2.0
+    assert L.orc_pexp(-INF) == 0.0 and L.orc_pexp(0.0) == 1.0
+    xs = np.concatenate([rng.uniform(0.01, 300, 20000), 10 ** rng.uniform(-5, 8, 5000)])
+    got = np.array([L.orc_plgamma(float(x)) for x in xs])
+    assert np.max(np.abs(got - gammaln(xs)) / np.maximum(1.0, np.abs(gammaln(xs)))) < 5e-14
+    s, c = C.c_double(), C.c_double()
+    us = np.concatenate([rng.random(20000), [0.0, 0.25, 0.5, 0.75, 0.125, 1 - 2.0 ** -53]])
+    err = 0.0
+    for u in us:
+        L.orc_psincos2pi(C.c_double(u), C.byref(s), C.byref(c))
+        err = max(err, abs(s.value - math.sin(2 * math.pi * u)), abs(c.value - math.cos(2 * math.pi * u)))
+        assert abs(s.value ** 2 + c.value ** 2 - 1.0) < 1e-15
+    assert err < 2e-15
