@@ -13,8 +13,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libabcdez_cuda.so")
+TAG = os.environ.get("ABCDEZ_BUILD_TAG", "")            # experiment builds: separate objects + library name
+OBJ = os.path.join(HERE, "build" + TAG)
+LIB = os.path.join(HERE, f"libabcdez_cuda{TAG}.so")
+EXTRA = os.environ.get("ABCDEZ_NVCC_EXTRA", "").split()   # experiment knobs, e.g. -DABCDEZ_SWEEP_MIN_BLOCKS=4
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
@@ -32,7 +34,7 @@ def _headers_mtime():
 
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC, *FLAGS, *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

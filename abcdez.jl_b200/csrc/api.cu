@@ -75,6 +75,7 @@ extern "C" int abcdez_destroy(abcdez_ctx* ctx)
     if (!ctx) return ABCDEZ_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
     return ABCDEZ_OK;
 }
@@ -281,7 +282,7 @@ extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
     cudaStreamSynchronize(pop->ctx->stream);
     PopDev& P = pop->dev;
     for (int b = 0; b < 2; ++b) { cudaFree(P.theta[b]); cudaFree(P.logpi[b]); cudaFree(P.delta[b]); cudaFree(P.blob[b]); }
-    cudaFree(P.W); cudaFree(P.alive); cudaFree(P.alive_list); cudaFree(P.ctrl); cudaFree(P.partial);
+    cudaFree(P.W); cudaFree(P.alive); cudaFree(P.moved); cudaFree(P.alive_list); cudaFree(P.ctrl); cudaFree(P.partial);
     cudaFree(P.tile_cnt); cudaFree(P.sel_hist); cudaFree(P.cumsum); cudaFree(P.inds); cudaFree(P.hist); cudaFree(P.tabs);
     if (pop->scratch) cudaFree(pop->scratch);
     if (pop->sorted_delta) cudaFree(pop->sorted_delta);
@@ -320,7 +321,7 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
         ALLOC(P.theta[b], n * pop->DS * 8); ALLOC(P.logpi[b], n * 8); ALLOC(P.delta[b], n * 8);
         ALLOC(P.blob[b], n * pop->NB * 8);
     }
-    ALLOC(P.W, n * 8); ALLOC(P.alive, n + 4); ALLOC(P.alive_list, n * 4); ALLOC(P.ctrl, sizeof(Ctrl));
+    ALLOC(P.W, n * 8); ALLOC(P.alive, n + 4); ALLOC(P.moved, n + 4); ALLOC(P.alive_list, n * 4); ALLOC(P.ctrl, sizeof(Ctrl));
     ALLOC(P.partial, (size_t)P.ntiles * 2 * 8 + 64); ALLOC(P.tile_cnt, (size_t)P.ntiles * 4 + 64);
     ALLOC(P.sel_hist, SEL_BINS * 4); ALLOC(P.cumsum, n * 8); ALLOC(P.inds, n * 4);
     ALLOC(P.hist, (size_t)(hist_cap > 0 ? hist_cap : 1) * 8 * 8); ALLOC(P.tabs, 2 * sizeof(SeqTab));
@@ -330,6 +331,7 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(P.sel_hist, 0, SEL_BINS * 4, st));
     CU(cudaMemsetAsync(P.alive, 1, n, st));
+    CU(cudaMemsetAsync(P.moved, 1, n, st));
     CU(cudaMemsetAsync(P.theta[0], 0, n * pop->DS * 8, st));
     CU(cudaMemsetAsync(P.theta[1], 0, n * pop->DS * 8, st));
     fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.W, N, 1.0 / (double)N);
@@ -373,14 +375,16 @@ extern "C" int abcdez_pop_upload(abcdez_pop* pop, const double* theta, const dou
     if (delta) CU(cudaMemcpyAsync(P.delta[cur], delta, n * 8, cudaMemcpyHostToDevice, st));
     if (blobs && pop->NB) CU(cudaMemcpyAsync(P.blob[cur], blobs, n * pop->NB * 8, cudaMemcpyHostToDevice, st));
     if (W) CU(cudaMemcpyAsync(P.W, W, n * 8, cudaMemcpyHostToDevice, st));
+    if (theta || logpi || delta || blobs) CU(cudaMemsetAsync(P.moved, 1, n, st));   // the other buffer is stale now
     if (alive) {
         CU(cudaMemcpyAsync(P.alive, alive, n, cudaMemcpyHostToDevice, st));
         // keep the control block and the compacted list consistent with the uploaded flags
         uint32_t na = 0; double wal = 0.0;
         for (size_t i = 0; i < n; ++i) if (alive[i]) { na++; if (W && wal == 0.0) wal = W[i]; }
-        std::vector<uint32_t> list; list.reserve(na);
+        std::vector<uint32_t> list; list.reserve(n);       // alive first, then dead (see compact_kernel)
         for (size_t i = 0; i < n; ++i) if (alive[i]) list.push_back((uint32_t)i);
-        if (na) CU(cudaMemcpyAsync(P.alive_list, list.data(), (size_t)na * 4, cudaMemcpyHostToDevice, st));
+        for (size_t i = 0; i < n; ++i) if (!alive[i]) list.push_back((uint32_t)i);
+        CU(cudaMemcpyAsync(P.alive_list, list.data(), n * 4, cudaMemcpyHostToDevice, st));
         pop->h_ctrl->n_alive = na;
         if (W) pop->h_ctrl->acc.w_alive = wal;
         CU(cudaStreamSynchronize(st));
@@ -742,7 +746,8 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     c->kind = o->kernel; c->facc_stop = o->facc_stop; c->facc_min = o->facc_min; c->facc_tune = o->facc_tune;
     c->seed = o->seed; c->max_iters = o->max_iters; c->hist_cap = hist_cap;
     rc = push_ctrl(pop);
-    std::vector<cudaEvent_t> evs;
+    std::vector<cudaEvent_t>& evs = ctx->ev_pool;
+    size_t nev = 0;
     cudaEvent_t e_init0 = nullptr, e_loop0 = nullptr, e_loop1 = nullptr;
     int64_t launches = 0;
     int64_t host_iters = 0;
@@ -764,11 +769,11 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         launches += launch_resample(st, pop->dev, pop->DS, pop->NB, nullptr, (uint32_t)host_iters, mode, 0);   // :324-326
         for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
             if (o->profile) {
-                cudaEvent_t a, b; RUN_CU(cudaEventCreate(&a)); RUN_CU(cudaEventCreate(&b));
-                evs.push_back(a); evs.push_back(b);
-                RUN_CU(cudaEventRecord(a, st));
+                while (evs.size() < nev + 2) { cudaEvent_t e; RUN_CU(cudaEventCreate(&e)); evs.push_back(e); }
+                RUN_CU(cudaEventRecord(evs[nev], st));
                 pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
-                RUN_CU(cudaEventRecord(b, st));
+                RUN_CU(cudaEventRecord(evs[nev + 1], st));
+                nev += 2;
             } else {
                 pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
             }
@@ -782,6 +787,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         if (host_iters > 10000000) break;
     }
     RUN_CU(cudaEventRecord(e_loop1, st));
+    launches += launch_minmax(st, pop->dev);      // extrema(delta) of the final generation -> last history record
     RUN_CU(cudaGetLastError());
     RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     RUN_CU(cudaStreamSynchronize(st));
@@ -793,7 +799,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         RUN_CU(cudaEventElapsedTime(&ms, e_init0, e_loop0)); res->init_ms = ms;
         RUN_CU(cudaEventElapsedTime(&ms, e_loop0, e_loop1)); res->total_ms = ms;
         double sw = 0.0;
-        for (size_t i = 0; i + 1 < evs.size(); i += 2) { RUN_CU(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); sw += ms; }
+        for (size_t i = 0; i + 1 < nev; i += 2) { RUN_CU(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); sw += ms; }
         res->sweep_ms = sw;
     }
     res->eps = c->eps; res->logZ = c->logZ; res->iters = c->iters; res->nsims = c->nsims_total;
@@ -825,7 +831,6 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         }
     }
 done:
-    for (cudaEvent_t e : evs) cudaEventDestroy(e);
     if (e_init0) cudaEventDestroy(e_init0);
     if (e_loop0) cudaEventDestroy(e_loop0);
     if (e_loop1) cudaEventDestroy(e_loop1);

@@ -68,6 +68,19 @@ __device__ __forceinline__ uint32_t load4_u8(const uint8_t* __restrict__ p, size
     return r;
 }
 
+// extrema(delta) of the generation that the previous iteration left behind: the sweeps no longer touch
+// every particle, so ranges_eps (src/abcdez_smc.jl:363) is taken from the first select pass of the next
+// iteration (same delta array) and written into the history record that iteration pushed
+__device__ void patch_extrema(const PopDev& P, Ctrl* c)
+{
+    c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
+    c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
+    if (P.hist && c->hist_len > 0 && c->hist_len <= c->hist_cap) {
+        double* h = P.hist + (size_t)(c->hist_len - 1) * 8;
+        h[1] = c->dmin; h[2] = c->dmax;
+    }
+}
+
 // pick the bin holding rank sel_rank; all BK_THREADS threads of the calling CTA participate
 __device__ void select_pick(const PopDev& P, Ctrl* c, int shift, int nbins, bool final_pass)
 {
@@ -126,10 +139,12 @@ select_hist_kernel(PopDev P, int shift, int nbins, unsigned long long himask, in
     load4_f64(dl, i0, P.N, v);
     uint32_t al = load4_u8(P.alive, i0, P.N);
     int nan_seen = 0;
+    unsigned long long kmn = ~0ull, kmx = 0ull;      // extrema(delta) over ALL particles (ranges_eps), first pass only
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         bool ok = (al >> (8 * k)) & 0xff;
         unsigned long long key = f64_key(v[k]);
+        if (first && i0 + k < P.N) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
         if (ok && first && isnan(v[k])) nan_seen = 1;
         ok = ok && ((key & himask) == prefix);
         unsigned digit = ok ? (unsigned)((key >> shift) & (unsigned long long)(nbins - 1)) : 0xffffffffu;
@@ -139,12 +154,23 @@ select_hist_kernel(PopDev P, int shift, int nbins, unsigned long long himask, in
         if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[digit], (unsigned)__popc(peers));
     }
     if (nan_seen) atomicMax(&c->acc.err, (int)ABCDEZ_ERR_NAN_DISTANCE);
+    __shared__ unsigned long long s_mn, s_mx;
+    if (first) {
+        if (threadIdx.x == 0) { s_mn = ~0ull; s_mx = 0ull; }
+        __syncthreads();
+        kmn = warp_min_u64(kmn); kmx = warp_max_u64(kmx);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_mn, kmn); atomicMax(&s_mx, kmx); }
+    }
     __syncthreads();
+    if (first && threadIdx.x == 0) { atomicMin(&c->acc.dmin_key, s_mn); atomicMax(&c->acc.dmax_key, s_mx); }
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
         unsigned cnt = sh[b];
         if (cnt) atomicAdd(&P.sel_hist[b], cnt);
     }
-    if (last_block(&c->acc.ticket[1], gridDim.x)) select_pick(P, c, shift, nbins, final_pass != 0);
+    if (last_block(&c->acc.ticket[1], gridDim.x)) {
+        if (first && threadIdx.x == 0) patch_extrema(P, c);
+        select_pick(P, c, shift, nbins, final_pass != 0);
+    }
 }
 
 // v[j+1]: count of keys <= v[j] and the smallest key above it; then the type-7 interpolation
@@ -350,9 +376,17 @@ __global__ void __launch_bounds__(BK_THREADS) compact_kernel(PopDev P)
     unsigned woff = 0;
     for (int q = 0; q < w; ++q) woff += s_w[q];
     (void)nw;
-    unsigned pos = P.tile_cnt[blockIdx.x] + woff + incl - cnt;
+    // alive particles (index order) fill list[0, n_alive); the dead ones follow in list[n_alive, N):
+    // the sweep maps thread j to particle list[j], so alive and dead warps are homogeneous
+    unsigned pos = P.tile_cnt[blockIdx.x] + woff + incl - cnt;          // alive before element i0
+    unsigned dpos = c->n_alive + ((unsigned)i0 - pos);                    // dead before element i0
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if ((al >> (8 * k)) & 0xff) P.alive_list[pos++] = (uint32_t)(i0 + k);
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < P.N) {
+            if ((al >> (8 * k)) & 0xff) P.alive_list[pos++] = (uint32_t)(i0 + k);
+            else P.alive_list[dpos++] = (uint32_t)(i0 + k);
+        }
+    }
 }
 
 int launch_compact(cudaStream_t st, const PopDev& P)
@@ -425,7 +459,7 @@ resample_uniform_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
         P.inds[si] = (int32_t)src;
     }
     __syncthreads();
-    if (si < N) { P.W[si] = sval; P.alive[si] = 1; }                         // :102-103
+    if (si < N) { P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1; }        // :102-103; the old buffer is stale
     if (last_block(&c->acc.ticket[3], gridDim.x)) {
         if (threadIdx.x == 0) ctrl_after_resample(P, c);
     }
@@ -523,7 +557,7 @@ resample_general_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
         P.inds[si] = (int32_t)src;
     }
     __syncthreads();
-    if (si < N) { P.W[si] = sval; P.alive[si] = 1; }
+    if (si < N) { P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1; }
     if (last_block(&c->acc.ticket[3], gridDim.x)) {
         if (threadIdx.x == 0) ctrl_after_resample(P, c);
     }
@@ -678,10 +712,7 @@ __global__ void __launch_bounds__(BK_THREADS) minmax_kernel(PopDev P)
     mn = warp_min_u64(mn); mx = warp_max_u64(mx);
     if ((threadIdx.x & 31) == 0) { atomicMin(&c->acc.dmin_key, mn); atomicMax(&c->acc.dmax_key, mx); }
     if (last_block(&c->acc.ticket[4], gridDim.x)) {
-        if (threadIdx.x == 0) {
-            c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
-            c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
-        }
+        if (threadIdx.x == 0) patch_extrema(P, c);
     }
 }
 

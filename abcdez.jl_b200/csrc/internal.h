@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "common.cuh"
 #include "models.cuh"
 
@@ -11,7 +12,14 @@ namespace abcdez {
 
 constexpr int TILE = 1024;            // particles per CTA in the bookkeeping kernels (256 thr x 4)
 constexpr int BK_THREADS = 256;
-constexpr int SWEEP_THREADS = 256;    // thread-per-particle sweeps
+#ifndef ABCDEZ_SWEEP_THREADS
+#define ABCDEZ_SWEEP_THREADS 256
+#endif
+constexpr int SWEEP_THREADS = ABCDEZ_SWEEP_THREADS;    // thread-per-particle sweeps
+#ifndef ABCDEZ_SWEEP_MIN_BLOCKS
+#define ABCDEZ_SWEEP_MIN_BLOCKS 3
+#endif
+constexpr int SWEEP_MIN_BLOCKS = ABCDEZ_SWEEP_MIN_BLOCKS;   // register cap of the fused sweep kernels
 constexpr int SEL_BINS = 2048;        // 11-bit radix-select digits
 constexpr int SEQTAB_MAX = 256;       // segments of the sequential-sum closed form
 
@@ -33,7 +41,8 @@ struct PopDev {
     double* blob[2];              // N x (BLOB/8) doubles
     double* W;
     uint8_t* alive;
-    uint32_t* alive_list;         // compacted indices of alive particles (valid when n_alive < N)
+    uint8_t* moved;               // 1: the row of this particle in the other generation buffer is stale (sweep.cuh)
+    uint32_t* alive_list;         // alive particle indices (index order), then the dead ones (valid when n_alive < N)
     Ctrl* ctrl;
     double* partial;              // per-CTA reduction partials (2 x nblocks)
     uint32_t* tile_cnt;           // per-tile alive counts -> exclusive offsets
@@ -103,6 +112,7 @@ struct abcdez_ctx {
     int rank, world;
     void* nccl_comm;
     int sm_count;
+    std::vector<cudaEvent_t> ev_pool;   // reused by profile=1 runs (cudaEventCreate costs ~0.2 ms each)
 };
 
 struct abcdez_prior {

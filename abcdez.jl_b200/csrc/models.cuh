@@ -16,7 +16,7 @@ struct ModelData { double v[ABCDEZ_MAXDATA]; };
 
 // examples/minimal_example.jl:17-24, test/runtests.jl:138: y ~ N(theta, sigma), d = |y - data|
 struct Gauss1D {
-    static constexpr int D = 1, BLOB = 0;
+    static constexpr int D = 1, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "gauss1d";
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
@@ -26,7 +26,7 @@ struct Gauss1D {
 
 // same simulator, the simulated y is carried as the particle's blob (docs/src/index.md:298-324)
 struct Gauss1DBlob {
-    static constexpr int D = 1, BLOB = 8;
+    static constexpr int D = 1, BLOB = 8, NOISE = 0;
     static constexpr const char* name = "gauss1d_blob";
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double* blob)
     {
@@ -37,18 +37,40 @@ struct Gauss1DBlob {
 };
 
 // config 2: y ~ N(theta, Sigma), Sigma_ij = rho^|i-j| (stationary AR(1) noise), d = ||y - y_obs||_2
+// NOISE > 0: the simulator's random input does not depend on theta, so the sweep kernel may draw it
+// (draw) while the partner rows are still in flight and score it afterwards (score); run == draw + score.
 struct GaussCorr10 {
-    static constexpr int D = 10, BLOB = 0;
+    static constexpr int D = 10, BLOB = 0, NOISE = 10;
     static constexpr const char* name = "gauss_corr10";
-    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    __device__ static __forceinline__ void draw(SimRng& r, double* nz)
     {
-        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0, z[10];
 #pragma unroll
-        for (int k = 0; k < 10; k += 2) r.n2(z[k], z[k + 1]);
+        for (int k = 0; k < 10; k += 2) r.n2(nz[k], nz[k + 1]);
+    }
+    __device__ static __forceinline__ double score(const double* th, const double* data, const double* nz, double*)
+    {
+        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
-            e = (k == 0) ? z[0] : rho * e + sr * z[k];
+            e = (k == 0) ? nz[0] : rho * e + sr * nz[k];
             double dy = th[k] + e - data[k];
+            acc += dy * dy;
+        }
+        return sqrt(acc);
+    }
+    // noise pairs are consumed as they are generated (same arithmetic as draw + score, 18 fewer live registers)
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    {
+        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) {
+            double za, zb;
+            r.n2(za, zb);
+            e = (k == 0) ? za : rho * e + sr * za;
+            double dy = th[k] + e - data[k];
+            acc += dy * dy;
+            e = rho * e + sr * zb;
+            dy = th[k + 1] + e - data[k + 1];
             acc += dy * dy;
         }
         return sqrt(acc);
@@ -57,7 +79,7 @@ struct GaussCorr10 {
 
 // test/runtests.jl:496-497
 struct Dirac {
-    static constexpr int D = 1, BLOB = 0;
+    static constexpr int D = 1, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "dirac";
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng&, double*)
     {
@@ -67,7 +89,7 @@ struct Dirac {
 
 // test/runtests.jl:524-525
 struct NormDU {
-    static constexpr int D = 2, BLOB = 0;
+    static constexpr int D = 2, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "normdu";
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
@@ -78,7 +100,7 @@ struct NormDU {
 // test/runtests.jl:603 (dist1!) and :614 (dist2!, returns Inf with probability 1/2)
 template <bool WITH_INF>
 struct TwoD {
-    static constexpr int D = 2, BLOB = 0;
+    static constexpr int D = 2, BLOB = 0, NOISE = 0;
     static constexpr const char* name = WITH_INF ? "twod_inf" : "twod";
     __device__ static __forceinline__ double run(const double* th, const double*, SimRng& r, double*)
     {
@@ -94,7 +116,7 @@ struct TwoD {
 
 // test/runtests.jl:582-583
 struct Mixture {
-    static constexpr int D = 1, BLOB = 0;
+    static constexpr int D = 1, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "mixture";
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
@@ -108,7 +130,7 @@ struct Mixture {
 
 // test/runtests.jl:537-549: 31-point drifted-Wiener RMS summary, mean absolute difference
 struct Wiener {
-    static constexpr int D = 2, BLOB = 0;
+    static constexpr int D = 2, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "wiener";
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
@@ -125,7 +147,7 @@ struct Wiener {
 
 // config 4: Lotka-Volterra, fixed-step RK4 (see DESIGN.md for the data layout)
 struct LotkaVolterra {
-    static constexpr int D = 4, BLOB = 0;
+    static constexpr int D = 4, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "lotka_volterra";
     __device__ static __forceinline__ void rhs(const double* th, double x, double y, double& dx, double& dy)
     {
@@ -159,7 +181,7 @@ struct LotkaVolterra {
 
 // config 5: linear birth-death process, Gillespie SSA (divergent trajectory lengths)
 struct BirthDeath {
-    static constexpr int D = 2, BLOB = 16;
+    static constexpr int D = 2, BLOB = 16, NOISE = 0;
     static constexpr const char* name = "birth_death";
     __device__ static double run(const double* th, const double* data, SimRng& r, double* blob)
     {
@@ -190,7 +212,7 @@ struct BirthDeath {
 
 // test/runtests.jl:427-437 (socks): sequential picks without replacement
 struct Socks {
-    static constexpr int D = 2, BLOB = 0;
+    static constexpr int D = 2, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "socks";
     __device__ static double run(const double* th, const double* data, SimRng& r, double*)
     {

@@ -38,7 +38,7 @@ static inline unsigned grid_for(int64_t N, int threads) { return (unsigned)((N +
 // prior stage calls on dense N x d arrays (abcdez_prior_sample / _logpdf / _push)
 // ---------------------------------------------------------------------------------------
 template <int D>
-__global__ void prior_op_kernel(PriorDev pr, int64_t N, int op, const double* __restrict__ in,
+__global__ void prior_op_kernel(const __grid_constant__ PriorDev pr, int64_t N, int op, const double* __restrict__ in,
                                 double* __restrict__ out, uint64_t seed, uint32_t epoch, uint32_t id0)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -3,11 +3,18 @@
 //   init_kernel       abcde_init!        src/abcdez_init.jl:2-22  (+ prior draws, src/abcdez_smc.jl:242-243)
 //   smc_sweep_kernel  abcdesmc_swarm!    src/abcdez_smc.jl:106-153
 //   mc_sweep_kernel   abcdemc_swarm!     src/abcdez_mc.jl:5-61
-// Thread-per-particle; theta rows are read with 16-byte vector loads (own row: streaming,
-// partner rows: random gathers that touch ceil(8d/32) sectors thanks to the row layout);
-// generation g is read-only and generation g+1 is written for EVERY particle (accepted ->
-// proposal, otherwise copy-through), which is the reference's Jacobi double buffer
-// (src/abcdez_smc.jl:337-350) without its four full-array copies per sweep.
+//
+// Jacobi double buffer without the copies.  The reference copies all four state arrays before every
+// sweep (identity.(), src/abcdez_smc.jl:337-340) so that generation g stays read-only while g+1 is
+// written.  Here the two device buffers are kept in sync *lazily*: `moved[i]` records that particle i
+// was accepted in the previous executed sweep, i.e. its row in the other buffer is stale.  A sweep
+// (1) repairs exactly those rows (read from g, written to g+1), (2) writes accepted proposals to g+1
+// and (3) updates `moved`.  Rejected and dead particles cost no store at all, and a dead particle
+// whose row is in sync is not even read.  Resampling and (re)initialisation mark every row stale.
+//
+// Thread j works on particle list[j] (alive first, then dead; bookkeeping.cu compact_kernel), so warps
+// are homogeneous.  theta rows are read with 16-byte vector loads; partner rows are random gathers that
+// touch ceil(8d/32) sectors thanks to the particle-major row layout.
 #pragma once
 #include "internal.h"
 #include "ctrl.cuh"
@@ -18,19 +25,21 @@ namespace abcdez {
 // control logic run by the last CTA of a sweep (src/abcdez_smc.jl:347-352)
 // ---------------------------------------------------------------------------------------
 // move the per-sweep accumulators (L2-resident, bypass L1) into the control block and reset them
-__device__ __forceinline__ void sweep_collect(Ctrl* c)
+__device__ __forceinline__ void sweep_collect(Ctrl* c, bool with_extrema)
 {
     c->last_nsims = __ldcg(&c->acc.sweep_nsims); c->last_naccs = __ldcg(&c->acc.sweep_naccs);
-    c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
+    if (with_extrema) {
+        c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
+        c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
+    }
     int e = __ldcg(&c->acc.err);
     if (e && !c->err) c->err = e;
     c->acc.sweep_nsims = 0ull; c->acc.sweep_naccs = 0ull;
-    c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
 }
 
 __device__ inline void ctrl_after_smc_sweep(const PopDev& P, Ctrl* c)
 {
-    sweep_collect(c);
+    sweep_collect(c, false);
     c->nsims_total += (long long)c->last_nsims;
     c->naccs_iter += c->last_naccs;
     c->cur ^= 1;                                   // swap buffers, :347-350
@@ -47,41 +56,63 @@ __device__ inline void ctrl_after_smc_sweep(const PopDev& P, Ctrl* c)
 
 __device__ inline void ctrl_after_mc_sweep(Ctrl* c)
 {
-    sweep_collect(c);
+    sweep_collect(c, true);
     c->nsims_total += (long long)c->last_nsims;
     c->cur ^= 1;
     c->sweep_epoch += 1;
     c->n_sweeps += 1;
 }
 
-// block-level accumulation of the sweep counters + extrema(delta); integer atomics only, so
-// the totals are independent of scheduling order
-__device__ __forceinline__ void sweep_block_reduce(Ctrl* c, unsigned nsim, unsigned nacc,
-                                                   unsigned long long kmin, unsigned long long kmax, int err)
+// Barrier-free epilogue: warps retire independently (no __syncthreads at the end, so a warp that has
+// finished does not hold its registers hostage until the slowest warp of the CTA arrives).  Warp totals
+// go to shared-memory atomics; the last warp of the CTA to arrive forwards the CTA totals with one set
+// of global REDs (integer only: order independent) and takes the grid ticket.  Returns true in exactly
+// one thread of the grid: the one that must run the control logic.
+struct SweepSmem {
+    unsigned long long mn, mx;
+    unsigned sim, acc, arrived;
+    int err;
+};
+
+__device__ __forceinline__ void sweep_smem_init(SweepSmem* s)
 {
-    __shared__ unsigned s_sim[32], s_acc[32];
-    __shared__ unsigned long long s_min[32], s_max[32];
-    __shared__ int s_err;
-    if (threadIdx.x == 0) s_err = 0;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) { s->mn = ~0ull; s->mx = 0ull; s->sim = 0u; s->acc = 0u; s->arrived = 0u; s->err = 0; }
+    __syncthreads();
+}
+
+template <bool EXTREMA>
+__device__ __forceinline__ bool sweep_finish(Ctrl* c, SweepSmem* s, unsigned nsim, unsigned nacc,
+                                             unsigned long long kmin, unsigned long long kmax, int err)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned nw = blockDim.x >> 5;
     nsim = warp_sum_u(nsim); nacc = warp_sum_u(nacc);
-    kmin = warp_min_u64(kmin); kmax = warp_max_u64(kmax);
-    __syncthreads();
-    if (err) atomicOr(&s_err, err);
-    if (lane == 0) { s_sim[w] = nsim; s_acc[w] = nacc; s_min[w] = kmin; s_max[w] = kmax; }
-    __syncthreads();
-    if (w == 0) {
-        unsigned a = lane < nw ? s_sim[lane] : 0u, b = lane < nw ? s_acc[lane] : 0u;
-        unsigned long long mn = lane < nw ? s_min[lane] : ~0ull, mx = lane < nw ? s_max[lane] : 0ull;
-        a = warp_sum_u(a); b = warp_sum_u(b); mn = warp_min_u64(mn); mx = warp_max_u64(mx);
-        if (lane == 0) {
+    if (EXTREMA) { kmin = warp_min_u64(kmin); kmax = warp_max_u64(kmax); }
+    err = __reduce_max_sync(0xffffffffu, err);
+    bool last = false;
+    if (lane == 0) {
+        if (nsim) atomicAdd(&s->sim, nsim);
+        if (nacc) atomicAdd(&s->acc, nacc);
+        if (EXTREMA) { atomicMin(&s->mn, kmin); atomicMax(&s->mx, kmax); }
+        if (err) atomicMax(&s->err, err);
+        __threadfence_block();
+        if (atomicAdd(&s->arrived, 1u) == nw - 1) {
+            __threadfence_block();
+            volatile SweepSmem* v = s;
+            unsigned a = v->sim, b = v->acc; int e = v->err;
             if (a) atomicAdd(&c->acc.sweep_nsims, (unsigned long long)a);
             if (b) atomicAdd(&c->acc.sweep_naccs, (unsigned long long)b);
-            atomicMin(&c->acc.dmin_key, mn);
-            atomicMax(&c->acc.dmax_key, mx);
-            if (s_err) atomicMax(&c->acc.err, s_err);
+            if (EXTREMA) { atomicMin(&c->acc.dmin_key, v->mn); atomicMax(&c->acc.dmax_key, v->mx); }
+            if (e) atomicMax(&c->acc.err, e);
+            __threadfence();
+            if (atomicAdd(&c->acc.ticket[0], 1u) == gridDim.x - 1) {
+                c->acc.ticket[0] = 0u;
+                __threadfence();
+                last = true;
+            }
         }
     }
+    return last;
 }
 
 // StatsBase.wsample(rng, 1:N, alive) (src/abcdez_smc.jl:121,125) in O(1): t = u * n_alive, the
@@ -99,19 +130,32 @@ __device__ __forceinline__ uint32_t wsample_alive(const uint32_t* __restrict__ a
 constexpr int PARTNER_MAX_ATTEMPTS = 100000;
 constexpr int INIT_MAX_ATTEMPTS = 100000;
 
+// copy the scalar state of particle i from generation `cur` to `nxt`
+template <int NB>
+__device__ __forceinline__ void copy_scalars(const PopDev& P, int cur, int nxt, uint32_t i, double lpi, double dli)
+{
+    P.logpi[nxt][i] = lpi;
+    P.delta[nxt][i] = dli;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = P.blob[cur][(size_t)i * NB + k];
+}
+
 // ---------------------------------------------------------------------------------------
 // abcde_init!  src/abcdez_init.jl:2-22
 // ---------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(SWEEP_THREADS)
-init_kernel(PopDev P, PriorDev pr, ModelData md, uint64_t seed, int draw_prior)
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+            uint64_t seed, int draw_prior)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
     const int cur = c->cur;
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned redraws = 0; int err = 0;
-    unsigned long long kmin = ~0ull, kmax = 0ull;
+    unsigned long long kdl = 0ull;
     if (i < P.N) {
         const uint32_t pid = P.id0 + i;
         double th[D], x[D], blob[NB > 0 ? NB : 1];
@@ -145,48 +189,55 @@ init_kernel(PopDev P, PriorDev pr, ModelData md, uint64_t seed, int draw_prior)
         P.delta[cur][i] = dl;
 #pragma unroll
         for (int k = 0; k < NB; ++k) P.blob[cur][(size_t)i * NB + k] = blob[k];
-        kmin = kmax = f64_key(dl);
+        P.moved[i] = 1;                                    // the other buffer is stale
+        kdl = f64_key(dl);
     }
     // counters: reuse the sweep accumulators (nsims slot carries the redraw count)
-    sweep_block_reduce(c, redraws, 0u, kmin, kmax, err);
-    if (last_block(&c->acc.ticket[0], gridDim.x)) {
-        if (threadIdx.x == 0) {
-            sweep_collect(c);
-            c->redraws += (long long)c->last_nsims;
-        }
+    if (sweep_finish<true>(c, &s_red, redraws, 0u, i < P.N ? kdl : ~0ull, i < P.N ? kdl : 0ull, err)) {
+        sweep_collect(c, true);
+        c->redraws += (long long)c->last_nsims;
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // abcdesmc_swarm!  src/abcdez_smc.jl:106-153
+// DISC: the prior has discrete marginals (push_p rounds a copy of the proposal); the common
+// all-continuous case passes the proposal registers straight to the simulator.
 // ---------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(SWEEP_THREADS)
-smc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj)
+template <class M, bool DISC>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+                 const __grid_constant__ SweepInj inj)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
     if (c->stop | c->sweeps_done) return;                  // skipped sweep (early exit :352 / stop :376)
     const int cur = c->cur, nxt = cur ^ 1;
     const uint32_t N = P.N, n_alive = c->n_alive;
-    const double eps = c->eps, gamma0 = c->gamma0, gsig = c->gsig;
-    const int kind = c->kind;
-    const uint64_t seed = c->seed;
-    const uint32_t epoch = c->sweep_epoch;
     const double* __restrict__ th = P.theta[cur];
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
 
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
-    unsigned long long kmin = ~0ull, kmax = 0ull;
-    if (i < N) {
-        double ti[D], bl[NB > 0 ? NB : 1];
-        load_row<D>(th, i, ti);
-        double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) bl[k] = P.blob[cur][(size_t)i * NB + k];
-        uint8_t flag = 0;
-        if (P.alive[i]) {                                                  // :114
+    if (j < N) {
+        const uint32_t i = (n_alive == N) ? j : P.alive_list[j];
+        const uint8_t mv = P.moved[i];
+        if (j >= n_alive) {                                                // dead particle (:114)
+            if (mv) {                                                      // repair its stale row, once
+                double row[D];
+                load_row<D>(th, i, row);
+                store_row<D>(P.theta[nxt], i, row);
+                copy_scalars<NB>(P, cur, nxt, i, P.logpi[cur][i], P.delta[cur][i]);
+                P.moved[i] = 0;
+            }
+            if (inj.flags) inj.flags[i] = 0;
+        } else {
+            uint8_t flag = 0;
             const uint32_t pid = P.id0 + i;
+            const uint64_t seed = c->seed;
+            const uint32_t epoch = c->sweep_epoch;
+            // (1) partners: integer work only (plus list lookups while some particles are dead)
             uint32_t a, b;
             if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
             else {
@@ -205,27 +256,32 @@ smc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj)
                     b = wsample_alive(P.alive_list, n_alive, N, u2);
                 }
             }
+            // (2) own state; repair the stale row in g+1
+            double thp[D];
+            load_row<D>(th, i, thp);
+            const double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
+            if (mv) {
+                store_row<D>(P.theta[nxt], i, thp);
+                copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
+            }
+            // (3) the gamma jitter (:128)
+            Stream ms(seed, pid, epoch, TAG_MOVE);
+            double z, z2;
+            if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
+            const double g = c->gamma0 * (1.0 + z * c->gsig);              // :128
+            SimRng r(seed, pid, epoch, TAG_MODEL);
             if (!err) {
-                double ta[D], tb[D], thp[D], x[D];
-                load_row<D>(th, a, ta);
-                load_row<D>(th, b, tb);
-                Stream ms(seed, pid, epoch, TAG_MOVE);
-                double z, z2;
-                if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
-                const double g = gamma0 * (1.0 + z * gsig);                // :128
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    double diff = ta[k] - tb[k];
-                    double sc = diff * g;
-                    thp[k] = ti[k] + sc;
-                }
-                push_p<D>(pr, thp, x);
+                de_proposal<D>(th, a, b, g, thp);                          // :128
+                double xs[DISC ? D : 1];
+                const double* x = thp;
+                if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
                 double lp = prior_logpdf<D>(pr, x);                        // :134
                 if (!(lp < 0.0 && isinf(lp))) {                            // :135
-                    SimRng r(seed, pid, epoch, TAG_MODEL);
                     double blp[NB > 0 ? NB : 1];
-                    double dp = M::run(x, md.v, r, blp);                   // :137
+                    double dp;                                             // :137
+                    dp = M::run(x, md.v, r, blp);
                     nsim = 1; flag |= ABCDEZ_FLAG_SIM;                     // :138
+                    const double eps = c->eps; const int kind = c->kind;
                     double w = lp - lpi;                                   // :140-141, left to right
                     w = w + abck_logpdf(kind, eps, dp);
                     w = w - abck_logpdf(kind, eps, dli);
@@ -236,57 +292,55 @@ smc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj)
                         acc = (plog(u) < w);
                     }
                     if (acc) {                                             // :146-150
-                        dli = dp; lpi = lp;
+                        store_row<D>(P.theta[nxt], i, thp);
+                        P.logpi[nxt][i] = lp;
+                        P.delta[nxt][i] = dp;
 #pragma unroll
-                        for (int k = 0; k < D; ++k) ti[k] = thp[k];
-#pragma unroll
-                        for (int k = 0; k < NB; ++k) bl[k] = blp[k];
+                        for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = blp[k];
                         nacc = 1; flag |= ABCDEZ_FLAG_ACC;
                     }
                 }
             }
+            if ((uint8_t)nacc != mv) P.moved[i] = (uint8_t)nacc;
+            if (inj.flags) inj.flags[i] = flag;
         }
-        store_row<D>(P.theta[nxt], i, ti);
-        P.logpi[nxt][i] = lpi;
-        P.delta[nxt][i] = dli;
-#pragma unroll
-        for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = bl[k];
-        if (inj.flags) inj.flags[i] = flag;
-        kmin = kmax = f64_key(dli);
     }
-    sweep_block_reduce(c, nsim, nacc, kmin, kmax, err);
-    if (last_block(&c->acc.ticket[0], gridDim.x)) {
-        if (threadIdx.x == 0) ctrl_after_smc_sweep(P, c);
-    }
+    if (sweep_finish<false>(c, &s_red, nsim, nacc, 0ull, 0ull, err)) ctrl_after_smc_sweep(P, c);
 }
 
 // ---------------------------------------------------------------------------------------
 // abcdemc_swarm!  src/abcdez_mc.jl:5-61
 // ---------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(SWEEP_THREADS)
-mc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj, McArgs mc)
+template <class M, bool DISC>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+                const __grid_constant__ SweepInj inj, const __grid_constant__ McArgs mc)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
     const int cur = c->cur, nxt = cur ^ 1;
     const uint32_t N = P.N;
-    const double gamma0 = c->gamma0, gsig = c->gsig;
-    const uint64_t seed = c->seed;
-    const uint32_t epoch = c->sweep_epoch;
     const double* __restrict__ th = P.theta[cur];
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
 
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
-    unsigned long long kmin = ~0ull, kmax = 0ull;
+    unsigned long long kdl = 0ull;
     if (i < N) {
-        double ti[D], bl[NB > 0 ? NB : 1];
-        load_row<D>(th, i, ti);
-        double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) bl[k] = P.blob[cur][(size_t)i * NB + k];
+        double thp[D];
+        load_row<D>(th, i, thp);
+        const double lpi = P.logpi[cur][i];
+        double dli = P.delta[cur][i];
+        const uint8_t mv = P.moved[i];
+        if (mv) {                                                          // repair the stale row in g+1
+            store_row<D>(P.theta[nxt], i, thp);
+            copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
+        }
         uint8_t flag = 0;
         const uint32_t pid = P.id0 + i;
+        const uint64_t seed = c->seed;
+        const uint32_t epoch = c->sweep_epoch;
         uint32_t s = i;                                                    // :18
         const double eps = (dli <= mc.eps_target) ? mc.eps_target : mc.eps_pop;   // :19
         if (dli > eps) {                                                   // :20-24
@@ -323,21 +377,25 @@ mc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj, McArgs mc)
             }
         }
         if (!err) {
-            double tsr[D], ta[D], tb[D], thp[D], x[D];
-            load_row<D>(th, s, tsr);
-            load_row<D>(th, a, ta);
-            load_row<D>(th, b, tb);
             Stream ms(seed, pid, epoch, TAG_MOVE);
-            double z, z2;
-            if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
-            const double g = gamma0 * (1.0 + z * gsig);                    // :34
+            if (s != i) load_row<D>(th, s, thp);                           // base particle theta_s
+            {
+                double ta[D], tb[D];
+                load_row<D>(th, a, ta);
+                load_row<D>(th, b, tb);
+                double z, z2;
+                if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
+                const double g = c->gamma0 * (1.0 + z * c->gsig);          // :34
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                double diff = ta[k] - tb[k];
-                double sc = diff * g;
-                thp[k] = tsr[k] + sc;
+                for (int k = 0; k < D; ++k) {
+                    double diff = ta[k] - tb[k];
+                    double sc = diff * g;
+                    thp[k] = thp[k] + sc;
+                }
             }
-            push_p<D>(pr, thp, x);
+            double xs[DISC ? D : 1];
+            const double* x = thp;
+            if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
             double lp = prior_logpdf<D>(pr, x);                            // :41
             double w_prior = lp - lpi;                                     // :42 (logpi[i], not [s])
             double u, u2;
@@ -348,33 +406,27 @@ mc_sweep_kernel(PopDev P, PriorDev pr, ModelData md, SweepInj inj, McArgs mc)
                 double blp[NB > 0 ? NB : 1];
                 double dp = M::run(x, md.v, r, blp);                       // :45
                 if (dp <= fmax(eps, dli)) {                                // :54-59
-                    dli = dp; lpi = lp;
+                    store_row<D>(P.theta[nxt], i, thp);
+                    P.logpi[nxt][i] = lp;
+                    P.delta[nxt][i] = dp;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) ti[k] = thp[k];
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) bl[k] = blp[k];
+                    for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = blp[k];
+                    dli = dp;
                     nacc = 1; flag |= ABCDEZ_FLAG_ACC;
                 }
             }
         }
-        store_row<D>(P.theta[nxt], i, ti);
-        P.logpi[nxt][i] = lpi;
-        P.delta[nxt][i] = dli;
-#pragma unroll
-        for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = bl[k];
+        if ((uint8_t)nacc != mv) P.moved[i] = (uint8_t)nacc;
         if (inj.flags) inj.flags[i] = flag;
-        kmin = kmax = f64_key(dli);
+        kdl = f64_key(dli);                                                // extrema(delta), src/abcdez_mc.jl:146
     }
-    sweep_block_reduce(c, nsim, nacc, kmin, kmax, err);
-    if (last_block(&c->acc.ticket[0], gridDim.x)) {
-        if (threadIdx.x == 0) ctrl_after_mc_sweep(c);
-    }
+    if (sweep_finish<true>(c, &s_red, nsim, nacc, i < N ? kdl : ~0ull, i < N ? kdl : 0ull, err)) ctrl_after_mc_sweep(c);
 }
 
 // one dist! evaluation per row (stage-level model parity); dense N x D input
 template <class M>
 __global__ void __launch_bounds__(SWEEP_THREADS)
-simulate_kernel(ModelData md, int64_t N, const double* __restrict__ theta_pushed, uint64_t seed,
+simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, uint64_t seed,
                 uint32_t epoch, uint32_t tag, uint32_t id0, double* __restrict__ dist, double* __restrict__ blobs)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
@@ -396,6 +448,14 @@ simulate_kernel(ModelData md, int64_t N, const double* __restrict__ theta_pushed
 // ---------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t N, int threads) { return (unsigned)((N + threads - 1) / threads); }
 
+template <int D>
+static inline bool prior_has_discrete(const PriorDev& pr)
+{
+    bool disc = false;
+    for (int k = 0; k < D; ++k) disc = disc || fam_is_discrete(pr.family[k]);
+    return disc;
+}
+
 template <class M>
 static void l_init(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
@@ -404,13 +464,19 @@ static void l_init(cudaStream_t st, const PopDev& P, const PriorDev& pr, const M
 template <class M>
 static void l_smc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
 {
-    smc_sweep_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    if (prior_has_discrete<M::D>(pr))
+        smc_sweep_kernel<M, true><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    else
+        smc_sweep_kernel<M, false><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
 }
 template <class M>
 static void l_mc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
                  const McArgs& mc)
 {
-    mc_sweep_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj, mc);
+    if (prior_has_discrete<M::D>(pr))
+        mc_sweep_kernel<M, true><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj, mc);
+    else
+        mc_sweep_kernel<M, false><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj, mc);
 }
 template <class M>
 static void l_sim(cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
@@ -418,7 +484,6 @@ static void l_sim(cudaStream_t st, const PriorDev*, const ModelData& md, int64_t
 {
     simulate_kernel<M><<<grid_for(N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(md, N, th, seed, epoch, tag, id0, dist, blobs);
 }
-
 
 template <class M>
 static ModelOps make_ops()

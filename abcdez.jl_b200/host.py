@@ -20,7 +20,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libabcdez_cuda.so")
+LIB_PATH = os.environ.get("ABCDEZ_LIB", os.path.join(_HERE, "libabcdez_cuda.so"))
 
 # status codes, include/abcdez_cuda.h
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_NAN_DISTANCE, ERR_NO_ALIVE, ERR_INIT_RETRY, ERR_PARTNER_RETRY, ERR_NCCL, \

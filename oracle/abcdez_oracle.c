@@ -85,7 +85,7 @@ void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 /* ------------------------------------------------------------------ */
 /* Portable math contract (DESIGN.md "Numerics"): log, exp, lgamma and  */
 /* sin/cos(2 pi u) defined operation by operation in IEEE-754 binary64  */
-/* with +,-,*,/ only (no FMA contraction).  The differential-evolution  */
+/* with +,-,*,/ and explicit fma() in the Horner steps (no implicit contraction).  The differential-evolution  */
 /* move amplifies a 1-ulp perturbation of theta by ~2.6x per accepted   */
 /* move, so two implementations whose libm differ in the last bit       */
 /* diverge within ~10 SMC iterations; with these definitions the CUDA   */
@@ -117,16 +117,16 @@ static inline double plog(double x)
     double z = s * s;
     /* log(m) = 2 atanh(s) = 2s + s*z*(2/3 + z*(2/5 + ... + z*2/23)) */
     double p = 2.0 / 23.0;
-    p = p * z + 2.0 / 21.0;
-    p = p * z + 2.0 / 19.0;
-    p = p * z + 2.0 / 17.0;
-    p = p * z + 2.0 / 15.0;
-    p = p * z + 2.0 / 13.0;
-    p = p * z + 2.0 / 11.0;
-    p = p * z + 2.0 / 9.0;
-    p = p * z + 2.0 / 7.0;
-    p = p * z + 2.0 / 5.0;
-    p = p * z + 2.0 / 3.0;
+    p = fma(p, z, 2.0 / 21.0);
+    p = fma(p, z, 2.0 / 19.0);
+    p = fma(p, z, 2.0 / 17.0);
+    p = fma(p, z, 2.0 / 15.0);
+    p = fma(p, z, 2.0 / 13.0);
+    p = fma(p, z, 2.0 / 11.0);
+    p = fma(p, z, 2.0 / 9.0);
+    p = fma(p, z, 2.0 / 7.0);
+    p = fma(p, z, 2.0 / 5.0);
+    p = fma(p, z, 2.0 / 3.0);
     double r = (s * z) * p;
     double lm = 2.0 * s + r;
     return ((double)e * PM_LN2_HI + lm) + (double)e * PM_LN2_LO;
@@ -140,19 +140,19 @@ static inline double pexp(double x)
     double k = floor(x * PM_INV_LN2 + 0.5);
     double r = (x - k * PM_LN2_HI) - k * PM_LN2_LO;
     double p = 1.0 / 6227020800.0;            /* 1/13! */
-    p = p * r + 1.0 / 479001600.0;
-    p = p * r + 1.0 / 39916800.0;
-    p = p * r + 1.0 / 3628800.0;
-    p = p * r + 1.0 / 362880.0;
-    p = p * r + 1.0 / 40320.0;
-    p = p * r + 1.0 / 5040.0;
-    p = p * r + 1.0 / 720.0;
-    p = p * r + 1.0 / 120.0;
-    p = p * r + 1.0 / 24.0;
-    p = p * r + 1.0 / 6.0;
-    p = p * r + 0.5;
-    p = p * r + 1.0;
-    p = p * r + 1.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
     /* scale by 2^k in two exact steps (k in [-1075, 1024]) */
     int ki = (int)k, k1 = ki / 2, k2 = ki - k1;
     uint64_t b1 = (uint64_t)(k1 + 1023) << 52, b2 = (uint64_t)(k2 + 1023) << 52;
@@ -168,23 +168,23 @@ static inline void psincos2pi(double u, double* sn, double* cs)
     double x = r * PM_TWO_PI;
     double x2 = x * x;
     double ps = -1.0 / 355687428096000.0;      /* -1/17! */
-    ps = ps * x2 + 1.0 / 1307674368000.0;
-    ps = ps * x2 - 1.0 / 6227020800.0;
-    ps = ps * x2 + 1.0 / 39916800.0;
-    ps = ps * x2 - 1.0 / 362880.0;
-    ps = ps * x2 + 1.0 / 5040.0;
-    ps = ps * x2 - 1.0 / 120.0;
-    ps = ps * x2 + 1.0 / 6.0;
+    ps = fma(ps, x2, 1.0 / 1307674368000.0);
+    ps = fma(ps, x2, -(1.0 / 6227020800.0));
+    ps = fma(ps, x2, 1.0 / 39916800.0);
+    ps = fma(ps, x2, -(1.0 / 362880.0));
+    ps = fma(ps, x2, 1.0 / 5040.0);
+    ps = fma(ps, x2, -(1.0 / 120.0));
+    ps = fma(ps, x2, 1.0 / 6.0);
     double s = x - x * (x2 * ps);
     double pc = 1.0 / 6402373705728000.0;      /* 1/18! */
-    pc = pc * x2 - 1.0 / 20922789888000.0;
-    pc = pc * x2 + 1.0 / 87178291200.0;
-    pc = pc * x2 - 1.0 / 479001600.0;
-    pc = pc * x2 + 1.0 / 3628800.0;
-    pc = pc * x2 - 1.0 / 40320.0;
-    pc = pc * x2 + 1.0 / 720.0;
-    pc = pc * x2 - 1.0 / 24.0;
-    pc = pc * x2 + 0.5;
+    pc = fma(pc, x2, -(1.0 / 20922789888000.0));
+    pc = fma(pc, x2, 1.0 / 87178291200.0);
+    pc = fma(pc, x2, -(1.0 / 479001600.0));
+    pc = fma(pc, x2, 1.0 / 3628800.0);
+    pc = fma(pc, x2, -(1.0 / 40320.0));
+    pc = fma(pc, x2, 1.0 / 720.0);
+    pc = fma(pc, x2, -(1.0 / 24.0));
+    pc = fma(pc, x2, 0.5);
     double c = 1.0 - x2 * pc;
     int k = (int)q & 3;
     if (k == 0) { *sn = s; *cs = c; }
@@ -202,11 +202,11 @@ static inline double plgamma(double z)
     while (z < 10.0) { prod = prod * z; z = z + 1.0; }
     double zi = 1.0 / z, z2 = zi * zi;
     double t = -691.0 / 360360.0;
-    t = t * z2 + 1.0 / 1188.0;
-    t = t * z2 - 1.0 / 1680.0;
-    t = t * z2 + 1.0 / 1260.0;
-    t = t * z2 - 1.0 / 360.0;
-    t = t * z2 + 1.0 / 12.0;
+    t = fma(t, z2, 1.0 / 1188.0);
+    t = fma(t, z2, -(1.0 / 1680.0));
+    t = fma(t, z2, 1.0 / 1260.0);
+    t = fma(t, z2, -(1.0 / 360.0));
+    t = fma(t, z2, 1.0 / 12.0);
     double st = ((z - 0.5) * plog(z) - z) + PM_HALF_LOG_2PI + t * zi;
     return st - plog(prod);
 }
