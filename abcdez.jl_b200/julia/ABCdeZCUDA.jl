@@ -1,0 +1,236 @@
+# ABCdeZCUDA.jl -- thin `ccall` shim that keeps the ABCdeZ.jl user interface
+# (`abcdesmc!`, `abcdemc!`, `Factored`, the ABC kernels; reference src/ABCdeZ.jl:1-20) and runs the
+# particle hot path in libabcdez_cuda.so (include/abcdez_cuda.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no `julia`.  It is a mechanical mirror of
+# the ctypes binding in ../host.py (same symbols, same struct layouts, same defaults and messages);
+# every executable check goes through that binding.  See INTEGRATION.md.
+#
+# Usage (drop-in for the reference, except that `dist!` is a registered device functor):
+#
+#   using ABCdeZCUDA, Distributions
+#   prior = Normal(0, sqrt(10))
+#   dist! = DeviceModel("gauss1d", [3.0, 1.0])        # instead of a Julia closure
+#   r = abcdesmc!(prior, dist!, 0.3, nothing, nparticles=1000)
+#   evidence = exp(r.logZ)
+module ABCdeZCUDA
+
+using Distributions
+using Random
+
+export Factored, abcdesmc!, abcdemc!, DeviceModel
+export Indicator0toϵ, IndicatorStrict0toϵ, Epa0toϵ, EpaStrict0toϵ
+
+const LIB = get(ENV, "ABCDEZ_LIB", joinpath(@__DIR__, "..", "libabcdez_cuda.so"))
+
+# ---- status / errors (include/abcdez_cuda.h: every export returns an int status) -----------------
+const ABCDEZ_OK = Cint(0)
+const ABCDEZ_ERR_NO_ALIVE = Cint(4)
+
+last_error() = unsafe_string(ccall((:abcdez_last_error, LIB), Cstring, ()))
+check(rc::Integer) = rc == ABCDEZ_OK ? nothing : error(last_error())     # reference: error("...") -> ErrorException
+
+# ---- Factored, reference src/abcdez_priors.jl:18-61 -----------------------------------------------
+struct Factored{N} <: Distribution{Multivariate, Continuous}
+    p::NTuple{N, UnivariateDistribution}
+    Factored(args::UnivariateDistribution...) = new{length(args)}(args)
+end
+Base.length(::Factored{N}) where {N} = N
+
+# (family, params) of a marginal; families of include/abcdez_cuda.h
+marginal(d::Normal) = (Cint(0), (d.μ, d.σ, 0.0, 0.0))
+marginal(d::Uniform) = (Cint(1), (d.a, d.b, 0.0, 0.0))
+marginal(d::DiscreteUniform) = (Cint(2), (Float64(d.a), Float64(d.b), 0.0, 0.0))
+marginal(d::LogNormal) = (Cint(3), (d.μ, d.σ, 0.0, 0.0))
+marginal(d::Exponential) = (Cint(4), (d.θ, 0.0, 0.0, 0.0))
+marginal(d::Gamma) = (Cint(5), (d.α, d.θ, 0.0, 0.0))
+marginal(d::Beta) = (Cint(6), (d.α, d.β, 0.0, 0.0))
+marginal(d::NegativeBinomial) = (Cint(7), (d.r, d.p, 0.0, 0.0))
+marginal(d) = error("ABCdeZCUDA: unsupported prior marginal $(typeof(d))")
+
+marginals(p::Factored) = collect(p.p)
+marginals(p::UnivariateDistribution) = [p]          # bare univariate prior: d = 1, scalar θ (examples/minimal_example.jl:17)
+
+# ---- ABC kernels, reference src/abcdez_types.jl:26-73 (type objects select the kernel enum) -------
+for (name, kind, strict, epa) in ((:Indicator0toϵ, 0, false, false), (:IndicatorStrict0toϵ, 1, true, false),
+                                  (:Epa0toϵ, 2, false, true), (:EpaStrict0toϵ, 3, true, true))
+    @eval begin
+        struct $name <: ContinuousUnivariateDistribution
+            ϵ::Float64
+            function $name(ϵ)
+                ϵ ≥ 0.0 || error("Expected ϵ ≥ 0.0")
+                new(ϵ)
+            end
+        end
+        kernel_kind(::Type{$name}) = Cint($kind)
+        Distributions.pdf(d::$name, x::Real) = ccall((:abcdez_kernel_pdf, LIB), Cdouble, (Cint, Cdouble, Cdouble), $kind, d.ϵ, x)
+        Distributions.logpdf(d::$name, x::Real) = ccall((:abcdez_kernel_logpdf, LIB), Cdouble, (Cint, Cdouble, Cdouble), $kind, d.ϵ, x)
+    end
+end
+
+# ---- handles ---------------------------------------------------------------------------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:abcdez_init, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, r))
+        c = new(r[])
+        finalizer(x -> ccall((:abcdez_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+        c
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
+default_context() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Context(parse(Int, get(ENV, "LOCAL_RANK", "0")))); DEFAULT_CTX[])
+
+"`dist!` as a registered device functor bound to observed data (the data a Julia closure would capture)."
+struct DeviceModel
+    name::String
+    data::Vector{Float64}
+end
+
+function prior_handle(ctx::Context, prior)
+    ms = marginals(prior)
+    fam = Cint[marginal(m)[1] for m in ms]
+    par = zeros(Float64, 4, length(ms))                 # column-major 4 x d == C's d x 4 rows
+    for (k, m) in enumerate(ms); par[:, k] .= marginal(m)[2]; end
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abcdez_prior_create, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                ctx.h, length(ms), fam, par, r))
+    r[]
+end
+
+function model_handle(ctx::Context, m::DeviceModel)
+    id = Ref{Cint}(0)
+    check(ccall((:abcdez_model_lookup, LIB), Cint, (Cstring, Ref{Cint}), m.name, id))
+    d = Ref{Cint}(0); b = Ref{Cint}(0)
+    check(ccall((:abcdez_model_info, LIB), Cint, (Cint, Ref{Cint}, Ref{Cint}), id[], d, b))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abcdez_model_bind, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Csize_t, Ref{Ptr{Cvoid}}),
+                ctx.h, id[], m.data, length(m.data), r))
+    r[], Int(d[]), Int(b[])
+end
+
+# ---- C structs (field order == include/abcdez_cuda.h) ----------------------------------------------
+mutable struct SmcOpts
+    nparticles::Int64; alpha::Cdouble; delta_ess::Cdouble; nsims_max::Int64; Kmcmc::Int32
+    Kmcmc_min::Cdouble; kernel::Int32; facc_stop::Cdouble; facc_min::Cdouble; facc_tune::Cdouble
+    seed::UInt64; verboseout::Int32; max_iters::Int32; exact_scan::Int32; profile::Int32; sync_every::Int32
+    fused_head::Int32
+    SmcOpts() = new()
+end
+
+mutable struct SmcResult
+    P::Ptr{Cdouble}; Wns::Ptr{Cdouble}; C::Ptr{Cdouble}; blobs::Ptr{UInt8}
+    hist_cap::Int32
+    h_eps::Ptr{Cdouble}; h_dmin::Ptr{Cdouble}; h_dmax::Ptr{Cdouble}; h_logZ::Ptr{Cdouble}; h_ess::Ptr{Cdouble}
+    h_facc::Ptr{Cdouble}; h_gamma0::Ptr{Cdouble}; h_Kmcmc::Ptr{Int32}
+    eps::Cdouble; logZ::Cdouble; iters::Int64; nsims::Int64; hist_len::Int32; status::Int32
+    n_resamples::Int64; n_sweeps::Int64; n_launches::Int64; sweep_ms::Cdouble; total_ms::Cdouble; init_ms::Cdouble
+    SmcResult() = new()
+end
+
+mutable struct McOpts
+    nparticles::Int64; generations::Int32; seed::UInt64
+end
+
+mutable struct McResult
+    P::Ptr{Cdouble}; C::Ptr{Cdouble}; blobs::Ptr{UInt8}; reached_eps::Int32; nsims::Int64
+    dmin::Cdouble; dmax::Cdouble; sweep_ms::Cdouble; total_ms::Cdouble; n_launches::Int64
+    McResult() = new()
+end
+
+seed_from(rng::AbstractRNG) = rand(rng, UInt64)       # `rng` -> the 64-bit Philox key
+seed_from(s::Integer) = UInt64(s)
+
+# P as the reference returns it (src/abcdez_smc.jl:382): a Vector of tuples (Factored) or scalars (univariate),
+# with discrete coordinates as Int (push_p, src/abcdez_types.jl:20-23)
+function particles(prior, P::Matrix{Float64})
+    ms = marginals(prior)
+    conv(m, x) = m isa DiscreteDistribution ? round(Int, x) : x
+    prior isa Factored ? [ntuple(k -> conv(ms[k], P[k, i]), length(ms)) for i in axes(P, 2)] :
+                         [conv(ms[1], P[1, i]) for i in axes(P, 2)]
+end
+
+blobs_out(raw::Matrix{UInt8}, B::Int) = B == 0 ? fill(nothing, size(raw, 2)) : [raw[1:B, i] for i in axes(raw, 2)]
+
+"""
+    abcdesmc!(prior, dist!, ϵ_target, varexternal; kwargs...)
+
+Same positional arguments, keyword names and defaults as the reference (src/abcdez_smc.jl:215-220).
+`dist!` is a `DeviceModel`; `varexternal` is accepted and ignored (device functors keep their scratch
+in registers); `parallel` is ignored (the GPU path is always parallel).
+"""
+function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
+                   nparticles::Int=100, α=0.95, δess=0.5, nsims_max::Int=10^7, Kmcmc::Int=3, Kmcmc_min=1.0,
+                   ABCk=IndicatorStrict0toϵ, facc_stop=0.0, facc_min=0.0, facc_tune=0.975,
+                   verbose::Bool=true, verboseout::Bool=true, rng=Random.default_rng(), parallel::Bool=false,
+                   ctx::Context=default_context(), hist_cap::Int=8192)
+    Kmcmc_min > facc_min || @warn("Kmcmc_min should be larger than facc_min")         # src/abcdez_smc.jl:232
+    ph = prior_handle(ctx, prior)
+    mh, d, B = model_handle(ctx, dist!)
+    o = SmcOpts()
+    ccall((:abcdez_smc_opts_default, LIB), Cvoid, (Ref{SmcOpts},), o)
+    o.nparticles = nparticles; o.alpha = α; o.delta_ess = δess; o.nsims_max = nsims_max; o.Kmcmc = Kmcmc
+    o.Kmcmc_min = Kmcmc_min; o.kernel = kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
+    o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout
+    N = nparticles
+    P = Matrix{Float64}(undef, d, N); Wns = Vector{Float64}(undef, N); C = Vector{Float64}(undef, N)
+    bl = zeros(UInt8, max(B, 1), N)
+    h = [zeros(Float64, hist_cap) for _ in 1:7]; hK = zeros(Int32, hist_cap)
+    r = SmcResult()
+    GC.@preserve P Wns C bl h hK begin
+        r.P = pointer(P); r.Wns = pointer(Wns); r.C = pointer(C); r.blobs = pointer(bl)
+        r.hist_cap = verboseout ? hist_cap : 0
+        r.h_eps, r.h_dmin, r.h_dmax, r.h_logZ, r.h_ess, r.h_facc, r.h_gamma0 = pointer.(h)
+        r.h_Kmcmc = pointer(hK)
+        # argument errors come back with the reference's messages (src/abcdez_smc.jl:223-235)
+        check(ccall((:abcdez_smc_run, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{SmcOpts}, Ref{SmcResult}),
+                    ctx.h, ph, mh, ϵ_target, o, r))
+    end
+    ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph); ccall((:abcdez_model_destroy, LIB), Cint, (Ptr{Cvoid},), mh)
+    r.status == ABCDEZ_ERR_NO_ALIVE && @warn("No alive particles")                      # src/abcdez_smc.jl:375
+    verbose && (@info "Final run:" iteration = r.iters nsim = r.nsims ϵ = r.eps logZ = r.logZ)
+    θs = particles(prior, P); blobs = blobs_out(bl, B)
+    if verboseout                                                                       # src/abcdez_smc.jl:388-393
+        n = r.hist_len
+        (P = θs, Wns = Wns, C = C, ϵ = r.eps, logZ = r.logZ, blobs = blobs,
+         ϵs = h[1][1:n], ranges_ϵ = collect(zip(h[2][1:n], h[3][1:n])), logZs = h[4][1:n], esss = h[5][1:n],
+         faccs = h[6][1:n], γ0s = h[7][1:n], Kmcmcs = Int.(hK[1:n]))
+    else
+        (P = θs, Wns = Wns, C = C, ϵ = r.eps, logZ = r.logZ, blobs = blobs)
+    end
+end
+
+"""
+    abcdemc!(prior, dist!, ϵ_target, varexternal; nparticles=50, generations=20, verbose=true, rng, parallel=false)
+
+Reference: src/abcdez_mc.jl:102-172.
+"""
+function abcdemc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
+                  nparticles::Int=50, generations::Int=20, verbose=true, rng=Random.default_rng(),
+                  parallel::Bool=false, ctx::Context=default_context())
+    ph = prior_handle(ctx, prior)
+    mh, d, B = model_handle(ctx, dist!)
+    o = McOpts(nparticles, generations, seed_from(rng))
+    N = nparticles
+    P = Matrix{Float64}(undef, d, N); C = Vector{Float64}(undef, N); bl = zeros(UInt8, max(B, 1), N)
+    r = McResult()
+    GC.@preserve P C bl begin
+        r.P = pointer(P); r.C = pointer(C); r.blobs = pointer(bl)
+        check(ccall((:abcdez_mc_run, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{McOpts}, Ref{McResult}),
+                    ctx.h, ph, mh, ϵ_target, o, r))
+    end
+    ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph); ccall((:abcdez_model_destroy, LIB), Cint, (Ptr{Cvoid},), mh)
+    verbose && (@info "End:" converged = r.reached_eps != 0 nsim = r.nsims range_ϵ = (r.dmin, r.dmax))
+    (P = particles(prior, P), C = C, reached_ϵ = r.reached_eps != 0, blobs = blobs_out(bl, B))   # src/abcdez_mc.jl:171
+end
+
+# `ABCdeZ.wsample_stratified!(rng, weights, inds)` (src/abcdez_smc.jl:15-56; used by test/runtests.jl:13-19)
+function wsample_stratified!(rng::AbstractRNG, weights::Vector{Float64}, inds::Vector{Int}; ctx::Context=default_context())
+    u = rand(rng, length(weights))
+    check(ccall((:abcdez_wsample_stratified, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Int64}),
+                ctx.h, length(weights), weights, u, 2, inds))
+    inds
+end
+
+end # module
