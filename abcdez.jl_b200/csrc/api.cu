@@ -3,6 +3,8 @@
 // two run loops abcdez_smc_run (abcdesmc!, src/abcdez_smc.jl:215-394 of the reference) and
 // abcdez_mc_run (abcdemc!, src/abcdez_mc.jl:102-172).
 #include "internal.h"
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +78,8 @@ extern "C" int abcdez_destroy(abcdez_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->h_ctrl_pool) cudaFreeHost(ctx->h_ctrl_pool);
     delete ctx;
     return ABCDEZ_OK;
 }
@@ -268,11 +272,7 @@ static int pull_ctrl(abcdez_pop* pop)
 static int ensure_scratch(abcdez_pop* pop, size_t bytes)
 {
     if (bytes <= pop->scratch_bytes) return ABCDEZ_OK;
-    if (pop->scratch) cudaFree(pop->scratch);
-    pop->scratch = nullptr; pop->scratch_bytes = 0;
-    CU(cudaMalloc(&pop->scratch, bytes));
-    pop->scratch_bytes = bytes;
-    return ABCDEZ_OK;
+    return fail(ABCDEZ_ERR_BAD_ARG, "internal: population scratch too small");   // sized for every caller in pop_create_impl
 }
 
 extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
@@ -280,15 +280,17 @@ extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
     if (!pop) return ABCDEZ_OK;
     cudaSetDevice(pop->ctx->device);
     cudaStreamSynchronize(pop->ctx->stream);
-    PopDev& P = pop->dev;
-    for (int b = 0; b < 2; ++b) { cudaFree(P.theta[b]); cudaFree(P.logpi[b]); cudaFree(P.delta[b]); cudaFree(P.blob[b]); }
-    cudaFree(P.W); cudaFree(P.alive); cudaFree(P.moved); cudaFree(P.alive_list); cudaFree(P.ctrl); cudaFree(P.partial);
-    cudaFree(P.tile_cnt); cudaFree(P.sel_hist); cudaFree(P.cumsum); cudaFree(P.inds); cudaFree(P.hist); cudaFree(P.tabs);
-    if (pop->scratch) cudaFree(pop->scratch);
+    if (pop->slab) {
+        if (pop->slab_from_arena) pop->ctx->arena_busy = false;     // the slab stays with the context
+        else cudaFree(pop->slab);
+    }
     if (pop->sorted_delta) cudaFree(pop->sorted_delta);
     if (pop->order) cudaFree(pop->order);
     if (pop->sort_tmp) cudaFree(pop->sort_tmp);
-    if (pop->h_ctrl) cudaFreeHost(pop->h_ctrl);
+    if (pop->h_ctrl) {
+        if (pop->h_ctrl_from_pool) pop->ctx->h_ctrl_busy = false;
+        else cudaFreeHost(pop->h_ctrl);
+    }
     if (pop->ev0) cudaEventDestroy(pop->ev0);
     if (pop->ev1) cudaEventDestroy(pop->ev1);
     delete pop;
@@ -312,24 +314,60 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     PopDev& P = pop->dev;
     P.N = (uint32_t)N; P.id0 = (uint32_t)id0; P.ntiles = (uint32_t)((N + TILE - 1) / TILE);
     size_t n = (size_t)N;
-#define ALLOC(ptr, bytes)                                                                          \
-    do {                                                                                           \
-        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes) ? (bytes) : 8);                        \
-        if (e_ != cudaSuccess) { abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); } \
-    } while (0)
-    for (int b = 0; b < 2; ++b) {
-        ALLOC(P.theta[b], n * pop->DS * 8); ALLOC(P.logpi[b], n * 8); ALLOC(P.delta[b], n * 8);
-        ALLOC(P.blob[b], n * pop->NB * 8);
+    // one slab for every device array of the population (256-byte aligned pieces), carved from the
+    // context arena when it is free, else from a private allocation
+    struct Piece { void** ptr; size_t bytes; };
+    const size_t scratch_need = std::max((size_t)29 * n + 64, n * (size_t)pop->D * 8);
+    Piece pieces[] = {
+        { (void**)&P.theta[0], n * pop->DS * 8 }, { (void**)&P.theta[1], n * pop->DS * 8 },
+        { (void**)&P.logpi[0], n * 8 }, { (void**)&P.logpi[1], n * 8 },
+        { (void**)&P.delta[0], n * 8 }, { (void**)&P.delta[1], n * 8 },
+        { (void**)&P.blob[0], n * pop->NB * 8 }, { (void**)&P.blob[1], n * pop->NB * 8 },
+        { (void**)&P.W, n * 8 }, { (void**)&P.alive, n + 4 }, { (void**)&P.moved, n + 4 },
+        { (void**)&P.alive_list, n * 4 }, { (void**)&P.ctrl, sizeof(Ctrl) },
+        { (void**)&P.partial, (size_t)P.ntiles * 2 * 8 + 64 }, { (void**)&P.tile_cnt, (size_t)P.ntiles * 4 + 64 },
+        { (void**)&P.sel_hist, 6 * SEL_BINS * 4 }, { (void**)&P.cumsum, n * 8 }, { (void**)&P.inds, n * 4 },
+        { (void**)&P.hist, (size_t)(hist_cap > 0 ? hist_cap : 1) * 8 * 8 }, { (void**)&P.tabs, 2 * sizeof(SeqTab) },
+        { (void**)&pop->scratch, scratch_need },
+    };
+    size_t total = 0;
+    for (const Piece& pc : pieces) total += (pc.bytes + 255) & ~(size_t)255;
+    if (!ctx->arena_busy) {
+        if (ctx->arena_bytes < total) {
+            if (ctx->arena) cudaFree(ctx->arena);
+            ctx->arena = nullptr; ctx->arena_bytes = 0;
+            cudaError_t e_ = cudaMalloc((void**)&ctx->arena, total);
+            if (e_ != cudaSuccess) { delete pop; return fail(ABCDEZ_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); }
+            ctx->arena_bytes = total;
+        }
+        pop->slab = ctx->arena; pop->slab_from_arena = true; ctx->arena_busy = true;
+    } else {
+        cudaError_t e_ = cudaMalloc((void**)&pop->slab, total);
+        if (e_ != cudaSuccess) { delete pop; return fail(ABCDEZ_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); }
+        pop->slab_from_arena = false;
     }
-    ALLOC(P.W, n * 8); ALLOC(P.alive, n + 4); ALLOC(P.moved, n + 4); ALLOC(P.alive_list, n * 4); ALLOC(P.ctrl, sizeof(Ctrl));
-    ALLOC(P.partial, (size_t)P.ntiles * 2 * 8 + 64); ALLOC(P.tile_cnt, (size_t)P.ntiles * 4 + 64);
-    ALLOC(P.sel_hist, SEL_BINS * 4); ALLOC(P.cumsum, n * 8); ALLOC(P.inds, n * 4);
-    ALLOC(P.hist, (size_t)(hist_cap > 0 ? hist_cap : 1) * 8 * 8); ALLOC(P.tabs, 2 * sizeof(SeqTab));
-#undef ALLOC
-    CU(cudaMallocHost((void**)&pop->h_ctrl, sizeof(Ctrl)));
-    CU(cudaEventCreate(&pop->ev0)); CU(cudaEventCreate(&pop->ev1));
+    pop->slab_bytes = total;
+    {
+        size_t off = 0;
+        for (const Piece& pc : pieces) { *pc.ptr = pop->slab + off; off += (pc.bytes + 255) & ~(size_t)255; }
+    }
+    pop->scratch_bytes = scratch_need;
+    P.cand[0] = reinterpret_cast<unsigned long long*>(P.cumsum);
+    P.cand[1] = reinterpret_cast<unsigned long long*>(pop->scratch);
+    if (!ctx->h_ctrl_busy) {
+        if (!ctx->h_ctrl_pool) {
+            cudaError_t e_ = cudaMallocHost((void**)&ctx->h_ctrl_pool, sizeof(Ctrl));
+            if (e_ != cudaSuccess) { abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e_)); }
+        }
+        pop->h_ctrl = ctx->h_ctrl_pool; pop->h_ctrl_from_pool = true; ctx->h_ctrl_busy = true;
+    } else {
+        cudaError_t e_ = cudaMallocHost((void**)&pop->h_ctrl, sizeof(Ctrl));
+        if (e_ != cudaSuccess) { pop->h_ctrl = nullptr; abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e_)); }
+        pop->h_ctrl_from_pool = false;
+    }
+    CU(cudaEventCreateWithFlags(&pop->ev0, cudaEventDefault)); CU(cudaEventCreateWithFlags(&pop->ev1, cudaEventDefault));
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(P.sel_hist, 0, SEL_BINS * 4, st));
+    CU(cudaMemsetAsync(P.sel_hist, 0, 6 * SEL_BINS * 4, st));
     CU(cudaMemsetAsync(P.alive, 1, n, st));
     CU(cudaMemsetAsync(P.moved, 1, n, st));
     CU(cudaMemsetAsync(P.theta[0], 0, n * pop->DS * 8, st));
@@ -344,6 +382,8 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     c->N = (uint32_t)N; c->n_alive = (uint32_t)N; c->ess_min = 0.5 * (double)N;
     c->hist_cap = hist_cap;
     c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull; c->acc.min_gt_key = ~0ull;
+    for (int q = 0; q < 6; ++q) { c->acc.cand_min[q] = ~0ull; c->acc.cand_max[q] = 0ull; }
+    c->acc.min_above = ~0ull;
     c->acc.w_alive = 1.0 / (double)N;
     int rc = push_ctrl(pop);
     if (rc) { abcdez_pop_destroy(pop); return rc; }
@@ -618,6 +658,45 @@ extern "C" int abcdez_pop_reweight(abcdez_pop* pop, double eps_new, double* wnor
     return ABCDEZ_OK;
 }
 
+// the fused head of one iteration (head.cu): eps quantile + clamp, reweight, ESS, alive list
+extern "C" int abcdez_pop_head(abcdez_pop* pop, double alpha, double eps_target, double* q, double* eps,
+                               double* wnorm, double* ess, int64_t* n_alive)
+{
+    CHECK_ARG(pop != nullptr, "abcdez_pop_head: pop is NULL");
+    CHECK_ARG(alpha >= 0.0 && alpha <= 1.0, "abcdez_pop_head: alpha out of [0,1]");
+    CU(cudaSetDevice(pop->ctx->device));
+    int rc = pull_ctrl(pop); if (rc) return rc;
+    Ctrl* c = pop->h_ctrl;
+    CHECK_ARG(c->n_alive >= 1, "abcdez_pop_head: no alive particles");
+    c->alpha = alpha; c->eps_target = eps_target; c->stop = 0; c->err = 0; c->acc.err = 0;
+    c->ess_min = -1.0;                                      // stage call: never triggers the resample flag
+    {   // host-side select_setup (same arithmetic as ctrl.cuh)
+        unsigned long long n = c->n_alive;
+        double m = 1.0 - alpha, aleph = fma((double)n, alpha, m);
+        long long j = (long long)trunc(aleph);
+        if (j > (long long)n - 1) j = (long long)n - 1;
+        if (j < 1) j = 1;
+        double g = aleph - (double)j; g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+        c->sel_j = (unsigned long long)j; c->sel_rank = (unsigned long long)(j - 1); c->sel_prefix = 0; c->q_gamma = g;
+    }
+    rc = push_ctrl(pop); if (rc) return rc;
+    TIME_BEGIN(pop);
+    int nl = launch_head(pop->ctx->stream, pop->dev, pop->ctx->sm_count);
+    CU(cudaGetLastError());
+    TIME_END(pop, nl);
+    rc = pull_ctrl(pop); if (rc) return rc;
+    if (q) *q = c->q;
+    if (eps) *eps = c->eps;
+    if (wnorm) *wnorm = c->wnorm;
+    if (ess) *ess = c->ess;
+    if (n_alive) *n_alive = c->n_alive;
+    rc = check_dev_err(pop, "abcdez_pop_head");
+    c->eps_k = c->eps;                                      // src/abcdez_smc.jl:360
+    int rc2 = push_ctrl(pop); if (rc2) return rc2;
+    CU(cudaStreamSynchronize(pop->ctx->stream));
+    return rc;
+}
+
 extern "C" int abcdez_pop_resample(abcdez_pop* pop, const double* uniforms, uint32_t epoch, int mode, int32_t* inds_out)
 {
     CHECK_ARG(pop != nullptr, "abcdez_pop_resample: pop is NULL");
@@ -706,7 +785,7 @@ extern "C" void abcdez_smc_opts_default(abcdez_smc_opts* o)
     o->nparticles = 100; o->alpha = 0.95; o->delta_ess = 0.5; o->nsims_max = 10000000; o->Kmcmc = 3;
     o->Kmcmc_min = 1.0; o->kernel = ABCDEZ_INDICATOR_STRICT; o->facc_stop = 0.0; o->facc_min = 0.0;
     o->facc_tune = 0.975; o->seed = 1; o->verboseout = 1; o->max_iters = 0; o->exact_scan = 0; o->profile = 0;
-    o->sync_every = 1;
+    o->sync_every = 1; o->fused_head = 1;
 }
 
 extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
@@ -733,12 +812,19 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         }
     }
     CU(cudaSetDevice(ctx->device));
+    static const bool trace = getenv("ABCDEZ_TRACE") != nullptr;     // host-side phase timings on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    auto t_begin = now();
+    double t_create = 0.0, t_loop = 0.0, t_result = 0.0;
     const int64_t N = o->nparticles;
     int hist_cap = o->verboseout ? (res->hist_cap > 0 ? res->hist_cap : 0) : 0;
     int dev_hist = hist_cap > 0 ? hist_cap : 1;
     abcdez_pop* pop = nullptr;
     int rc = pop_create_impl(ctx, prior, model, N, 0, dev_hist, &pop);
     if (rc) return rc;
+    t_create = ms_since(t_begin);
     cudaStream_t st = ctx->stream;
     Ctrl* c = pop->h_ctrl;
     c->eps_target = eps_target; c->alpha = o->alpha; c->ess_min = (double)N * o->delta_ess;   // :259
@@ -763,9 +849,12 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
         host_iters++;
-        launches += launch_eps_quantile(st, pop->dev);                       // :301
-        launches += launch_reweight(st, pop->dev);                           // :305-324
-        launches += launch_compact(st, pop->dev);
+        if (o->fused_head) launches += launch_head(st, pop->dev, ctx->sm_count);   // :301-324 in one cooperative kernel
+        else {
+            launches += launch_eps_quantile(st, pop->dev);                   // :301
+            launches += launch_reweight(st, pop->dev);                       // :305-324
+            launches += launch_compact(st, pop->dev);
+        }
         launches += launch_resample(st, pop->dev, pop->DS, pop->NB, nullptr, (uint32_t)host_iters, mode, 0);   // :324-326
         for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
             if (o->profile) {
@@ -791,6 +880,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     RUN_CU(cudaGetLastError());
     RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     RUN_CU(cudaStreamSynchronize(st));
+    t_loop = ms_since(t_begin);
     rc = check_dev_err(pop, "abcdez_smc_run");
     if (rc == ABCDEZ_ERR_NO_ALIVE) rc = ABCDEZ_OK;       // a warning in the reference (:375); reported in status
     if (rc) goto done;
@@ -831,10 +921,14 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         }
     }
 done:
+    t_result = ms_since(t_begin);
     if (e_init0) cudaEventDestroy(e_init0);
     if (e_loop0) cudaEventDestroy(e_loop0);
     if (e_loop1) cudaEventDestroy(e_loop1);
     abcdez_pop_destroy(pop);
+    if (trace)
+        fprintf(stderr, "[abcdez] smc_run N=%lld: create %.2f ms, loop done at %.2f, results at %.2f, destroyed at %.2f (device loop %.2f ms)\n",
+                (long long)N, t_create, t_loop, t_result, ms_since(t_begin), res->total_ms);
     return rc;
 #undef RUN_CU
 }

@@ -37,50 +37,6 @@ __global__ void begin_run_kernel(PopDev P)
 // ---------------------------------------------------------------------------------------
 // radix select of v[j] among the alive distances: 11-bit digits, MSB first
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void load4_f64(const double* __restrict__ p, size_t i0, uint32_t N, double v[4])
-{
-    if (i0 + 3 < N) {
-        double2 a = *reinterpret_cast<const double2*>(p + i0), b = *reinterpret_cast<const double2*>(p + i0 + 2);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < N) ? p[i0 + k] : 0.0;
-    }
-}
-
-__device__ __forceinline__ void store4_f64(double* __restrict__ p, size_t i0, uint32_t N, const double v[4])
-{
-    if (i0 + 3 < N) {
-        *reinterpret_cast<double2*>(p + i0) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(p + i0 + 2) = make_double2(v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (i0 + k < N) p[i0 + k] = v[k];
-    }
-}
-
-__device__ __forceinline__ uint32_t load4_u8(const uint8_t* __restrict__ p, size_t i0, uint32_t N)
-{
-    if (i0 + 3 < N) return *reinterpret_cast<const uint32_t*>(p + i0);
-    uint32_t r = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (i0 + k < N) r |= (uint32_t)p[i0 + k] << (8 * k);
-    return r;
-}
-
-// extrema(delta) of the generation that the previous iteration left behind: the sweeps no longer touch
-// every particle, so ranges_eps (src/abcdez_smc.jl:363) is taken from the first select pass of the next
-// iteration (same delta array) and written into the history record that iteration pushed
-__device__ void patch_extrema(const PopDev& P, Ctrl* c)
-{
-    c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
-    c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
-    if (P.hist && c->hist_len > 0 && c->hist_len <= c->hist_cap) {
-        double* h = P.hist + (size_t)(c->hist_len - 1) * 8;
-        h[1] = c->dmin; h[2] = c->dmax;
-    }
-}
-
 // pick the bin holding rank sel_rank; all BK_THREADS threads of the calling CTA participate
 __device__ void select_pick(const PopDev& P, Ctrl* c, int shift, int nbins, bool final_pass)
 {
@@ -270,22 +226,6 @@ __global__ void __launch_bounds__(BK_THREADS) reweight_a_kernel(PopDev P)
             c->wnorm = a;                                                   // :309
             c->logZ += plog(a);                                              // :315
         }
-    }
-}
-
-// reweight pass B + the decisions of :318-324.  Builds the sequential-sum tables for the
-// closed-form resampling when it will be needed.
-__device__ void ctrl_after_reweight(const PopDev& P, Ctrl* c, double sumsq, unsigned n_alive)
-{
-    c->n_alive = n_alive;
-    c->ess = 1.0 / sumsq;                                                   // :8,:323
-    c->naccs_iter = 0ull; c->Ki = c->Kmcmc;                                 // :318-319
-    c->sweep_idx = 0; c->sweeps_done = 0;
-    if (c->facc < c->facc_min) c->gamma0 *= c->facc_tune;                   // :320
-    c->do_resample = (c->ess < c->ess_min) ? 1 : 0;                         // :324
-    if (c->do_resample && abck_is_indicator(c->kind)) {
-        seqtab_build(&P.tabs[0], __ldcg(&c->acc.w_alive), (unsigned long long)n_alive);
-        seqtab_build(&P.tabs[1], 1.0 / (double)P.N, (unsigned long long)P.N);
     }
 }
 

@@ -46,7 +46,8 @@ struct PopDev {
     Ctrl* ctrl;
     double* partial;              // per-CTA reduction partials (2 x nblocks)
     uint32_t* tile_cnt;           // per-tile alive counts -> exclusive offsets
-    uint32_t* sel_hist;           // SEL_BINS radix-select histogram
+    uint32_t* sel_hist;           // 6 x SEL_BINS radix-select histograms (one per digit pass)
+    unsigned long long* cand[2];  // head.cu candidate lists (alias cumsum / scratch)
     double* cumsum;               // N inclusive cumulative weights (general-weight resampling)
     int32_t* inds;                // N resampling indices (0-based)
     double* hist;                 // hist_cap x 8 history records
@@ -90,6 +91,7 @@ enum { PRIOR_OP_SAMPLE = 0, PRIOR_OP_LOGPDF = 1, PRIOR_OP_PUSH = 2 };
 int launch_eps_quantile(cudaStream_t, const PopDev&);                 // -> ctrl.q_a, q_b, q, eps (clamped)
 int launch_reweight(cudaStream_t, const PopDev&);                     // -> W, alive, wnorm, logZ, ess, flags
 int launch_compact(cudaStream_t, const PopDev&);                      // -> alive_list
+int launch_head(cudaStream_t, const PopDev&, int sm_count);           // head.cu: the three above in one cooperative kernel
 int launch_resample(cudaStream_t, const PopDev&, int D, int NB, const double* inj_u, uint32_t epoch,
                     int mode, int force);
 int launch_end_iter(cudaStream_t, const PopDev&);
@@ -113,6 +115,11 @@ struct abcdez_ctx {
     void* nccl_comm;
     int sm_count;
     std::vector<cudaEvent_t> ev_pool;   // reused by profile=1 runs (cudaEventCreate costs ~0.2 ms each)
+    // device arena: populations are carved from one slab that lives as long as the context, so repeated
+    // runs pay cudaMalloc/cudaFree (each a device-wide synchronisation) once, not 25 times per run
+    char* arena; size_t arena_bytes; bool arena_busy;
+    abcdez::Ctrl* h_ctrl_pool;          // pinned control-block mirror, reused like the arena
+    bool h_ctrl_busy;
 };
 
 struct abcdez_prior {
@@ -132,6 +139,8 @@ struct abcdez_pop {
     abcdez::ModelData data;
     abcdez::PopDev dev;
     abcdez::Ctrl* h_ctrl;         // pinned mirror
+    char* slab; size_t slab_bytes;   // all device arrays of the population live in this slab
+    bool slab_from_arena, h_ctrl_from_pool;
     int64_t N;
     int D, DS, NB;
     int hist_cap;

@@ -43,7 +43,7 @@ class _SmcOpts(C.Structure):
                 ("kernel", C.c_int32), ("facc_stop", C.c_double), ("facc_min", C.c_double),
                 ("facc_tune", C.c_double), ("seed", C.c_uint64), ("verboseout", C.c_int32),
                 ("max_iters", C.c_int32), ("exact_scan", C.c_int32), ("profile", C.c_int32),
-                ("sync_every", C.c_int32)]
+                ("sync_every", C.c_int32), ("fused_head", C.c_int32)]
 
 
 class _SmcResult(C.Structure):
@@ -77,7 +77,7 @@ EXPORTS = [
     "abcdez_smc_opts_default", "abcdez_smc_run", "abcdez_mc_opts_default", "abcdez_mc_run",
     "abcdez_pop_create", "abcdez_pop_destroy", "abcdez_pop_upload", "abcdez_pop_download", "abcdez_pop_set",
     "abcdez_pop_init", "abcdez_pop_smc_sweep", "abcdez_pop_mc_sweep", "abcdez_pop_eps_quantile",
-    "abcdez_pop_reweight", "abcdez_pop_resample", "abcdez_wsample_stratified", "abcdez_pop_last_timing",
+    "abcdez_pop_reweight", "abcdez_pop_head", "abcdez_pop_resample", "abcdez_wsample_stratified", "abcdez_pop_last_timing",
     "abcdez_pop_bench_sweeps",
 ]
 
@@ -484,7 +484,8 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
              nsims_max: int = 10**7, Kmcmc: int = 3, Kmcmc_min=1.0, ABCk=IndicatorStrict0toEps, facc_stop=0.0,
              facc_min=0.0, facc_tune=0.975, verbose: bool = True, verboseout: bool = True, rng=None,
              parallel: bool = False, ctx: Optional[Context] = None, max_iters: int = 0, exact_scan: bool = False,
-             profile: bool = False, sync_every: int = 1, hist_cap: int = 8192, **greek) -> SMCResult:
+             profile: bool = False, sync_every: int = 1, hist_cap: int = 8192, fused_head: bool = True,
+             **greek) -> SMCResult:
     """`abcdesmc!(prior, dist!, ϵ_target, varexternal; kwargs...)`, src/abcdez_smc.jl:215-394.
 
     `dist` is a :class:`Model`; `varexternal` is accepted for signature compatibility (the device
@@ -507,6 +508,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     o.Kmcmc_min = float(Kmcmc_min); o.kernel = _kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
     o.facc_tune = facc_tune; o.seed = _seed_from(rng); o.verboseout = int(verboseout); o.max_iters = int(max_iters)
     o.exact_scan = int(exact_scan); o.profile = int(profile); o.sync_every = int(sync_every)
+    o.fused_head = int(fused_head)
     Np = max(N, 1)
     P = np.empty((Np, d)); W = np.empty(Np); Cc = np.empty(Np); bl = np.zeros((Np, max(B, 1)), dtype=np.uint8)
     h = {k: np.zeros(hist_cap) for k in ("eps", "dmin", "dmax", "logZ", "ess", "facc", "gamma0")}
@@ -652,6 +654,13 @@ class Population:
         wn = C.c_double(); ess = C.c_double(); na = C.c_int64()
         _check(lib().abcdez_pop_reweight(self._h, C.c_double(eps_new), C.byref(wn), C.byref(ess), C.byref(na)))
         return wn.value, ess.value, na.value
+
+    def head(self, alpha, eps_target=0.0):
+        """One fused iteration head (head.cu): returns (q, eps, wnorm, ess, n_alive)."""
+        q = C.c_double(); eps = C.c_double(); wn = C.c_double(); ess = C.c_double(); na = C.c_int64()
+        _check(lib().abcdez_pop_head(self._h, C.c_double(alpha), C.c_double(eps_target), C.byref(q), C.byref(eps),
+                                     C.byref(wn), C.byref(ess), C.byref(na)))
+        return q.value, eps.value, wn.value, ess.value, na.value
 
     def resample(self, uniforms=None, epoch=0, mode=0):
         u = None if uniforms is None else _f64(uniforms)

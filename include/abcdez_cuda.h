@@ -134,6 +134,8 @@ typedef struct {
     int32_t exact_scan;      /* 1: sequential FP64 cumsum for Epanechnikov resampling (parity mode) */
     int32_t profile;         /* 1: time every sweep launch with CUDA events */
     int32_t sync_every;      /* host polls the stop flag every this many iterations (default 1) */
+    int32_t fused_head;      /* 1 (default): eps quantile + reweight + ESS + alive list in one cooperative kernel;
+                                0: the stage kernels one by one (same results bit for bit) */
 } abcdez_smc_opts;
 
 typedef struct {
@@ -216,6 +218,12 @@ int abcdez_pop_eps_quantile(abcdez_pop* pop, double alpha, double* q, double* v_
 
 /* abcdesmc_update_ws! + src/abcdez_smc.jl:305-315,323: ws, wprod, wnorm, Wns, alive, ess */
 int abcdez_pop_reweight(abcdez_pop* pop, double eps_new, double* wnorm, double* ess, int64_t* n_alive);
+
+/* src/abcdez_smc.jl:301-324 in one launch: eps = max(min(quantile(delta[alive], alpha), eps), eps_target), then the
+ * reweighting, ESS and alive-list steps of the two calls above against that eps.  Bit-identical to calling them
+ * one by one. */
+int abcdez_pop_head(abcdez_pop* pop, double alpha, double eps_target, double* q, double* eps, double* wnorm,
+                    double* ess, int64_t* n_alive);
 
 /* abcdesmc_resample! (src/abcdez_smc.jl:85-104, wsample_stratified! :15-56): indices + gather +
  * weight reset.  uniforms (N, host) NULL -> Philox stream (seed, stratum, epoch).  inds_out

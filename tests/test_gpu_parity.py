@@ -356,6 +356,96 @@ def test_reweight_parity(A, oracle, gpu_ctx, kind, N):
 
 
 # ---------------------------------------------------------------------------------------------
+# fused iteration head (head.cu): quantile + clamp + reweight + ESS + alive list in one launch
+# ---------------------------------------------------------------------------------------------
+def _head_case(rng, N, dead, ties):
+    dl = rng.exponential(size=N) ** 2
+    if ties == "discrete":
+        dl = np.floor(dl * 3.0)                                  # few distinct values: huge ties (socks-like)
+    elif ties == "some" and N > 10:
+        dl[rng.choice(N, N // 10, replace=False)] = dl[0]
+        dl[1] = 0.0; dl[2] = 1e300; dl[3] = 5e-324
+    elif ties == "narrow":
+        dl = 1.0 + dl * 1e-9                                     # all keys share > 22 leading bits: long candidate list
+    alive = (rng.random(N) >= dead).astype(np.uint8)
+    alive[0] = 1
+    return dl, alive
+
+
+@pytest.mark.parametrize("kind", ["indicator_strict", "epa"])
+@pytest.mark.parametrize("N,dead,alpha,ties", [
+    (1, 0.0, 0.95, "none"), (2, 0.0, 0.95, "none"), (7, 0.3, 0.5, "none"), (1000, 0.3, 0.95, "some"),
+    (4099, 0.9, 0.95, "some"), (100003, 0.5, 0.95, "some"), (100003, 0.0, 0.0, "none"), (50000, 0.2, 0.999, "discrete"),
+    (300000, 0.1, 0.95, "narrow"), (1 << 20, 0.4, 0.95, "none"), (3000001, 0.0, 0.9, "narrow")])
+def test_fused_head_equals_stage_calls_and_oracle(A, oracle, gpu_ctx, kind, N, dead, alpha, ties):
+    """head_kernel == eps_quantile + clamp + reweight + compact, bit for bit, and == the oracle."""
+    rng = np.random.default_rng(N + int(alpha * 1000))
+    dl, alive = _head_case(rng, N, dead, ties)
+    eps_prev = float(np.max(dl[alive > 0])) * 2 + 1.0
+    Wv = np.where(alive > 0, rng.random(N) if kind == "epa" else 1.0, 0.0); Wv /= Wv.sum()
+    spec, data = MODEL_CASES["gauss1d"]
+    res = {}
+    for mode in ("fused", "stage"):
+        pop = A.Population(to_prior(A, spec), A.Model("gauss1d", data), N)
+        pop.upload(delta=dl, W=Wv, alive=alive)
+        pop.set(eps=eps_prev, eps_prev=eps_prev, kernel=kind)
+        if mode == "fused":
+            q, eps, wn, ess, na = pop.head(alpha, 0.0)
+        else:
+            q = pop.eps_quantile(alpha)[0]
+            eps = max(min(q, eps_prev), 0.0)
+            wn, ess, na = pop.reweight(eps)
+        st = pop.download()
+        res[mode] = (q, eps, wn, ess, na, st["W"].copy(), st["alive"].copy())
+        pop.close()
+    f, s_ = res["fused"], res["stage"]
+    assert f[:5] == s_[:5]
+    assert np.array_equal(f[5], s_[5]) and np.array_equal(f[6], s_[6])
+    wq = oracle.quantile_alive(dl, alive, alpha)[0]
+    assert f[0] == wq
+    wW, wal, wnorm, wess, wna = oracle.reweight(dl, Wv, alive, eps_prev, f[1], kind)
+    assert np.array_equal(f[6], wal) and f[4] == wna
+    np.testing.assert_allclose(f[5], wW, rtol=1e-12, atol=0)
+    assert math.isclose(f[2], wnorm, rel_tol=1e-12) and math.isclose(f[3], wess, rel_tol=1e-12)
+
+
+def test_fused_head_alive_list_drives_partner_draws(A, oracle, gpu_ctx):
+    """After the fused head, a Philox sweep (partners through the compacted alive list) equals the oracle's."""
+    name = "gauss_corr10"
+    spec, data = MODEL_CASES[name]
+    N = 20000
+    th, lp, dl, _, alive = _population_state(oracle, spec, name, data, N, seed=5, dead_frac=0.0)
+    pop = A.Population(to_prior(A, spec), A.Model(name, data), N)
+    pop.upload(theta=th, logpi=lp, delta=dl, alive=alive)
+    pop.set(eps=math.inf, eps_prev=math.inf, kernel="indicator_strict", seed=99, epoch=3)
+    q, eps, wn, ess, na = pop.head(0.6, 0.0)
+    st = pop.download()
+    assert na == int(st["alive"].sum()) and 0.55 * N < na < 0.65 * N
+    pop.set(eps=eps, eps_prev=eps, kernel="indicator_strict", seed=99, epoch=3)
+    got = pop.smc_sweep()          # NB: pop.set leaves n_alive / alive_list of the head untouched
+    want = oracle.smc_sweep(spec, name, data, th, lp, dl, st["alive"], eps, "indicator_strict",
+                            2.38 / math.sqrt(20), seed=99, epoch=3)
+    assert np.array_equal(got["flags"], want["flags"])
+    g = pop.download()
+    np.testing.assert_array_equal(g["theta"], want["theta"])
+    pop.close()
+
+
+def test_fused_head_nan_and_empty(A, gpu_ctx):
+    spec, data = MODEL_CASES["gauss1d"]
+    N = 5000
+    dl = np.random.default_rng(2).exponential(size=N)
+    dl[17] = math.nan
+    pop = A.Population(to_prior(A, spec), A.Model("gauss1d", data), N)
+    pop.upload(delta=dl, alive=np.ones(N, dtype=np.uint8))
+    pop.set(eps=math.inf, eps_prev=math.inf)
+    with pytest.raises(A.ABCdeZError) as e:
+        pop.head(0.95)
+    assert e.value.code == A.host.ERR_NAN_DISTANCE
+    pop.close()
+
+
+# ---------------------------------------------------------------------------------------------
 # stratified resampling
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,alive_frac", [(3, 1.0), (100, 0.5), (1000, 0.49), (4097, 0.3), (65536, 0.5), (100003, 0.37),

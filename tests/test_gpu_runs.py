@@ -38,7 +38,9 @@ def isaround(x, val, f=1.0):
     ("normdu", 0.05, 500, {}),
     ("lotka_volterra", 0.3, 1200, dict(nsims_max=40000)),
 ])
-def test_smc_run_follows_oracle(A, oracle, gpu_ctx, name, eps_target, N, kw):
+@pytest.mark.parametrize("fused", [True, False])
+def test_smc_run_follows_oracle(A, oracle, gpu_ctx, name, eps_target, N, kw, fused):
+    kw = dict(kw)
     spec, data = MODEL_CASES[name]
     kind = kw.pop("kernel", "indicator_strict")
     exact = kw.pop("exact_scan", False)
@@ -46,7 +48,7 @@ def test_smc_run_follows_oracle(A, oracle, gpu_ctx, name, eps_target, N, kw):
     want = oracle.smc_run(spec, name, data, eps_target, **okw)
     gkw = {k: v for k, v in kw.items()}
     got = A.abcdesmc(to_prior(A, spec), A.Model(name, data), eps_target, None, nparticles=N, rng=4242, ABCk=kind,
-                     exact_scan=exact, verbose=False, **gkw)
+                     exact_scan=exact, verbose=False, fused_head=fused, **gkw)
     assert (got.iters, got.nsims, got.status) == (want.iters, want.nsims, want.status)
     assert np.array_equal(got.Kmcmcs, want.hist["Kmcmc"])
     np.testing.assert_allclose(got.eps_hist, want.hist["eps"], rtol=1e-9)
