@@ -5,5 +5,5 @@ The directory name contains a dot, so import it through the alias module at the 
 """
 from .host import *  # noqa: F401,F403
 from .host import (ABCdeZError, Context, Factored, Model, Population, abcdesmc, abcdemc, lib, model_names,
-                   wsample_stratified, default_context, EXPORTS, LIB_PATH)
-from . import host, build  # noqa: F401
+                   wsample_stratified, default_context, shard_range, EXPORTS, LIB_PATH)
+from . import host, build, dist  # noqa: F401

@@ -58,7 +58,7 @@ extern "C" int abcdez_init(int device, void* stream, abcdez_ctx** out)
     abcdez_ctx* c = new (std::nothrow) abcdez_ctx();
     if (!c) return fail(ABCDEZ_ERR_CUDA, "abcdez_init: out of host memory");
     c->device = device;
-    c->rank = 0; c->world = 1; c->nccl_comm = nullptr;
+    c->rank = 0; c->world = 1; c->comm = nullptr;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else {
         cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -77,6 +77,7 @@ extern "C" int abcdez_destroy(abcdez_ctx* ctx)
     if (!ctx) return ABCDEZ_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->comm) comm_destroy(ctx->comm);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->h_ctrl_pool) cudaFreeHost(ctx->h_ctrl_pool);
@@ -91,12 +92,47 @@ extern "C" int abcdez_sync(abcdez_ctx* ctx)
     return ABCDEZ_OK;
 }
 
-extern "C" int abcdez_nccl_unique_id(void*) { return fail(ABCDEZ_ERR_UNSUPPORTED, "NCCL sharding: see abcdez.jl_b200/dist.py (round 1 shards by independent sub-populations)"); }
-extern "C" int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void*)
+// ---- sharded runs: one process per GPU -------------------------------------------------
+extern "C" int abcdez_nccl_unique_id(void* id128)
+{
+    CHECK_ARG(id128 != nullptr, "abcdez_nccl_unique_id: id128 is NULL");
+    std::string why;
+    int rc = nccl_unique_id(id128, &why);
+    return rc ? fail(rc, why) : ABCDEZ_OK;
+}
+
+extern "C" int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void* id128)
 {
     CHECK_ARG(ctx != nullptr, "abcdez_comm_init: ctx is NULL");
-    CHECK_ARG(world >= 1 && rank >= 0 && rank < world, "abcdez_comm_init: bad rank/world");
+    CHECK_ARG(world >= 1 && world <= XCHG_MAXR && rank >= 0 && rank < world, "abcdez_comm_init: need 0 <= rank < world <= 8");
+    CHECK_ARG(ctx->comm == nullptr, "abcdez_comm_init: the context already has a communicator");
     ctx->rank = rank; ctx->world = world;
+    if (world == 1) return ABCDEZ_OK;
+    CHECK_ARG(id128 != nullptr, "abcdez_comm_init: id128 is NULL");
+    CU(cudaSetDevice(ctx->device));
+    std::string why;
+    int rc = comm_create(rank, world, id128, ctx->stream, &ctx->comm, &why);
+    if (rc) { ctx->rank = 0; ctx->world = 1; return fail(rc, "abcdez_comm_init: " + why); }
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_comm_selftest(abcdez_ctx* ctx, int rounds, uint64_t* checksum, double* us_per_round)
+{
+    CHECK_ARG(ctx && ctx->comm && checksum, "abcdez_comm_selftest: needs a context with a communicator");
+    CHECK_ARG(rounds >= 1 && rounds <= 100000, "abcdez_comm_selftest: rounds out of range");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long r = 0;
+    int rc = comm_selftest(ctx->comm, ctx->stream, rounds, &r, us_per_round);
+    *checksum = r;
+    return rc ? fail(rc, std::string("abcdez_comm_selftest: ") + comm_error(ctx->comm)) : ABCDEZ_OK;
+}
+
+// contiguous block of global particle indices owned by `rank`: [floor(rank N / world), floor((rank+1) N / world))
+extern "C" int abcdez_shard_range(int64_t N, int rank, int world, int64_t* lo, int64_t* hi)
+{
+    CHECK_ARG(N >= 0 && world >= 1 && rank >= 0 && rank < world && lo && hi, "abcdez_shard_range: bad argument");
+    *lo = (int64_t)(((__int128)N * rank) / world);
+    *hi = (int64_t)(((__int128)N * (rank + 1)) / world);
     return ABCDEZ_OK;
 }
 
@@ -282,7 +318,7 @@ extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
     cudaStreamSynchronize(pop->ctx->stream);
     if (pop->slab) {
         if (pop->slab_from_arena) pop->ctx->arena_busy = false;     // the slab stays with the context
-        else cudaFree(pop->slab);
+        else if (!pop->slab_shared) cudaFree(pop->slab);            // (the shared arena stays with the communicator)
     }
     if (pop->sorted_delta) cudaFree(pop->sorted_delta);
     if (pop->order) cudaFree(pop->order);
@@ -297,8 +333,10 @@ extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
     return ABCDEZ_OK;
 }
 
+// Ng > 0: this population is one shard (N particles from global index id0) of a sharded population of Ng
+// particles; its slab then comes from the communicator's shared arena (mapped by every peer; collective call).
 static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, int64_t N,
-                           int64_t id0, int hist_cap, abcdez_pop** out)
+                           int64_t id0, int hist_cap, abcdez_pop** out, int64_t Ng = 0)
 {
     CHECK_ARG(ctx && prior && model && out, "abcdez_pop_create: NULL argument");
     CHECK_ARG(N >= 1 && N < (int64_t)0x7fffffff, "abcdez_pop_create: N must be in 1..2^31-2 per GPU");
@@ -313,6 +351,10 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     pop->hist_cap = hist_cap;
     PopDev& P = pop->dev;
     P.N = (uint32_t)N; P.id0 = (uint32_t)id0; P.ntiles = (uint32_t)((N + TILE - 1) / TILE);
+    const bool shard = Ng > 0;
+    P.Ng = (uint32_t)(shard ? Ng : N);
+    P.x.rank = 0; P.x.world = 1; P.x.seq = nullptr; P.peers = nullptr;
+    for (int q = 0; q < XCHG_MAXR; ++q) P.x.mbox[q] = nullptr;
     size_t n = (size_t)N;
     // one slab for every device array of the population (256-byte aligned pieces), carved from the
     // context arena when it is free, else from a private allocation
@@ -332,7 +374,11 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     };
     size_t total = 0;
     for (const Piece& pc : pieces) total += (pc.bytes + 255) & ~(size_t)255;
-    if (!ctx->arena_busy) {
+    if (shard) {
+        int rc_ = comm_shared_slab(ctx->comm, ctx->stream, total, &pop->slab);
+        if (rc_) { delete pop; return fail(rc_, std::string("abcdez: shared slab: ") + comm_error(ctx->comm)); }
+        pop->slab_shared = true; pop->slab_from_arena = false;
+    } else if (!ctx->arena_busy) {
         if (ctx->arena_bytes < total) {
             if (ctx->arena) cudaFree(ctx->arena);
             ctx->arena = nullptr; ctx->arena_bytes = 0;
@@ -372,19 +418,19 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     CU(cudaMemsetAsync(P.moved, 1, n, st));
     CU(cudaMemsetAsync(P.theta[0], 0, n * pop->DS * 8, st));
     CU(cudaMemsetAsync(P.theta[1], 0, n * pop->DS * 8, st));
-    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.W, N, 1.0 / (double)N);
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.W, N, 1.0 / (double)P.Ng);
     Ctrl* c = pop->h_ctrl;
     memset(c, 0, sizeof(Ctrl));
     c->eps = INFINITY; c->eps_k = INFINITY; c->eps_target = 0.0;
     c->facc = 1.0; c->gamma0 = 2.38 / sqrt(2.0 * (double)pop->D); c->gsig = 1e-5;     // src/abcdez_smc.jl:280-281
     c->alpha = 0.95; c->Kmcmc_min = 1.0; c->facc_tune = 0.975;
     c->nsims_max = (long long)10000000; c->kind = ABCDEZ_INDICATOR_STRICT; c->Kmcmc = 3; c->Ki = 3;
-    c->N = (uint32_t)N; c->n_alive = (uint32_t)N; c->ess_min = 0.5 * (double)N;
+    c->N = (uint32_t)N; c->n_alive = (uint32_t)N; c->Ng = P.Ng; c->n_alive_g = P.Ng; c->ess_min = 0.5 * (double)P.Ng;
     c->hist_cap = hist_cap;
     c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull; c->acc.min_gt_key = ~0ull;
     for (int q = 0; q < 6; ++q) { c->acc.cand_min[q] = ~0ull; c->acc.cand_max[q] = 0ull; }
     c->acc.min_above = ~0ull;
-    c->acc.w_alive = 1.0 / (double)N;
+    c->acc.w_alive = 1.0 / (double)P.Ng;
     int rc = push_ctrl(pop);
     if (rc) { abcdez_pop_destroy(pop); return rc; }
     CU(cudaStreamSynchronize(st));
@@ -425,7 +471,7 @@ extern "C" int abcdez_pop_upload(abcdez_pop* pop, const double* theta, const dou
         for (size_t i = 0; i < n; ++i) if (alive[i]) list.push_back((uint32_t)i);
         for (size_t i = 0; i < n; ++i) if (!alive[i]) list.push_back((uint32_t)i);
         CU(cudaMemcpyAsync(P.alive_list, list.data(), n * 4, cudaMemcpyHostToDevice, st));
-        pop->h_ctrl->n_alive = na;
+        pop->h_ctrl->n_alive = na; pop->h_ctrl->n_alive_g = na;
         if (W) pop->h_ctrl->acc.w_alive = wal;
         CU(cudaStreamSynchronize(st));
         rc = push_ctrl(pop); if (rc) return rc;
@@ -818,16 +864,32 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     auto t_begin = now();
     double t_create = 0.0, t_loop = 0.0, t_result = 0.0;
-    const int64_t N = o->nparticles;
+    // sharded run (abcdez_comm_init with world > 1): nparticles is the size of the WHOLE population; this rank
+    // owns the contiguous block abcdez_shard_range(nparticles, rank, world) and returns that block's rows
+    const bool shard = ctx->comm != nullptr && ctx->world > 1;
+    const int64_t Ng = o->nparticles;
+    int64_t lo = 0, hi = Ng;
+    if (shard) {
+        abcdez_shard_range(Ng, ctx->rank, ctx->world, &lo, &hi);
+        if (!abck_is_indicator(o->kernel))
+            return fail(ABCDEZ_ERR_UNSUPPORTED, "sharded abcdesmc!: only the indicator kernels are supported across GPUs in this build");
+        CHECK_ARG(Ng >= 4 * (int64_t)ctx->world, "sharded abcdesmc!: need at least 4 particles per rank");
+        CHECK_ARG(Ng < (int64_t)0x7fffffff, "sharded abcdesmc!: nparticles must be below 2^31");
+    }
+    const int64_t N = hi - lo;
     int hist_cap = o->verboseout ? (res->hist_cap > 0 ? res->hist_cap : 0) : 0;
     int dev_hist = hist_cap > 0 ? hist_cap : 1;
     abcdez_pop* pop = nullptr;
-    int rc = pop_create_impl(ctx, prior, model, N, 0, dev_hist, &pop);
+    int rc = pop_create_impl(ctx, prior, model, N, lo, dev_hist, &pop, shard ? Ng : 0);
     if (rc) return rc;
+    if (shard) {
+        rc = comm_begin_run(ctx->comm, ctx->stream, pop->dev, &pop->dev.x, &pop->dev.peers);
+        if (rc) { abcdez_pop_destroy(pop); return fail(rc, std::string("sharded abcdesmc!: ") + comm_error(ctx->comm)); }
+    }
     t_create = ms_since(t_begin);
     cudaStream_t st = ctx->stream;
     Ctrl* c = pop->h_ctrl;
-    c->eps_target = eps_target; c->alpha = o->alpha; c->ess_min = (double)N * o->delta_ess;   // :259
+    c->eps_target = eps_target; c->alpha = o->alpha; c->ess_min = (double)Ng * o->delta_ess;   // :259
     c->nsims_max = o->nsims_max; c->Kmcmc = o->Kmcmc; c->Ki = o->Kmcmc; c->Kmcmc_min = o->Kmcmc_min;
     c->kind = o->kernel; c->facc_stop = o->facc_stop; c->facc_min = o->facc_min; c->facc_tune = o->facc_tune;
     c->seed = o->seed; c->max_iters = o->max_iters; c->hist_cap = hist_cap;
@@ -849,7 +911,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
         host_iters++;
-        if (o->fused_head) launches += launch_head(st, pop->dev, ctx->sm_count);   // :301-324 in one cooperative kernel
+        if (o->fused_head || shard) launches += launch_head(st, pop->dev, ctx->sm_count);   // :301-324 in one cooperative kernel
         else {
             launches += launch_eps_quantile(st, pop->dev);                   // :301
             launches += launch_reweight(st, pop->dev);                       // :305-324

@@ -11,6 +11,7 @@
 #include "internal.h"
 #include "seqsum.cuh"
 #include "ctrl.cuh"
+#include "comm.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace abcdez {
@@ -28,7 +29,7 @@ __global__ void end_iter_kernel(PopDev P)
 __global__ void begin_run_kernel(PopDev P)
 {
     Ctrl* c = P.ctrl;
-    double N = (double)P.N;
+    double N = (double)P.Ng;
     double w = 1.0 / N;
     push_hist(P, c, c->eps, 1.0 / (N * (w * w)), c->facc, c->Kmcmc);
     select_setup(c);
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(BK_THREADS) reweight_b_kernel(PopDev P)
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_cnt[0] = off;   // total alive (last chunk's end)
         __syncthreads();
-        if (threadIdx.x == 0) ctrl_after_reweight(P, c, a, s_cnt[0]);
+        if (threadIdx.x == 0) ctrl_after_reweight(P, c, a, s_cnt[0], s_cnt[0]);
     }
 }
 
@@ -340,9 +341,9 @@ int launch_compact(cudaStream_t st, const PopDev& P)
 // ---------------------------------------------------------------------------------------
 __device__ void ctrl_after_resample(const PopDev& P, Ctrl* c)
 {
-    double N = (double)P.N, w = 1.0 / N;
+    double N = (double)P.Ng, w = 1.0 / N;
     c->cur ^= 1;                     // the gathered generation is the live one
-    c->n_alive = P.N;                // :102-103
+    c->n_alive = P.N; c->n_alive_g = P.Ng;   // :102-103
     c->ess = 1.0 / (N * (w * w));    // get_ess(Wns) after the reset, :326
     c->n_resamples += 1;
 }
@@ -402,6 +403,74 @@ resample_uniform_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
     if (si < N) { P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1; }        // :102-103; the old buffer is stale
     if (last_block(&c->acc.ticket[3], gridDim.x)) {
         if (threadIdx.x == 0) ctrl_after_resample(P, c);
+    }
+}
+
+// ---- sharded runs (exchange 3): GLOBAL stratified resampling over NVLink peer memory ------------
+// Rank r resolves its own output strata [id0, id0 + N) against the whole population: the k-th alive particle
+// of the concatenated per-rank alive lists is looked up in its owner's HBM (peer loads through the mapped
+// population slabs, PeerTable) and its row is gathered straight into this rank's next generation -- no
+// send/recv plan, no staging.  Same uniforms (Philox stream of the global stratum), same closed-form
+// sequential sums and therefore the same indices as a single-GPU run over the same particles.
+// Peers may read a rank's live generation only between two barriers: peer_barrier_kernel (everyone's alive
+// list and particle rows are final) and the exchange in this kernel's last CTA (everyone is done reading).
+__global__ void peer_barrier_kernel(PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    xchg_small(P.x, c, nullptr, 0);
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+resample_uniform_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB, uint32_t epoch, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ SeqTab s_w;
+    __shared__ unsigned s_end[XCHG_MAXR];         // inclusive prefix of the per-rank alive counts
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.tabs[0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_w);
+        for (unsigned q = threadIdx.x; q < sizeof(SeqTab) / 4; q += blockDim.x) dst[q] = src[q];
+        if (threadIdx.x == 0) { unsigned a = 0; for (int r = 0; r < P.x.world; ++r) { a += c->rank_alive[r]; s_end[r] = a; } }
+    }
+    __syncthreads();
+    const int cur = c->cur;
+    const uint32_t N = P.N, n_alive_g = c->n_alive_g;
+    const double sval = 1.0 / (double)P.Ng;                                  // :34
+    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si < N) {
+        const uint32_t sg = P.id0 + si;                                      // global stratum
+        double u, u2;
+        Stream rs(c->seed, sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
+        double r = stratum_draw(&P.tabs[1], sval, sg, u);
+        unsigned long long k = seqtab_first_ge(&s_w, r);                     // :48-51 in closed form
+        int q = 0; uint32_t src = 0u;                                        // r == 0: global particle 0 (the reference leaves i = 0)
+        if (k != 0) {
+            if (k > n_alive_g) k = n_alive_g;
+            while (q < P.x.world - 1 && k > s_end[q]) ++q;                   // owner of the k-th alive particle
+            const uint32_t kk = (uint32_t)k - (q ? s_end[q - 1] : 0u);       // 1-based among its alive particles
+            const PeerPop& pp = P.peers->p[q];
+            src = (c->rank_alive[q] == pp.N) ? kk - 1 : pp.alive_list[kk - 1];
+        }
+        const PeerPop& pp = P.peers->p[q];
+        {
+            const double* s = pp.theta[cur] + (size_t)src * DS;
+            double* d = P.theta[cur ^ 1] + (size_t)si * DS;
+            if (DS & 1) { for (int e = 0; e < DS; ++e) d[e] = s[e]; }
+            else { for (int e = 0; e < DS; e += 2) *reinterpret_cast<double2*>(d + e) = *reinterpret_cast<const double2*>(s + e); }
+            P.logpi[cur ^ 1][si] = pp.logpi[cur][src];
+            P.delta[cur ^ 1][si] = pp.delta[cur][src];
+            for (int e = 0; e < NB; ++e) P.blob[cur ^ 1][(size_t)si * NB + e] = pp.blob[cur][(size_t)src * NB + e];
+        }
+        P.inds[si] = (int32_t)(pp.id0 + src);                                // global source index
+        P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1;                    // :102-103; the old buffer is stale
+    }
+    if (last_block(&c->acc.ticket[3], gridDim.x)) {
+        if (threadIdx.x == 0) {
+            xchg_small(P.x, c, nullptr, 0);      // nobody reads this rank's old generation any more
+            ctrl_after_resample(P, c);
+        }
     }
 }
 
@@ -586,6 +655,11 @@ int launch_resample(cudaStream_t st, const PopDev& P, int DS, int NB, const doub
                     int mode, int force)
 {
     unsigned gt = tiles_for(P.N), gp = (unsigned)((P.N + BK_THREADS - 1) / BK_THREADS);
+    if (P.x.world > 1) {             // sharded: indicator kernels only (checked by abcdez_smc_run)
+        peer_barrier_kernel<<<1, 1, 0, st>>>(P, force);
+        resample_uniform_sharded_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, epoch, force);
+        return 2;
+    }
     if (mode == 0) {
         if (force) build_tabs_kernel<<<1, 1, 0, st>>>(P);
         resample_uniform_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, inj_u, epoch, force);
@@ -652,7 +726,19 @@ __global__ void __launch_bounds__(BK_THREADS) minmax_kernel(PopDev P)
     mn = warp_min_u64(mn); mx = warp_max_u64(mx);
     if ((threadIdx.x & 31) == 0) { atomicMin(&c->acc.dmin_key, mn); atomicMax(&c->acc.dmax_key, mx); }
     if (last_block(&c->acc.ticket[4], gridDim.x)) {
-        if (threadIdx.x == 0) patch_extrema(P, c);
+        if (threadIdx.x == 0) {
+            if (P.x.world > 1 && c->err != ABCDEZ_ERR_NCCL) {     // global extrema
+                unsigned long long rec[2] = { __ldcg(&c->acc.dmin_key), __ldcg(&c->acc.dmax_key) };
+                const unsigned slot = xchg_small(P.x, c, rec, 2);
+                unsigned long long mn = ~0ull, mx = 0ull;
+                for (int r = 0; r < P.x.world; ++r) {
+                    unsigned long long a = xchg_word(P.x, slot, r, 0), b = xchg_word(P.x, slot, r, 1);
+                    mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+                }
+                __stcg(&c->acc.dmin_key, mn); __stcg(&c->acc.dmax_key, mx);
+            }
+            patch_extrema(P, c);
+        }
     }
 }
 

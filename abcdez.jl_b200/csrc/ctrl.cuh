@@ -23,7 +23,7 @@ __device__ inline void push_hist(const PopDev& P, Ctrl* c, double eps, double es
 // src/abcdez_smc.jl:301: aleph = fma(n, p, 1-p); j = clamp(trunc(aleph), 1, n-1); g = clamp(aleph-j, 0, 1)
 __device__ inline void select_setup(Ctrl* c)
 {
-    unsigned long long n = c->n_alive;
+    unsigned long long n = c->n_alive_g;
     double p = c->alpha, m = 1.0 - p;
     double aleph = fma((double)n, p, m);
     long long j = (long long)trunc(aleph);
@@ -42,11 +42,11 @@ __device__ inline void select_setup(Ctrl* c)
 // end of an SMC iteration, src/abcdez_smc.jl:357-376 (called by the last CTA of the last sweep)
 __device__ inline void ctrl_end_iter(const PopDev& P, Ctrl* c)
 {
-    c->facc = (double)c->naccs_iter / ((double)c->n_alive * (double)c->Ki);   // :357
+    c->facc = (double)c->naccs_iter / ((double)c->n_alive_g * (double)c->Ki);   // :357
     c->eps_k = c->eps;                                                         // :360
     c->iters += 1;
     push_hist(P, c, c->eps, c->ess, c->facc, c->Ki);                           // :362-370
-    if (c->n_alive == 0) { c->status = ABCDEZ_ERR_NO_ALIVE; c->stop = 1; }     // :375
+    if (c->n_alive_g == 0) { c->status = ABCDEZ_ERR_NO_ALIVE; c->stop = 1; }     // :375
     else if (c->eps <= c->eps_target || c->nsims_total >= c->nsims_max || c->facc < c->facc_stop)
         c->stop = 1;                                                           // :376
     if (c->max_iters > 0 && c->iters >= c->max_iters) c->stop = 1;
@@ -103,17 +103,18 @@ __device__ inline void patch_extrema(const PopDev& P, Ctrl* c)
 
 // reweight pass B + the decisions of :318-324.  Builds the sequential-sum tables for the
 // closed-form resampling when it will be needed.
-__device__ inline void ctrl_after_reweight(const PopDev& P, Ctrl* c, double sumsq, unsigned n_alive)
+// n_alive: this rank's alive count; n_alive_g: the whole population's (equal on one GPU)
+__device__ inline void ctrl_after_reweight(const PopDev& P, Ctrl* c, double sumsq, unsigned n_alive, unsigned n_alive_g)
 {
-    c->n_alive = n_alive;
+    c->n_alive = n_alive; c->n_alive_g = n_alive_g;
     c->ess = 1.0 / sumsq;                                                   // :8,:323
     c->naccs_iter = 0ull; c->Ki = c->Kmcmc;                                 // :318-319
     c->sweep_idx = 0; c->sweeps_done = 0;
     if (c->facc < c->facc_min) c->gamma0 *= c->facc_tune;                   // :320
     c->do_resample = (c->ess < c->ess_min) ? 1 : 0;                         // :324
     if (c->do_resample && abck_is_indicator(c->kind)) {
-        seqtab_build(&P.tabs[0], __ldcg(&c->acc.w_alive), (unsigned long long)n_alive);
-        seqtab_build(&P.tabs[1], 1.0 / (double)P.N, (unsigned long long)P.N);
+        seqtab_build(&P.tabs[0], __ldcg(&c->acc.w_alive), (unsigned long long)n_alive_g);
+        seqtab_build(&P.tabs[1], 1.0 / (double)P.Ng, (unsigned long long)P.Ng);
     }
 }
 

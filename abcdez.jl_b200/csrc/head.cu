@@ -18,6 +18,7 @@
 #include "internal.h"
 #include "seqsum.cuh"
 #include "ctrl.cuh"
+#include "comm.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -37,6 +38,8 @@ struct HeadSmem {
     unsigned long long wmin[32];
     unsigned long long mn, mx, mab;
     unsigned found_bin, found_before, flag;
+    unsigned long long xh[8];                     // sharded runs: header record of an exchange
+    int xflag;
 };
 
 __device__ __forceinline__ int pass_shift(int p) { const int s[6] = { 53, 42, 31, 20, 9, 0 }; return s[p]; }
@@ -146,6 +149,80 @@ __device__ void tail_select(const unsigned long long* L, unsigned M, int p0, uns
     else bkey = (mn != ~0ull) ? mn : min_above;
 }
 
+// ---------------------------------------------------------------------------------------
+// sharded runs (exchange 1 and 2): CTA 0 turns this rank's partial results into the
+// whole population's, in place, over NVLink peer memory (comm.cuh); the caller wraps each of these in
+// grid barriers.  Integer sums and rank-ordered FP64 sums: bit-identical on every rank.
+// ---------------------------------------------------------------------------------------
+// H[0..nbins) += every other rank's histogram; optionally global extrema(delta) and the sticky error
+__device__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins, bool first, HeadSmem* s)
+{
+    const unsigned tid = threadIdx.x;
+    if (tid == 0 && first) {
+        int e0 = c->err, e1 = __ldcg(&c->acc.err);
+        s->xh[0] = __ldcg(&c->acc.dmin_key); s->xh[1] = __ldcg(&c->acc.dmax_key);
+        s->xh[2] = (unsigned long long)(e0 > e1 ? e0 : e1);
+    }
+    __syncthreads();
+    const unsigned slot = xchg_block(P.x, c, s->xh, first ? 3 : 0, H, nbins, &s->xflag);
+    for (int b = tid; b < nbins; b += HEAD_THREADS) {
+        unsigned tot = 0;
+        for (int r = 0; r < P.x.world; ++r) tot += __ldcg(xchg_body(P.x, slot, r) + b);
+        H[b] = tot;
+    }
+    if (tid == 0 && first) {
+        unsigned long long mn = ~0ull, mx = 0ull, e = 0ull;
+        for (int r = 0; r < P.x.world; ++r) {
+            unsigned long long a = xchg_word(P.x, slot, r, 0), b = xchg_word(P.x, slot, r, 1), er = xchg_word(P.x, slot, r, 2);
+            mn = a < mn ? a : mn; mx = b > mx ? b : mx; e = er > e ? er : e;
+        }
+        __stcg(&c->acc.dmin_key, mn); __stcg(&c->acc.dmax_key, mx);
+        if (e) { c->acc.err = (int)e; if (!c->err) c->err = (int)e; }
+    }
+}
+
+// candidate-list bookkeeping of generation g: global count / extrema / min-above into c->acc.g_*; when the
+// global list fits the per-CTA tail (and is not all-equal) every rank's candidates are gathered into every
+// rank's mailbox (XCHG_GCAND_OFF) so that the tail runs on the same multiset everywhere
+__device__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
+{
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {
+        s->xh[0] = __ldcg(&c->acc.cand_count[g]); s->xh[1] = __ldcg(&c->acc.cand_min[g]);
+        s->xh[2] = __ldcg(&c->acc.cand_max[g]); s->xh[3] = __ldcg(&c->acc.min_above);
+    }
+    __syncthreads();
+    const unsigned slot = xchg_block(P.x, c, s->xh, 4, nullptr, 0, &s->xflag);
+    unsigned long long M = 0ull, off = 0ull, mn = ~0ull, mx = 0ull, mab = ~0ull;
+    for (int r = 0; r < P.x.world; ++r) {
+        unsigned long long m = xchg_word(P.x, slot, r, 0), a = xchg_word(P.x, slot, r, 1), b = xchg_word(P.x, slot, r, 2),
+                           ab = xchg_word(P.x, slot, r, 3);
+        if (r < P.x.rank) off += m;
+        M += m; mn = a < mn ? a : mn; mx = b > mx ? b : mx; mab = ab < mab ? ab : mab;
+    }
+    const unsigned long long mine = s->xh[0];
+    __syncthreads();
+    if (tid == 0) {
+        c->acc.g_cand_count = M; c->acc.g_cand_min = mn; c->acc.g_cand_max = mx; c->acc.g_min_above = mab;
+        c->acc.g_cand_off = off;
+    }
+    if (M <= (unsigned long long)XCHG_GCAND && mn != mx) {                 // uniform over ranks
+        const unsigned long long* src = P.cand[g & 1];
+        for (int q = 0; q < P.x.world; ++q) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.x.mbox[q] + XCHG_GCAND_OFF) + off;
+            for (unsigned i = tid; i < (unsigned)mine; i += HEAD_THREADS) dst[i] = __ldcg(&src[i]);
+        }
+        xchg_block(P.x, c, nullptr, 0, nullptr, 0, &s->xflag);               // everyone's keys have landed everywhere
+    }
+}
+
+// all-gather of the nw-word record the caller put into s->xh (thread 0); returns the mailbox slot
+__device__ unsigned head_xchg_rec(const PopDev& P, Ctrl* c, int nw, HeadSmem* s)
+{
+    __syncthreads();
+    return xchg_block(P.x, c, s->xh, nw, nullptr, 0, &s->xflag);
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constant__ PopDev P)
 {
     Ctrl* c = P.ctrl;
@@ -159,7 +236,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
     // schedule scalars of the previous iteration (CTA 0 overwrites them after the third barrier)
     const int cur = c->cur, kind = c->kind;
     const double eps_prev = c->eps, eps_old = c->eps_k, eps_target = c->eps_target, q_gamma = c->q_gamma;
-    const unsigned n_alive_prev = c->n_alive;
+    const unsigned n_alive_prev = c->n_alive_g;
+    const bool sharded = P.x.world > 1;
     const double* __restrict__ dl = P.delta[cur];
     unsigned* H1 = P.sel_hist; unsigned* H2 = P.sel_hist + SEL_BINS;
     unsigned long long rank = c->sel_rank;
@@ -191,6 +269,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         if (tid == 0) { atomicMin(&c->acc.dmin_key, s.mn); atomicMax(&c->acc.dmax_key, s.mx); }
     }
     grid.sync();
+    if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H1, 2048, true, &s); grid.sync(); }
     unsigned bin; unsigned long long before;
     pick_bin(H1, true, 2048, rank, &s, bin, before);
     if (blockIdx.x == 0 && tid == 0) patch_extrema(P, c);   // ranges_eps of the previous record, :363
@@ -219,6 +298,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
     }
     hist_flush(&s, H2, 2048);
     grid.sync();
+    if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H2, 2048, false, &s); grid.sync(); }
     pick_bin(H2, true, 2048, rank, &s, bin, before);
     prefix |= (unsigned long long)bin << 42; himask = ~0ull << 42;
     rank -= before;
@@ -262,14 +342,18 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         }
     }
     grid.sync();
-    // candidate-list generation g: list P.cand[g & 1], accumulators cand_count/min/max[g] (reset after the run)
+    if (sharded) { if (blockIdx.x == 0) head_xchg_cands(P, c, 0, &s); grid.sync(); }
+    // candidate-list generation g: list P.cand[g & 1], accumulators cand_count/min/max[g] (reset after the run).
+    // M: this rank's candidates; Mg, cmin, cmax, min_above: the whole population's
     int p_next = 2, g = 0;
     unsigned M = (unsigned)__ldcg(&c->acc.cand_count[0]);
-    unsigned long long cmin = __ldcg(&c->acc.cand_min[0]), cmax = __ldcg(&c->acc.cand_max[0]);
-    unsigned long long min_above = __ldcg(&c->acc.min_above);
+    unsigned long long Mg = sharded ? __ldcg(&c->acc.g_cand_count) : (unsigned long long)M;
+    unsigned long long cmin = sharded ? __ldcg(&c->acc.g_cand_min) : __ldcg(&c->acc.cand_min[0]);
+    unsigned long long cmax = sharded ? __ldcg(&c->acc.g_cand_max) : __ldcg(&c->acc.cand_max[0]);
+    unsigned long long min_above = sharded ? __ldcg(&c->acc.g_min_above) : __ldcg(&c->acc.min_above);
 
     // ---- large candidate lists: refine grid-cooperatively, one digit per round -----------------------
-    while (M > (unsigned)CAND_SMEM && cmin != cmax && p_next < 6) {
+    while (Mg > (unsigned long long)CAND_SMEM && cmin != cmax && p_next < 6) {
         const int shift = pass_shift(p_next), nbins = pass_bins(p_next);
         unsigned* H = P.sel_hist + (size_t)p_next * SEL_BINS;
         const unsigned long long* src = P.cand[g & 1]; unsigned long long* dst = P.cand[(g + 1) & 1];
@@ -278,6 +362,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
             atomicAdd(&s.hist[(unsigned)((__ldcg(&src[i]) >> shift) & (unsigned long long)(nbins - 1))], 1u);
         hist_flush(&s, H, nbins);
         grid.sync();
+        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H, nbins, false, &s); grid.sync(); }
         pick_bin(H, true, nbins, rank, &s, bin, before);
         prefix |= (unsigned long long)bin << shift; himask = pass_himask_after(p_next);
         rank -= before;
@@ -309,20 +394,25 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         }
         grid.sync();
         g++; p_next++;
+        if (sharded) { if (blockIdx.x == 0) head_xchg_cands(P, c, g, &s); grid.sync(); }
         M = (unsigned)__ldcg(&c->acc.cand_count[g]);
-        cmin = __ldcg(&c->acc.cand_min[g]); cmax = __ldcg(&c->acc.cand_max[g]);
-        min_above = __ldcg(&c->acc.min_above);
+        Mg = sharded ? __ldcg(&c->acc.g_cand_count) : (unsigned long long)M;
+        cmin = sharded ? __ldcg(&c->acc.g_cand_min) : __ldcg(&c->acc.cand_min[g]);
+        cmax = sharded ? __ldcg(&c->acc.g_cand_max) : __ldcg(&c->acc.cand_max[g]);
+        min_above = sharded ? __ldcg(&c->acc.g_min_above) : __ldcg(&c->acc.min_above);
     }
 
     // ---- tail: v[j], tie test, v[j+1], type-7 interpolation, clamp (every CTA, same integers) ---------
     unsigned long long akey, bkey;
     if (cmin == cmax) {                                     // all candidates equal (discrete distances, ties)
         akey = cmin;
-        bkey = (rank + 1 < (unsigned long long)M) ? akey : min_above;
-    } else {                                                // M <= CAND_SMEM (after p_next == 6 all keys are equal)
-        for (unsigned i = tid; i < M; i += HEAD_THREADS) s.cand[i] = __ldcg(&P.cand[g & 1][i]);
+        bkey = (rank + 1 < Mg) ? akey : min_above;
+    } else {                                                // Mg <= CAND_SMEM (after p_next == 6 all keys are equal)
+        const unsigned long long* L = sharded ? reinterpret_cast<const unsigned long long*>(P.x.mbox[P.x.rank] + XCHG_GCAND_OFF)
+                                              : P.cand[g & 1];
+        for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&L[i]);
         __syncthreads();
-        tail_select(s.cand, M, p_next, prefix, himask, rank, min_above, &s, akey, bkey);
+        tail_select(s.cand, (unsigned)Mg, p_next, prefix, himask, rank, min_above, &s, akey, bkey);
     }
     double eps;
     {
@@ -359,6 +449,19 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         double a = 0.0;
         for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) a += __ldcg(&P.partial[b]);
         wnorm = block_sum_all(a, &s);                                                             // :309
+    }
+    if (sharded) {                                          // wnorm = sum over ranks, rank order (exchange 2)
+        if (blockIdx.x == 0) {
+            if (tid == 0) s.xh[0] = (unsigned long long)__double_as_longlong(wnorm);
+            const unsigned slot = head_xchg_rec(P, c, 1, &s);
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int r = 0; r < P.x.world; ++r) tot += __longlong_as_double((long long)xchg_word(P.x, slot, r, 0));
+                c->acc.g_wnorm = tot;
+            }
+        }
+        grid.sync();
+        wnorm = __ldcg(&c->acc.g_wnorm);
     }
     if (blockIdx.x == 0) {
         if (tid == 0) {
@@ -419,7 +522,25 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         for (int q = 0; q < HEAD_THREADS / 32; ++q) { n_alive += s.wcnt[q]; my_off += s.part[q]; }
         __syncthreads();
     }
-    if (blockIdx.x == 0 && tid == 0) ctrl_after_reweight(P, c, sumsq, n_alive);                  // :318-324
+    if (sharded) {                                          // sum(Wns^2), alive counts, common alive weight (exchange 2)
+        if (blockIdx.x == 0) {
+            if (tid == 0) {
+                s.xh[0] = (unsigned long long)__double_as_longlong(sumsq); s.xh[1] = (unsigned long long)n_alive;
+                s.xh[2] = (unsigned long long)__double_as_longlong(__ldcg(&c->acc.w_alive));
+            }
+            const unsigned slot = head_xchg_rec(P, c, 3, &s);
+            if (tid == 0) {
+                double tot = 0.0; unsigned ng = 0;
+                for (int r = 0; r < P.x.world; ++r) {
+                    tot += __longlong_as_double((long long)xchg_word(P.x, slot, r, 0));
+                    unsigned na = (unsigned)xchg_word(P.x, slot, r, 1);
+                    c->rank_alive[r] = na; ng += na;
+                    if (na) __stcg(&c->acc.w_alive, __longlong_as_double((long long)xchg_word(P.x, slot, r, 2)));   // same double on every rank
+                }
+                ctrl_after_reweight(P, c, tot, n_alive, ng);                                      // :318-324
+            }
+        }
+    } else if (blockIdx.x == 0 && tid == 0) ctrl_after_reweight(P, c, sumsq, n_alive, n_alive);   // :318-324
 
     // ---- compaction: alive particles first (index order), the dead ones behind them ------------------
     if (n_alive != N) {

@@ -33,6 +33,31 @@ struct SeqTab {
     unsigned long long kmax;      // largest valid k
 };
 
+// ---- sharded runs (comm.cuh / comm.cu): in-kernel exchanges over NVLink peer memory -----------------
+constexpr int XCHG_MAXR = 8;                      // ranks of one NVSwitch domain
+constexpr int XCHG_RING = 4;                      // mailbox slots (power of two)
+constexpr int XCHG_HDR = 32;                      // 64-bit header words per entry: [0] flag, [1..31] small record
+constexpr int XCHG_BODY = SEL_BINS * 4;           // body bytes per entry (one radix histogram)
+constexpr int XCHG_STRIDE = XCHG_HDR * 8 + XCHG_BODY;
+constexpr int XCHG_GCAND = 4096;                  // gathered candidate keys of the distributed radix select (= CAND_SMEM)
+constexpr size_t XCHG_GCAND_OFF = (size_t)XCHG_RING * XCHG_MAXR * XCHG_STRIDE;
+constexpr size_t XCHG_MBOX_BYTES = XCHG_GCAND_OFF + (size_t)XCHG_GCAND * 8;
+constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct XchgDev {
+    int rank, world;                              // world == 1: no exchange anywhere
+    unsigned long long* seq;                      // local exchange counter (device memory)
+    char* mbox[XCHG_MAXR];                        // every rank's mailbox mapped into this process (own one included)
+};
+
+// what a rank needs to read a peer's particles during the global resampling (pointers valid in THIS process)
+struct PeerPop {
+    const double* theta[2]; const double* logpi[2]; const double* delta[2]; const double* blob[2];
+    const uint32_t* alive_list;
+    uint32_t N, id0;
+};
+struct PeerTable { PeerPop p[XCHG_MAXR]; };
+
 // device pointers of one population, passed to kernels by value
 struct PopDev {
     double* theta[2];
@@ -52,9 +77,12 @@ struct PopDev {
     int32_t* inds;                // N resampling indices (0-based)
     double* hist;                 // hist_cap x 8 history records
     SeqTab* tabs;                 // [0]: weights, [1]: strata edges
-    uint32_t N;
-    uint32_t id0;
+    uint32_t N;                   // particles of this rank
+    uint32_t id0;                 // global index of this rank's first particle
     uint32_t ntiles;
+    uint32_t Ng;                  // particles of the whole (sharded) population; == N on one GPU
+    XchgDev x;
+    const PeerTable* peers;       // device table, sharded runs only
 };
 
 struct SweepInj {
@@ -105,6 +133,20 @@ int launch_mc_prepare(cudaStream_t, uint32_t N, const double* delta_live, double
                       void* tmp, size_t tmp_bytes);
 size_t mc_sort_tmp_bytes(int64_t N);
 
+// sharded runs, host side (comm.cu)
+struct Comm;
+int nccl_unique_id(void* id128, std::string* why);
+int comm_create(int rank, int world, const void* id128, cudaStream_t st, Comm** out, std::string* why);
+void comm_destroy(Comm* cm);
+const char* comm_error(const Comm* cm);
+int comm_rank(const Comm* cm);
+int comm_world(const Comm* cm);
+int comm_barrier(Comm* cm, cudaStream_t st);
+int comm_allgather(Comm* cm, cudaStream_t st, const void* in, void* out, size_t bytes);
+int comm_shared_slab(Comm* cm, cudaStream_t st, size_t need, char** slab);
+int comm_begin_run(Comm* cm, cudaStream_t st, const PopDev& P, XchgDev* x, const PeerTable** d_peers);
+int comm_selftest(Comm* cm, cudaStream_t st, int rounds, unsigned long long* result, double* us_per_round);
+
 }  // namespace abcdez
 
 struct abcdez_ctx {
@@ -112,7 +154,7 @@ struct abcdez_ctx {
     cudaStream_t stream;
     bool own_stream;
     int rank, world;
-    void* nccl_comm;
+    abcdez::Comm* comm;           // non-null after abcdez_comm_init with world > 1
     int sm_count;
     std::vector<cudaEvent_t> ev_pool;   // reused by profile=1 runs (cudaEventCreate costs ~0.2 ms each)
     // device arena: populations are carved from one slab that lives as long as the context, so repeated
@@ -140,7 +182,7 @@ struct abcdez_pop {
     abcdez::PopDev dev;
     abcdez::Ctrl* h_ctrl;         // pinned mirror
     char* slab; size_t slab_bytes;   // all device arrays of the population live in this slab
-    bool slab_from_arena, h_ctrl_from_pool;
+    bool slab_from_arena, slab_shared, h_ctrl_from_pool;
     int64_t N;
     int D, DS, NB;
     int hist_cap;

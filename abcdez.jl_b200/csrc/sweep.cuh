@@ -18,6 +18,7 @@
 #pragma once
 #include "internal.h"
 #include "ctrl.cuh"
+#include "comm.cuh"
 
 namespace abcdez {
 
@@ -37,16 +38,37 @@ __device__ __forceinline__ void sweep_collect(Ctrl* c, bool with_extrema)
     c->acc.sweep_nsims = 0ull; c->acc.sweep_naccs = 0ull;
 }
 
+// sharded runs: replace this rank's sweep counters by the sums over all ranks (in-kernel exchange, comm.cuh);
+// integers, so every rank holds the same totals and takes the same early-exit / stop decisions
+static __device__ __noinline__ void sweep_exchange(const PopDev& P, Ctrl* c, bool with_extrema)
+{
+    unsigned long long rec[5] = { c->last_nsims, c->last_naccs, (unsigned long long)c->err, f64_key(c->dmin), f64_key(c->dmax) };
+    const unsigned slot = xchg_small(P.x, c, rec, with_extrema ? 5 : 3);
+    unsigned long long ns = 0ull, na = 0ull, e = 0ull, mn = ~0ull, mx = 0ull;
+    for (int r = 0; r < P.x.world; ++r) {
+        ns += xchg_word(P.x, slot, r, 0); na += xchg_word(P.x, slot, r, 1);
+        unsigned long long er = xchg_word(P.x, slot, r, 2); e = er > e ? er : e;
+        if (with_extrema) {
+            unsigned long long a = xchg_word(P.x, slot, r, 3), b = xchg_word(P.x, slot, r, 4);
+            mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+        }
+    }
+    c->last_nsims = ns; c->last_naccs = na;
+    if (e && !c->err) c->err = (int)e;
+    if (with_extrema) { c->dmin = key_f64(mn); c->dmax = key_f64(mx); }
+}
+
 __device__ inline void ctrl_after_smc_sweep(const PopDev& P, Ctrl* c)
 {
     sweep_collect(c, false);
+    if (P.x.world > 1) sweep_exchange(P, c, false);
     c->nsims_total += (long long)c->last_nsims;
     c->naccs_iter += c->last_naccs;
     c->cur ^= 1;                                   // swap buffers, :347-350
     c->sweep_epoch += 1;
     c->sweep_idx += 1;
     c->n_sweeps += 1;
-    if ((double)c->naccs_iter / (double)c->n_alive >= c->Kmcmc_min) {   // :352
+    if ((double)c->naccs_iter / (double)c->n_alive_g >= c->Kmcmc_min) {   // :352
         c->Ki = c->sweep_idx; c->sweeps_done = 1;
     } else if (c->sweep_idx >= c->Kmcmc) {
         c->sweeps_done = 1;
@@ -54,9 +76,10 @@ __device__ inline void ctrl_after_smc_sweep(const PopDev& P, Ctrl* c)
     if (c->sweeps_done) ctrl_end_iter(P, c);       // :357-376
 }
 
-__device__ inline void ctrl_after_mc_sweep(Ctrl* c)
+__device__ inline void ctrl_after_mc_sweep(const PopDev& P, Ctrl* c)
 {
     sweep_collect(c, true);
+    if (P.x.world > 1) sweep_exchange(P, c, true);     // global extrema(delta), src/abcdez_mc.jl:146
     c->nsims_total += (long long)c->last_nsims;
     c->cur ^= 1;
     c->sweep_epoch += 1;
@@ -420,7 +443,7 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
         if (inj.flags) inj.flags[i] = flag;
         kdl = f64_key(dli);                                                // extrema(delta), src/abcdez_mc.jl:146
     }
-    if (sweep_finish<true>(c, &s_red, nsim, nacc, i < N ? kdl : ~0ull, i < N ? kdl : 0ull, err)) ctrl_after_mc_sweep(c);
+    if (sweep_finish<true>(c, &s_red, nsim, nacc, i < N ? kdl : ~0ull, i < N ? kdl : 0ull, err)) ctrl_after_mc_sweep(P, c);
 }
 
 // one dist! evaluation per row (stage-level model parity); dense N x D input

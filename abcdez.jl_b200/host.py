@@ -70,7 +70,7 @@ class _McResult(C.Structure):
 # every symbol include/abcdez_cuda.h declares (tests check the library exports all of them)
 EXPORTS = [
     "abcdez_init", "abcdez_destroy", "abcdez_version", "abcdez_last_error", "abcdez_sync",
-    "abcdez_nccl_unique_id", "abcdez_comm_init",
+    "abcdez_nccl_unique_id", "abcdez_comm_init", "abcdez_shard_range", "abcdez_comm_selftest",
     "abcdez_prior_create", "abcdez_prior_destroy", "abcdez_prior_sample", "abcdez_prior_logpdf", "abcdez_prior_push",
     "abcdez_model_count", "abcdez_model_name", "abcdez_model_lookup", "abcdez_model_info", "abcdez_model_bind",
     "abcdez_model_destroy", "abcdez_simulate", "abcdez_kernel_pdf", "abcdez_kernel_logpdf",
@@ -216,6 +216,26 @@ class Context:
         self._h = C.c_void_p()
         _check(lib().abcdez_init(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = device
+        self.rank, self.world = 0, 1
+
+    # ---- sharded runs (one process per GPU), include/abcdez_cuda.h "sharded runs" -----------------
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().abcdez_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: Optional[bytes]):
+        """Collective.  After it abcdesmc/abcdemc on this context run ONE population sharded over `world` GPUs."""
+        if world > 1 and (unique_id is None or len(unique_id) != 128):
+            raise ABCdeZError(ERR_BAD_ARG, "comm_init: unique_id must be the 128 bytes of Context.nccl_unique_id()")
+        _check(lib().abcdez_comm_init(self._h, int(rank), int(world), unique_id))
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_selftest(self, rounds: int = 16):
+        chk = C.c_uint64(); us = C.c_double()
+        _check(lib().abcdez_comm_selftest(self._h, int(rounds), C.byref(chk), C.byref(us)))
+        return chk.value, us.value
 
     def sync(self):
         _check(lib().abcdez_sync(self._h))
@@ -233,6 +253,13 @@ class Context:
 
 
 _default_ctx: Optional[Context] = None
+
+
+def shard_range(N: int, rank: int, world: int):
+    """The contiguous block [lo, hi) of global particle indices owned by `rank` (abcdez_shard_range)."""
+    lo, hi = C.c_int64(), C.c_int64()
+    _check(lib().abcdez_shard_range(C.c_int64(N), int(rank), int(world), C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
 
 
 def default_context() -> Context:
@@ -504,7 +531,11 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     N, d, B = int(nparticles), len(fprior), dist.blob_bytes
     o = _SmcOpts()
     lib().abcdez_smc_opts_default(C.byref(o))
-    o.nparticles = N; o.alpha = alpha; o.delta_ess = delta_ess; o.nsims_max = int(nsims_max); o.Kmcmc = int(Kmcmc)
+    Nglobal = N
+    if ctx.world > 1:                         # sharded: this rank returns the rows of its own block
+        lo, hi = shard_range(Nglobal, ctx.rank, ctx.world)
+        N = hi - lo
+    o.nparticles = Nglobal; o.alpha = alpha; o.delta_ess = delta_ess; o.nsims_max = int(nsims_max); o.Kmcmc = int(Kmcmc)
     o.Kmcmc_min = float(Kmcmc_min); o.kernel = _kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
     o.facc_tune = facc_tune; o.seed = _seed_from(rng); o.verboseout = int(verboseout); o.max_iters = int(max_iters)
     o.exact_scan = int(exact_scan); o.profile = int(profile); o.sync_every = int(sync_every)
@@ -523,7 +554,8 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     if r.status == ERR_NO_ALIVE and verbose:
         print("Warning: No alive particles")                                 # src/abcdez_smc.jl:375
     stats = dict(n_resamples=r.n_resamples, n_sweeps=r.n_sweeps, n_launches=r.n_launches, sweep_ms=r.sweep_ms,
-                 total_ms=r.total_ms, init_ms=r.init_ms, seed=o.seed)
+                 total_ms=r.total_ms, init_ms=r.init_ms, seed=o.seed, rank=ctx.rank, world=ctx.world,
+                 nparticles=Nglobal)
     Pout = P[:, 0] if scalar else P
     out = SMCResult(Pout, W, Cc, r.eps, r.logZ, _blob_view(bl, B), iters=r.iters, nsims=r.nsims, status=r.status,
                     stats=stats)

@@ -79,11 +79,23 @@ int abcdez_version(void);
 const char* abcdez_last_error(void);       /* thread-local message of the last failure */
 int abcdez_sync(abcdez_ctx* ctx);          /* cudaStreamSynchronize on the context stream */
 
-/* Multi-GPU (one process per GPU): attach rank/world and an NCCL unique id (128 bytes,
- * from abcdez_nccl_unique_id on rank 0, distributed by the caller).  libnccl.so.2 is
- * dlopen-ed on first use.  id0 is the global index of this rank's first particle. */
+/* ---- sharded runs: one process per GPU, particles in contiguous blocks ----------------
+ * Replaces the `parallel=true` executor of src/abcdez_smc.jl:237 / src/abcdez_mc.jl:112 across GPUs.
+ * abcdez_nccl_unique_id: rank 0 creates a 128-byte ncclUniqueId; the caller distributes it (MPI,
+ * torch.distributed, Julia Distributed ...).  abcdez_comm_init (collective): libnccl.so.2 is dlopen-ed and
+ * used for the host-level plumbing only (IPC handle all-gathers, barriers); it maps every rank's mailbox
+ * over CUDA IPC so that the per-iteration exchanges (eps-quantile histograms, weight sums, ESS, counters)
+ * run INSIDE the kernels over NVLink peer memory and the resampling gathers read peer particles directly.
+ * After it, abcdez_smc_run / abcdez_mc_run on this context are collective: opts.nparticles is the size
+ * of the whole population, this rank owns the block abcdez_shard_range(nparticles, rank, world) and fills
+ * its result buffers with that block's rows; scalars and histories are global and identical on all ranks.
+ * DE partners are drawn inside the rank's block (island variant); everything else is global. */
 int abcdez_nccl_unique_id(void* id128);
 int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void* id128);
+int abcdez_shard_range(int64_t N, int rank, int world, int64_t* lo, int64_t* hi);
+/* `rounds` in-kernel exchanges (one histogram-sized and one scalar record each); checksum is a known
+ * function of (world, rounds) -- see tests/test_multi_gpu.py -- and us_per_round their latency */
+int abcdez_comm_selftest(abcdez_ctx* ctx, int rounds, uint64_t* checksum, double* us_per_round);
 
 /* ---- prior: Factored(dists...) src/abcdez_priors.jl:18-61 ------------------------------ */
 int abcdez_prior_create(abcdez_ctx* ctx, int d, const int32_t* family, const double* params /* d x 4 */,

@@ -820,11 +820,11 @@ static int64_t wsample_faithful(const uint8_t* alive, int64_t N, double u)
 
 /* same answer in O(1) from the compacted list of alive indices:
  * the ceil(t)-th alive particle, and index 0 when t == 0. */
-static inline int64_t wsample_list(const uint32_t* alive_list, int64_t n_alive, double u)
+static inline int64_t wsample_list(const uint32_t* alive_list, int64_t n_alive, double u, int64_t first)
 {
     double t = u * (double)n_alive;
     int64_t k = (int64_t)ceil(t);
-    if (k <= 0) return 0;
+    if (k <= 0) return first;      /* index 1 of the (sub)population, alive or not */
     if (k > n_alive) k = n_alive;
     return (int64_t)alive_list[k - 1];
 }
@@ -845,20 +845,37 @@ static int64_t build_alive_list(const uint8_t* alive, int64_t N, uint32_t* list)
  * pre-filled with a copy of g (smc.jl:337-340).  inj_* may be NULL (Philox
  * contract) or per-particle arrays (indices 0-based).  flags[i] gets
  * FLAG_SIM / FLAG_ACC. */
-int orc_smc_sweep(int d, const int32_t* family, const double* params, int model, const double* data,
+/* islands > 1 (sharded runs of the CUDA library): the population is cut into `islands`
+ * contiguous blocks [floor(r N / R), floor((r+1) N / R)) and the DE partners of a particle are drawn from
+ * the alive particles of its own block (the north-star's rank-local subpopulations); islands = 1 is the
+ * reference's global pool (src/abcdez_smc.jl:121). */
+#define ORC_MAX_ISLANDS 64
+int orc_smc_sweep_islands(int d, const int32_t* family, const double* params, int model, const double* data,
                   int64_t N, const double* theta, const double* logpi, const double* delta,
                   const uint8_t* blobs, const uint8_t* alive,
                   double eps, int kind, double gamma0, double gsig,
                   uint64_t seed, uint32_t epoch, int64_t id0,
                   const int32_t* inj_a, const int32_t* inj_b, const double* inj_z, const double* inj_u,
-                  int faithful_wsample,
+                  int faithful_wsample, int islands,
                   double* ntheta, double* nlogpi, double* ndelta, uint8_t* nblobs, uint8_t* flags,
                   int64_t* nsims_out, int64_t* naccs_out)
 {
     prior_t pr; mk_prior(&pr, d, family, params);
     int B = MODELS[model].blob;
+    if (islands < 1) islands = 1;
+    if (islands > ORC_MAX_ISLANDS) return 1;
     uint32_t* alist = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(N > 0 ? N : 1));
-    int64_t n_alive = build_alive_list(alive, N, alist);
+    int64_t isl_lo[ORC_MAX_ISLANDS + 1], isl_off[ORC_MAX_ISLANDS + 1];
+    {   /* per-island alive lists, stored back to back */
+        int64_t n = 0;
+        for (int r = 0; r < islands; ++r) {
+            isl_lo[r] = (int64_t)(((__int128)N * r) / islands);
+            int64_t hi = (int64_t)(((__int128)N * (r + 1)) / islands);
+            isl_off[r] = n;
+            for (int64_t i = isl_lo[r]; i < hi; ++i) if (alive[i]) alist[n++] = (uint32_t)i;
+        }
+        isl_lo[islands] = N; isl_off[islands] = n;
+    }
     int64_t nsims = 0, naccs = 0; int fail = 0;
     memcpy(ntheta, theta, sizeof(double) * (size_t)(N * d));
     memcpy(nlogpi, logpi, sizeof(double) * (size_t)N);
@@ -870,6 +887,10 @@ int orc_smc_sweep(int d, const int32_t* family, const double* params, int model,
         if (!alive[i]) continue;                                           /* :114 */
         uint32_t pid = (uint32_t)(id0 + i);
         int64_t a, b;
+        int isl = 0;
+        while (isl + 1 < islands && i >= isl_lo[isl + 1]) isl++;
+        const uint32_t* ilist = alist + isl_off[isl];
+        const int64_t in_alive = isl_off[isl + 1] - isl_off[isl], ifirst = isl_lo[isl];
         if (inj_a && inj_b) { a = inj_a[i]; b = inj_b[i]; }
         else {
             stream_t ps = mk_stream(seed, pid, epoch, TAG_PARTNER);
@@ -878,13 +899,13 @@ int orc_smc_sweep(int d, const int32_t* family, const double* params, int model,
             while (a == i) {                                               /* :119-122 */
                 if (att >= ORC_PARTNER_MAX_ATTEMPTS) { fail = 1; break; }
                 stream_u2(&ps, att++, &u1, &u2);
-                a = faithful_wsample ? wsample_faithful(alive, N, u1) : wsample_list(alist, n_alive, u1);
+                a = faithful_wsample ? wsample_faithful(alive, N, u1) : wsample_list(ilist, in_alive, u1, ifirst);
             }
             att = 0; b = a;
             while (b == a || b == i) {                                     /* :123-126 */
                 if (att >= ORC_PARTNER_MAX_ATTEMPTS) { fail = 1; break; }
                 stream_u2(&ps, att++, &u1, &u2);
-                b = faithful_wsample ? wsample_faithful(alive, N, u2) : wsample_list(alist, n_alive, u2);
+                b = faithful_wsample ? wsample_faithful(alive, N, u2) : wsample_list(ilist, in_alive, u2, ifirst);
             }
             if (fail) continue;
         }
@@ -928,6 +949,21 @@ int orc_smc_sweep(int d, const int32_t* family, const double* params, int model,
     if (nsims_out) *nsims_out = nsims;
     if (naccs_out) *naccs_out = naccs;
     return fail ? 6 : 0;
+}
+
+int orc_smc_sweep(int d, const int32_t* family, const double* params, int model, const double* data,
+                  int64_t N, const double* theta, const double* logpi, const double* delta,
+                  const uint8_t* blobs, const uint8_t* alive,
+                  double eps, int kind, double gamma0, double gsig,
+                  uint64_t seed, uint32_t epoch, int64_t id0,
+                  const int32_t* inj_a, const int32_t* inj_b, const double* inj_z, const double* inj_u,
+                  int faithful_wsample,
+                  double* ntheta, double* nlogpi, double* ndelta, uint8_t* nblobs, uint8_t* flags,
+                  int64_t* nsims_out, int64_t* naccs_out)
+{
+    return orc_smc_sweep_islands(d, family, params, model, data, N, theta, logpi, delta, blobs, alive, eps, kind,
+                                 gamma0, gsig, seed, epoch, id0, inj_a, inj_b, inj_z, inj_u, faithful_wsample, 1,
+                                 ntheta, nlogpi, ndelta, nblobs, flags, nsims_out, naccs_out);
 }
 
 /* Statistics.quantile(v, p) default (type 7) over the alive distances,
@@ -1057,6 +1093,7 @@ typedef struct {
     uint64_t seed;
     int32_t faithful_wsample;   /* 1: O(N) StatsBase scan, 0: O(1) alive list */
     int32_t max_iters;          /* safety bound for benchmarks; 0 = unbounded */
+    int32_t islands;            /* 0/1: the reference's global partner pool; R > 1: rank-local partners (sharded runs) */
 } orc_smc_opts;
 
 typedef struct {
@@ -1160,9 +1197,9 @@ int orc_smc_run(int d, const int32_t* family, const double* params, int model, c
         for (int i = 1; i <= o->Kmcmc; ++i) {                              /* :336-353 */
             int64_t ns = 0, na = 0;
             double t0 = now_s();
-            rc = orc_smc_sweep(d, family, params, model, data, N, th, lp, dl, bl, alive, eps, o->kind,
+            rc = orc_smc_sweep_islands(d, family, params, model, data, N, th, lp, dl, bl, alive, eps, o->kind,
                                gamma0, gsig, o->seed, sweep_epoch++, 0, NULL, NULL, NULL, NULL,
-                               o->faithful_wsample, nth, nlp, ndl, nbl, NULL, &ns, &na);
+                               o->faithful_wsample, o->islands, nth, nlp, ndl, nbl, NULL, &ns, &na);
             res->sweep_seconds += now_s() - t0; res->nsweeps++;
             if (rc) break;
             nsims += ns; naccs += na;

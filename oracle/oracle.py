@@ -43,7 +43,7 @@ class _SmcOpts(C.Structure):
                 ("nsims_max", C.c_int64), ("Kmcmc", C.c_int32), ("Kmcmc_min", C.c_double),
                 ("kind", C.c_int32), ("facc_stop", C.c_double), ("facc_min", C.c_double),
                 ("facc_tune", C.c_double), ("seed", C.c_uint64), ("faithful_wsample", C.c_int32),
-                ("max_iters", C.c_int32)]
+                ("max_iters", C.c_int32), ("islands", C.c_int32)]
 
 
 class _SmcResult(C.Structure):
@@ -286,11 +286,13 @@ class SmcOut:
 
 def smc_run(prior, model, data, eps_target, nparticles=100, alpha=0.95, delta_ess=0.5, nsims_max=10**7,
             Kmcmc=3, Kmcmc_min=1.0, kind="indicator_strict", facc_stop=0.0, facc_min=0.0, facc_tune=0.975,
-            seed=1, faithful=False, max_iters=0, hist_cap=4096):
+            seed=1, faithful=False, max_iters=0, hist_cap=4096, islands=1):
+    """islands = R > 1: DE partners are drawn inside R contiguous blocks of the population (the sharded
+    runs of the CUDA library); everything else (quantile, weights, resampling) stays global."""
     d, fam, par = _prior_args(prior)
     mid = model_id(model); B = model_blob(model); N = nparticles
     o = _SmcOpts(N, alpha, delta_ess, nsims_max, Kmcmc, Kmcmc_min, KERNELS[kind], facc_stop, facc_min,
-                 facc_tune, seed, int(faithful), max_iters)
+                 facc_tune, seed, int(faithful), max_iters, int(islands))
     r = _SmcResult()
     P = np.empty((N, d)); W = np.empty(N); Cc = np.empty(N); bl = np.zeros((N, max(B, 1)), dtype=np.uint8)
     h = {k: np.zeros(hist_cap) for k in ("eps", "dmin", "dmax", "logZ", "ess", "facc", "gamma0")}
