@@ -116,13 +116,14 @@ extern "C" int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void
     return ABCDEZ_OK;
 }
 
-extern "C" int abcdez_comm_selftest(abcdez_ctx* ctx, int rounds, uint64_t* checksum, double* us_per_round)
+extern "C" int abcdez_comm_selftest(abcdez_ctx* ctx, int rounds, int mode, uint64_t* checksum, double* us_per_round)
 {
     CHECK_ARG(ctx && ctx->comm && checksum, "abcdez_comm_selftest: needs a context with a communicator");
     CHECK_ARG(rounds >= 1 && rounds <= 100000, "abcdez_comm_selftest: rounds out of range");
+    CHECK_ARG(mode == 0 || mode == 1, "abcdez_comm_selftest: mode must be 0 (fenced ring) or 1 (low-latency ring)");
     CU(cudaSetDevice(ctx->device));
     unsigned long long r = 0;
-    int rc = comm_selftest(ctx->comm, ctx->stream, rounds, &r, us_per_round);
+    int rc = comm_selftest(ctx->comm, ctx->stream, rounds, mode, &r, us_per_round);
     *checksum = r;
     return rc ? fail(rc, std::string("abcdez_comm_selftest: ") + comm_error(ctx->comm)) : ABCDEZ_OK;
 }
@@ -623,6 +624,7 @@ extern "C" int abcdez_pop_mc_sweep(abcdez_pop* pop, double eps_pop, double eps_t
 {
     CHECK_ARG(pop != nullptr, "abcdez_pop_mc_sweep: pop is NULL");
     CHECK_ARG((inj_a == nullptr) == (inj_b == nullptr), "abcdez_pop_mc_sweep: inject both partners or neither");
+    if (!pop->ops->mc_sweep) return fail(ABCDEZ_ERR_UNSUPPORTED, "abcdez_pop_mc_sweep: this model has no abcdemc! sweep in this build");
     CU(cudaSetDevice(pop->ctx->device));
     int rc = pull_ctrl(pop); if (rc) return rc;
     rc = mc_prepare(pop); if (rc) return rc;
@@ -1012,6 +1014,7 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
     CHECK_ARG(0.0 <= eps_target, "\xcf\xb5_target must be non-negative");      // src/abcdez_mc.jl:108
     CHECK_ARG(5 <= o->nparticles, "nparticles must be at least 5");          // :109
     CHECK_ARG(1 <= o->generations, "generations must be at least 1");        // :110
+    if (!model->ops->mc_sweep) return fail(ABCDEZ_ERR_UNSUPPORTED, std::string("abcdemc!: model '") + model->ops->name + "' has no abcdemc! sweep in this build");
     CU(cudaSetDevice(ctx->device));
     const int64_t N = o->nparticles;
     abcdez_pop* pop = nullptr;

@@ -241,30 +241,42 @@ int comm_begin_run(Comm* cm, cudaStream_t st, const PopDev& P, XchgDev* x, const
     return ABCDEZ_OK;
 }
 
-// ---- self test: R rounds of the in-kernel exchange (used by the multi-GPU tests and the latency probe) ---
-__global__ void xchg_selftest_kernel(XchgDev X, Ctrl* c, int rounds, unsigned long long* out, unsigned* hist)
+// ---- self test: rounds of the in-kernel exchanges (used by the multi-GPU tests and the latency probe) ---
+// mode 0: fenced ring (xchg_block + xchg_small); mode 1: low-latency ring (xchg_ll_block + xchg_ll_warp)
+__global__ void xchg_selftest_kernel(XchgDev X, Ctrl* c, int rounds, int mode, unsigned long long* out, unsigned* hist)
 {
     __shared__ unsigned long long s_h[4];
+    __shared__ unsigned long long s_all[XCHG_MAXR * 4];
     __shared__ int s_flag;
     unsigned long long acc = 0ull;
     for (int it = 0; it < rounds; ++it) {
-        if (threadIdx.x == 0) { s_h[0] = (unsigned long long)(X.rank + 1) * 1000ull + it; s_h[1] = it; }
+        if (threadIdx.x == 0) { s_h[0] = (unsigned long long)(X.rank + 1) * 1000ull + it; s_h[1] = 0x100000000ull * (X.rank + 1) + it; }
         for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) hist[b] = (unsigned)(X.rank * 7 + b + it);
         __threadfence();
         __syncthreads();
-        unsigned slot = xchg_block(X, c, s_h, 2, hist, SEL_BINS, &s_flag);
-        for (int r = 0; r < X.world; ++r) {
-            acc += xchg_word(X, slot, r, 0);
-            for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) acc += __ldcg(xchg_body(X, slot, r) + b);
-        }
-        if (threadIdx.x == 0) {
-            unsigned long long rec[2] = { (unsigned long long)X.rank, (unsigned long long)it };
-            unsigned s2 = xchg_small(X, c, rec, 2);
-            for (int r = 0; r < X.world; ++r) acc += xchg_word(X, s2, r, 0) * 3ull + xchg_word(X, s2, r, 1);
+        if (mode == 0) {
+            unsigned slot = xchg_block(X, c, s_h, 2, hist, SEL_BINS, &s_flag);
+            for (int r = 0; r < X.world; ++r) {
+                if (threadIdx.x == 0) acc += xchg_word(X, slot, r, 0) + (xchg_word(X, slot, r, 1) >> 32);
+                for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) acc += __ldcg(xchg_body(X, slot, r) + b);
+            }
+            if (threadIdx.x == 0) {
+                unsigned long long rec[2] = { (unsigned long long)X.rank, (unsigned long long)it };
+                unsigned s2 = xchg_small(X, c, rec, 2);
+                for (int r = 0; r < X.world; ++r) acc += xchg_word(X, s2, r, 0) * 3ull + xchg_word(X, s2, r, 1);
+            }
+        } else {
+            xchg_ll_block(X, c, s_h, 2, hist, SEL_BINS, s_all, &s_flag);      // hist <- sum over ranks
+            for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) acc += __ldcg(&hist[b]);
+            if (threadIdx.x == 0) for (int r = 0; r < X.world; ++r) acc += s_all[2 * r] + (s_all[2 * r + 1] >> 32);
+            if (threadIdx.x < 32) {
+                unsigned long long rec[2] = { (unsigned long long)X.rank, (unsigned long long)it }, got[2];
+                bool valid = xchg_ll_warp<2>(X, c, rec, got);
+                if (valid) acc += got[0] * 3ull + got[1];
+            }
         }
         __syncthreads();
     }
-    // block-wide sum of acc (order independent: integers)
     __shared__ unsigned long long s_acc;
     if (threadIdx.x == 0) s_acc = 0ull;
     __syncthreads();
@@ -273,7 +285,7 @@ __global__ void xchg_selftest_kernel(XchgDev X, Ctrl* c, int rounds, unsigned lo
     if (threadIdx.x == 0) *out = s_acc;
 }
 
-int comm_selftest(Comm* cm, cudaStream_t st, int rounds, unsigned long long* result, double* us_per_round)
+int comm_selftest(Comm* cm, cudaStream_t st, int rounds, int mode, unsigned long long* result, double* us_per_round)
 {
     Ctrl* d_ctrl = nullptr; unsigned long long* d_out = nullptr; unsigned* d_hist = nullptr;
     CM_CU(cudaMalloc((void**)&d_ctrl, sizeof(Ctrl))); CM_CU(cudaMalloc((void**)&d_out, 8)); CM_CU(cudaMalloc((void**)&d_hist, SEL_BINS * 4));
@@ -286,9 +298,9 @@ int comm_selftest(Comm* cm, cudaStream_t st, int rounds, unsigned long long* res
     for (int q = 0; q < XCHG_MAXR; ++q) x.mbox[q] = q < cm->world ? cm->peer_mbox[q] : nullptr;
     cudaEvent_t e0, e1;
     CM_CU(cudaEventCreate(&e0)); CM_CU(cudaEventCreate(&e1));
-    xchg_selftest_kernel<<<1, 256, 0, st>>>(x, d_ctrl, 2, d_out, d_hist);       // warm-up
+    xchg_selftest_kernel<<<1, 256, 0, st>>>(x, d_ctrl, 2, mode, d_out, d_hist);       // warm-up
     CM_CU(cudaEventRecord(e0, st));
-    xchg_selftest_kernel<<<1, 256, 0, st>>>(x, d_ctrl, rounds, d_out, d_hist);
+    xchg_selftest_kernel<<<1, 256, 0, st>>>(x, d_ctrl, rounds, mode, d_out, d_hist);
     CM_CU(cudaEventRecord(e1, st));
     CM_CU(cudaGetLastError());
     Ctrl h;

@@ -38,7 +38,8 @@ struct HeadSmem {
     unsigned long long wmin[32];
     unsigned long long mn, mx, mab;
     unsigned found_bin, found_before, flag;
-    unsigned long long xh[8];                     // sharded runs: header record of an exchange
+    unsigned long long xh[8];                     // sharded runs: this rank's header record of an exchange
+    unsigned long long xall[XCHG_MAXR * 8];       // ... and every rank's, after it
     int xflag;
 };
 
@@ -164,16 +165,11 @@ __device__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins,
         s->xh[2] = (unsigned long long)(e0 > e1 ? e0 : e1);
     }
     __syncthreads();
-    const unsigned slot = xchg_block(P.x, c, s->xh, first ? 3 : 0, H, nbins, &s->xflag);
-    for (int b = tid; b < nbins; b += HEAD_THREADS) {
-        unsigned tot = 0;
-        for (int r = 0; r < P.x.world; ++r) tot += __ldcg(xchg_body(P.x, slot, r) + b);
-        H[b] = tot;
-    }
+    xchg_ll_block(P.x, c, s->xh, first ? 3 : 0, H, nbins, s->xall, &s->xflag);
     if (tid == 0 && first) {
         unsigned long long mn = ~0ull, mx = 0ull, e = 0ull;
         for (int r = 0; r < P.x.world; ++r) {
-            unsigned long long a = xchg_word(P.x, slot, r, 0), b = xchg_word(P.x, slot, r, 1), er = xchg_word(P.x, slot, r, 2);
+            unsigned long long a = s->xall[3 * r], b = s->xall[3 * r + 1], er = s->xall[3 * r + 2];
             mn = a < mn ? a : mn; mx = b > mx ? b : mx; e = er > e ? er : e;
         }
         __stcg(&c->acc.dmin_key, mn); __stcg(&c->acc.dmax_key, mx);
@@ -182,8 +178,8 @@ __device__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins,
 }
 
 // candidate-list bookkeeping of generation g: global count / extrema / min-above into c->acc.g_*; when the
-// global list fits the per-CTA tail (and is not all-equal) every rank's candidates are gathered into every
-// rank's mailbox (XCHG_GCAND_OFF) so that the tail runs on the same multiset everywhere
+// global list fits the per-CTA tail (and is not all-equal) this rank's candidates are posted into every
+// rank's mailbox (XCHG_GCAND_OFF), where every CTA of every rank collects the same multiset for the tail
 __device__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
 {
     const unsigned tid = threadIdx.x;
@@ -192,35 +188,27 @@ __device__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
         s->xh[2] = __ldcg(&c->acc.cand_max[g]); s->xh[3] = __ldcg(&c->acc.min_above);
     }
     __syncthreads();
-    const unsigned slot = xchg_block(P.x, c, s->xh, 4, nullptr, 0, &s->xflag);
+    xchg_ll_block(P.x, c, s->xh, 4, nullptr, 0, s->xall, &s->xflag);
     unsigned long long M = 0ull, off = 0ull, mn = ~0ull, mx = 0ull, mab = ~0ull;
     for (int r = 0; r < P.x.world; ++r) {
-        unsigned long long m = xchg_word(P.x, slot, r, 0), a = xchg_word(P.x, slot, r, 1), b = xchg_word(P.x, slot, r, 2),
-                           ab = xchg_word(P.x, slot, r, 3);
+        unsigned long long m = s->xall[4 * r], a = s->xall[4 * r + 1], b = s->xall[4 * r + 2], ab = s->xall[4 * r + 3];
         if (r < P.x.rank) off += m;
         M += m; mn = a < mn ? a : mn; mx = b > mx ? b : mx; mab = ab < mab ? ab : mab;
     }
-    const unsigned long long mine = s->xh[0];
-    __syncthreads();
     if (tid == 0) {
         c->acc.g_cand_count = M; c->acc.g_cand_min = mn; c->acc.g_cand_max = mx; c->acc.g_min_above = mab;
         c->acc.g_cand_off = off;
     }
-    if (M <= (unsigned long long)XCHG_GCAND && mn != mx) {                 // uniform over ranks
-        const unsigned long long* src = P.cand[g & 1];
-        for (int q = 0; q < P.x.world; ++q) {
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.x.mbox[q] + XCHG_GCAND_OFF) + off;
-            for (unsigned i = tid; i < (unsigned)mine; i += HEAD_THREADS) dst[i] = __ldcg(&src[i]);
-        }
-        xchg_block(P.x, c, nullptr, 0, nullptr, 0, &s->xflag);               // everyone's keys have landed everywhere
-    }
+    if (M <= (unsigned long long)XCHG_GCAND && mn != mx)                   // uniform over ranks
+        ll_post_keys(P.x, P.cand[g & 1], (unsigned)s->xh[0], (unsigned)off);
+    __syncthreads();
 }
 
-// all-gather of the nw-word record the caller put into s->xh (thread 0); returns the mailbox slot
-__device__ unsigned head_xchg_rec(const PopDev& P, Ctrl* c, int nw, HeadSmem* s)
+// all-gather of the nw-word record the caller put into s->xh (thread 0): rank r's words at s->xall[nw*r ...]
+__device__ void head_xchg_rec(const PopDev& P, Ctrl* c, int nw, HeadSmem* s)
 {
     __syncthreads();
-    return xchg_block(P.x, c, s->xh, nw, nullptr, 0, &s->xflag);
+    xchg_ll_block(P.x, c, s->xh, nw, nullptr, 0, s->xall, &s->xflag);
 }
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constant__ PopDev P)
@@ -408,9 +396,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         akey = cmin;
         bkey = (rank + 1 < Mg) ? akey : min_above;
     } else {                                                // Mg <= CAND_SMEM (after p_next == 6 all keys are equal)
-        const unsigned long long* L = sharded ? reinterpret_cast<const unsigned long long*>(P.x.mbox[P.x.rank] + XCHG_GCAND_OFF)
-                                              : P.cand[g & 1];
-        for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&L[i]);
+        if (sharded) ll_collect_keys(P.x, c, (unsigned)Mg, s.cand);        // every rank's candidates, from the local mailbox
+        else { for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&P.cand[g & 1][i]); }
         __syncthreads();
         tail_select(s.cand, (unsigned)Mg, p_next, prefix, himask, rank, min_above, &s, akey, bkey);
     }
@@ -453,10 +440,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
     if (sharded) {                                          // wnorm = sum over ranks, rank order (exchange 2)
         if (blockIdx.x == 0) {
             if (tid == 0) s.xh[0] = (unsigned long long)__double_as_longlong(wnorm);
-            const unsigned slot = head_xchg_rec(P, c, 1, &s);
+            head_xchg_rec(P, c, 1, &s);
             if (tid == 0) {
                 double tot = 0.0;
-                for (int r = 0; r < P.x.world; ++r) tot += __longlong_as_double((long long)xchg_word(P.x, slot, r, 0));
+                for (int r = 0; r < P.x.world; ++r) tot += __longlong_as_double((long long)s.xall[r]);
                 c->acc.g_wnorm = tot;
             }
         }
@@ -528,14 +515,14 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
                 s.xh[0] = (unsigned long long)__double_as_longlong(sumsq); s.xh[1] = (unsigned long long)n_alive;
                 s.xh[2] = (unsigned long long)__double_as_longlong(__ldcg(&c->acc.w_alive));
             }
-            const unsigned slot = head_xchg_rec(P, c, 3, &s);
+            head_xchg_rec(P, c, 3, &s);
             if (tid == 0) {
                 double tot = 0.0; unsigned ng = 0;
                 for (int r = 0; r < P.x.world; ++r) {
-                    tot += __longlong_as_double((long long)xchg_word(P.x, slot, r, 0));
-                    unsigned na = (unsigned)xchg_word(P.x, slot, r, 1);
+                    tot += __longlong_as_double((long long)s.xall[3 * r]);
+                    unsigned na = (unsigned)s.xall[3 * r + 1];
                     c->rank_alive[r] = na; ng += na;
-                    if (na) __stcg(&c->acc.w_alive, __longlong_as_double((long long)xchg_word(P.x, slot, r, 2)));   // same double on every rank
+                    if (na) __stcg(&c->acc.w_alive, __longlong_as_double((long long)s.xall[3 * r + 2]));   // same double on every rank
                 }
                 ctrl_after_reweight(P, c, tot, n_alive, ng);                                      // :318-324
             }

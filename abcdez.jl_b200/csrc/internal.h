@@ -40,13 +40,19 @@ constexpr int XCHG_HDR = 32;                      // 64-bit header words per ent
 constexpr int XCHG_BODY = SEL_BINS * 4;           // body bytes per entry (one radix histogram)
 constexpr int XCHG_STRIDE = XCHG_HDR * 8 + XCHG_BODY;
 constexpr int XCHG_GCAND = 4096;                  // gathered candidate keys of the distributed radix select (= CAND_SMEM)
-constexpr size_t XCHG_GCAND_OFF = (size_t)XCHG_RING * XCHG_MAXR * XCHG_STRIDE;
-constexpr size_t XCHG_MBOX_BYTES = XCHG_GCAND_OFF + (size_t)XCHG_GCAND * 8;
+// low-latency region: every 8-byte word carries 32 data bits and the 32-bit sequence number of the exchange
+// that wrote it, so a word is valid as soon as it is seen -- no fence, one NVLink crossing (comm.cuh)
+constexpr int LL_HDR = 32;                        // LL words of an entry's header record (16 64-bit values)
+constexpr int LL_BODY = SEL_BINS;                 // LL words of an entry's body (one radix histogram)
+constexpr size_t LL_STRIDE = (size_t)(LL_HDR + LL_BODY) * 8;
+constexpr size_t XCHG_LL_OFF = (size_t)XCHG_RING * XCHG_MAXR * XCHG_STRIDE;
+constexpr size_t XCHG_GCAND_OFF = XCHG_LL_OFF + (size_t)XCHG_RING * XCHG_MAXR * LL_STRIDE;   // 2 LL words per gathered key
+constexpr size_t XCHG_MBOX_BYTES = XCHG_GCAND_OFF + (size_t)XCHG_GCAND * 16;
 constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct XchgDev {
     int rank, world;                              // world == 1: no exchange anywhere
-    unsigned long long* seq;                      // local exchange counter (device memory)
+    unsigned long long* seq;                      // local exchange counters (device memory): [0] fenced ring, [1] LL ring
     char* mbox[XCHG_MAXR];                        // every rank's mailbox mapped into this process (own one included)
 };
 
@@ -145,7 +151,7 @@ int comm_barrier(Comm* cm, cudaStream_t st);
 int comm_allgather(Comm* cm, cudaStream_t st, const void* in, void* out, size_t bytes);
 int comm_shared_slab(Comm* cm, cudaStream_t st, size_t need, char** slab);
 int comm_begin_run(Comm* cm, cudaStream_t st, const PopDev& P, XchgDev* x, const PeerTable** d_peers);
-int comm_selftest(Comm* cm, cudaStream_t st, int rounds, unsigned long long* result, double* us_per_round);
+int comm_selftest(Comm* cm, cudaStream_t st, int rounds, int mode, unsigned long long* result, double* us_per_round);
 
 }  // namespace abcdez
 

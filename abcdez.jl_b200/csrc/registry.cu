@@ -7,9 +7,8 @@ namespace abcdez {
 const ModelOps* ops_gauss1d(); const ModelOps* ops_gauss1d_blob(); const ModelOps* ops_gauss_corr10();
 const ModelOps* ops_dirac(); const ModelOps* ops_normdu(); const ModelOps* ops_twod(); const ModelOps* ops_twod_inf();
 const ModelOps* ops_mixture(); const ModelOps* ops_wiener(); const ModelOps* ops_lotka_volterra();
-const ModelOps* ops_birth_death(); const ModelOps* ops_socks();
+const ModelOps* ops_birth_death(); const ModelOps* ops_socks(); const ModelOps* ops_gk();
 
-static const ModelOps GK_PENDING = { "gk", 4, 0, nullptr, nullptr, nullptr, nullptr };   // cooperative simulator, later round
 
 const ModelOps* model_ops(int id)
 {
@@ -25,7 +24,7 @@ const ModelOps* model_ops(int id)
     case M_WIENER: return ops_wiener();
     case M_LOTKA_VOLTERRA: return ops_lotka_volterra();
     case M_BIRTH_DEATH: return ops_birth_death();
-    case M_GK: return &GK_PENDING;
+    case M_GK: return ops_gk();            // CTA-cooperative simulator (gk.cu)
     case M_SOCKS: return ops_socks();
     }
     return nullptr;

@@ -38,30 +38,40 @@ __device__ __forceinline__ void sweep_collect(Ctrl* c, bool with_extrema)
     c->acc.sweep_nsims = 0ull; c->acc.sweep_naccs = 0ull;
 }
 
-// sharded runs: replace this rank's sweep counters by the sums over all ranks (in-kernel exchange, comm.cuh);
-// integers, so every rank holds the same totals and takes the same early-exit / stop decisions
-static __device__ __noinline__ void sweep_exchange(const PopDev& P, Ctrl* c, bool with_extrema)
+// sharded runs: the warp that finished the grid replaces this rank's sweep counters by the sums over all ranks
+// (one low-latency in-kernel exchange, comm.cuh); integers, so every rank holds the same totals and takes the
+// same early-exit / stop decisions.  All 32 lanes call; lane 0 writes the control block.
+static __device__ __noinline__ void sweep_exchange_warp(const PopDev& P, Ctrl* c, bool with_extrema)
 {
-    unsigned long long rec[5] = { c->last_nsims, c->last_naccs, (unsigned long long)c->err, f64_key(c->dmin), f64_key(c->dmax) };
-    const unsigned slot = xchg_small(P.x, c, rec, with_extrema ? 5 : 3);
-    unsigned long long ns = 0ull, na = 0ull, e = 0ull, mn = ~0ull, mx = 0ull;
-    for (int r = 0; r < P.x.world; ++r) {
-        ns += xchg_word(P.x, slot, r, 0); na += xchg_word(P.x, slot, r, 1);
-        unsigned long long er = xchg_word(P.x, slot, r, 2); e = er > e ? er : e;
-        if (with_extrema) {
-            unsigned long long a = xchg_word(P.x, slot, r, 3), b = xchg_word(P.x, slot, r, 4);
-            mn = a < mn ? a : mn; mx = b > mx ? b : mx;
-        }
+    const int lane = threadIdx.x & 31;
+    unsigned long long rec[5] = { 0ull, 0ull, 0ull, 0ull, 0ull }, got[5];
+    if (lane == 0) {
+        sweep_collect(c, with_extrema);
+        rec[0] = c->last_nsims; rec[1] = c->last_naccs; rec[2] = (unsigned long long)c->err;
+        rec[3] = f64_key(c->dmin); rec[4] = f64_key(c->dmax);
     }
-    c->last_nsims = ns; c->last_naccs = na;
-    if (e && !c->err) c->err = (int)e;
-    if (with_extrema) { c->dmin = key_f64(mn); c->dmax = key_f64(mx); }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) rec[k] = __shfl_sync(0xffffffffu, rec[k], 0);
+    const bool valid = xchg_ll_warp<5>(P.x, c, rec, got);
+    unsigned long long ns = valid ? got[0] : 0ull, na = valid ? got[1] : 0ull, e = valid ? got[2] : 0ull;
+    unsigned long long mn = valid ? got[3] : ~0ull, mx = valid ? got[4] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ns += __shfl_xor_sync(0xffffffffu, ns, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, e, o); e = t > e ? t : e;
+    }
+    mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+    if (lane == 0) {
+        c->last_nsims = ns; c->last_naccs = na;
+        if (e && !c->err) c->err = (int)e;
+        if (with_extrema) { c->dmin = key_f64(mn); c->dmax = key_f64(mx); }
+    }
+    __syncwarp();
 }
 
 __device__ inline void ctrl_after_smc_sweep(const PopDev& P, Ctrl* c)
 {
-    sweep_collect(c, false);
-    if (P.x.world > 1) sweep_exchange(P, c, false);
+    if (P.x.world == 1) sweep_collect(c, false);   // (sharded: sweep_exchange_warp has collected and reduced)
     c->nsims_total += (long long)c->last_nsims;
     c->naccs_iter += c->last_naccs;
     c->cur ^= 1;                                   // swap buffers, :347-350
@@ -78,8 +88,7 @@ __device__ inline void ctrl_after_smc_sweep(const PopDev& P, Ctrl* c)
 
 __device__ inline void ctrl_after_mc_sweep(const PopDev& P, Ctrl* c)
 {
-    sweep_collect(c, true);
-    if (P.x.world > 1) sweep_exchange(P, c, true);     // global extrema(delta), src/abcdez_mc.jl:146
+    if (P.x.world == 1) sweep_collect(c, true);    // (sharded: global extrema(delta), src/abcdez_mc.jl:146, already reduced)
     c->nsims_total += (long long)c->last_nsims;
     c->cur ^= 1;
     c->sweep_epoch += 1;
@@ -328,7 +337,9 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
             if (inj.flags) inj.flags[i] = flag;
         }
     }
-    if (sweep_finish<false>(c, &s_red, nsim, nacc, 0ull, 0ull, err)) ctrl_after_smc_sweep(P, c);
+    const bool last = sweep_finish<false>(c, &s_red, nsim, nacc, 0ull, 0ull, err);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, false);
+    if (last) ctrl_after_smc_sweep(P, c);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -443,7 +454,9 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
         if (inj.flags) inj.flags[i] = flag;
         kdl = f64_key(dli);                                                // extrema(delta), src/abcdez_mc.jl:146
     }
-    if (sweep_finish<true>(c, &s_red, nsim, nacc, i < N ? kdl : ~0ull, i < N ? kdl : 0ull, err)) ctrl_after_mc_sweep(P, c);
+    const bool last = sweep_finish<true>(c, &s_red, nsim, nacc, i < N ? kdl : ~0ull, i < N ? kdl : 0ull, err);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, true);
+    if (last) ctrl_after_mc_sweep(P, c);
 }
 
 // one dist! evaluation per row (stage-level model parity); dense N x D input

@@ -232,9 +232,9 @@ class Context:
         _check(lib().abcdez_comm_init(self._h, int(rank), int(world), unique_id))
         self.rank, self.world = int(rank), int(world)
 
-    def comm_selftest(self, rounds: int = 16):
+    def comm_selftest(self, rounds: int = 16, mode: int = 1):
         chk = C.c_uint64(); us = C.c_double()
-        _check(lib().abcdez_comm_selftest(self._h, int(rounds), C.byref(chk), C.byref(us)))
+        _check(lib().abcdez_comm_selftest(self._h, int(rounds), int(mode), C.byref(chk), C.byref(us)))
         return chk.value, us.value
 
     def sync(self):

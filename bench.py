@@ -10,7 +10,9 @@ SMC loop down to eps_target) over that batch of synthetic input; every step uses
 seed.  `value` = sum(nsims) of the K timed runs / device time, with nothing but scalars leaving
 the GPU; `e2e` = the same run through the reference-facing call (abcdez_smc_run with HOST result
 buffers: P, Wns, C come back over PCIe inside the timed region); ms_per_step is the
-time-to-target-eps.  With --gpus N every rank runs the same per-GPU workload (weak scaling).
+time-to-target-eps.  With --gpus N (torchrun, one process per GPU) the run is ONE sharded population of
+N x 10^6 particles (weak scaling: 10^6 particles per GPU): per-iteration exchanges inside the kernels over
+NVLink peer memory, global stratified resampling through peer loads.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles P]
 """
@@ -141,10 +143,12 @@ def run_reference(args, rank: int):
     print(json.dumps(line))
 
 
-def config_dict(args, particles):
+def config_dict(args, particles, world=1):
     return {"workload": "BASELINE.json configs[1]: 10-d correlated Gaussian model (gauss_corr10), abcdesmc!, "
                         f"{particles} particles per GPU, eps_target={EPS_TARGET}, defaults alpha=0.95 delta_ess=0.5 Kmcmc=3",
-            "particles_per_gpu": particles, "d": D, "eps_target": EPS_TARGET, "rho": RHO, "sigma0": SIGMA0,
+            "particles_per_gpu": particles, "particles": particles * world,
+            "parallelism": "single GPU" if world == 1 else f"one population sharded over {world} GPUs (contiguous blocks, "
+                           "in-kernel NVLink exchanges, rank-local DE partners)", "d": D, "eps_target": EPS_TARGET, "rho": RHO, "sigma0": SIGMA0,
             "kernel": "IndicatorStrict0to-eps", "step": "one complete abcdesmc! run (init + SMC loop to eps_target), fresh seed per step",
             "l2": "working set ~230 MB of particle state per run exceeds the 126 MB L2; no explicit flush"}
 
@@ -176,16 +180,21 @@ def main():
     import abcdez_b200 as A
     stream = torch.cuda.current_stream().cuda_stream
     ctx = A.Context(local_rank, stream=stream)
+    if world > 1:
+        A.dist.init_sharded(ctx)               # collective: NCCL bootstrap + IPC-mapped mailboxes
     spec, data = workload_spec()
     prior = A.Factored(*[A.host.Normal(0.0, SIGMA0)] * D)
     model = A.Model("gauss_corr10", data)
-    N = args.particles
+    N = args.particles                         # per GPU
+    Nglobal = N * world
+    lo, hi = A.shard_range(Nglobal, rank, world)
+    Nloc = hi - lo
     L = A.lib()
     import ctypes as C
 
     def run(seed, host_out=None, profile=False):
         o = A.host._SmcOpts(); L.abcdez_smc_opts_default(C.byref(o))
-        o.nparticles = N; o.nsims_max = 10**15; o.seed = seed; o.verboseout = 0; o.profile = int(profile); o.sync_every = 4
+        o.nparticles = Nglobal; o.nsims_max = 10**15; o.seed = seed; o.verboseout = 0; o.profile = int(profile); o.sync_every = 4
         r = A.host._SmcResult()
         if host_out is not None:
             r.P, r.Wns, r.C = host_out
@@ -199,7 +208,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    base = PHILOX_KEY + 7919 * rank
+    base = PHILOX_KEY                          # one population: the same seed on every rank
     for s in range(args.warmup):
         run(base + 100000 + s, profile=True)
     # ---- timed region: K complete runs, device-resident results -------------------------------
@@ -217,8 +226,8 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     # ---- e2e: the reference-facing call with HOST result buffers ------------------------------
-    Ph = torch.empty((N, D), dtype=torch.float64).pin_memory(); Wh = torch.empty(N, dtype=torch.float64).pin_memory()
-    Ch = torch.empty(N, dtype=torch.float64).pin_memory()
+    Ph = torch.empty((Nloc, D), dtype=torch.float64).pin_memory(); Wh = torch.empty(Nloc, dtype=torch.float64).pin_memory()
+    Ch = torch.empty(Nloc, dtype=torch.float64).pin_memory()
     host_out = (Ph.data_ptr(), Wh.data_ptr(), Ch.data_ptr())
     run(base + 200000, host_out=host_out)
     barrier()
@@ -230,23 +239,25 @@ def main():
         assert math.isfinite(float(Wh.sum()))           # the host reads the result
     barrier()
     e2e_s = time.perf_counter() - t0
-    d2h = N * (D + 2) * 8
+    d2h = Nglobal * (D + 2) * 8                 # all ranks together
     h2d = (len(data) + 4 * D) * 8 + 4 * D               # bound data + prior parameters; the state is born on the device
 
     # ---- max over ranks / sums ---------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    c = torch.tensor([nsims, e2e_nsims, launches, iters, sweeps], dtype=torch.float64, device="cuda")
-    swt = torch.tensor([sweep_ms], dtype=torch.float64, device="cuda")
+    # nsims / iters / sweeps are properties of the one sharded population (identical on every rank); launches add up
+    c = torch.tensor([launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    ms_all, e2e_ms_all = t.tolist(); nsims_all, e2e_nsims_all, launches_all, iters_all, sweeps_all = c.tolist()
+    ms_all, e2e_ms_all = t.tolist(); launches_all = c.tolist()[0]
+    nsims_all, e2e_nsims_all, iters_all, sweeps_all = nsims, e2e_nsims, iters * world, sweeps * world
     if rank == 0:
         peak, peak_src = peaks()
         value = nsims_all / (ms_all * 1e-3)
-        ach = BYTES_PER_EVAL * nsims / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None      # rank 0's kernel
+        # rank 0's sweep kernel: it simulates its own block, 1/world of the population's evaluations
+        ach = BYTES_PER_EVAL * (nsims / world) / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config_dict(args, N),
+                "dtype": "f64", "data": "synthetic", "config": config_dict(args, N, world),
                 "time_to_target_eps_ms": ms_all / args.steps,
                 "iters_per_run": iters_all / (args.steps * world), "sweeps_per_run": sweeps_all / (args.steps * world),
                 "logZ_mean": float(np.mean(logZ)), "logZ_sd": float(np.std(logZ)),

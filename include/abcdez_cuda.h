@@ -93,9 +93,10 @@ int abcdez_sync(abcdez_ctx* ctx);          /* cudaStreamSynchronize on the conte
 int abcdez_nccl_unique_id(void* id128);
 int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void* id128);
 int abcdez_shard_range(int64_t N, int rank, int world, int64_t* lo, int64_t* hi);
-/* `rounds` in-kernel exchanges (one histogram-sized and one scalar record each); checksum is a known
- * function of (world, rounds) -- see tests/test_multi_gpu.py -- and us_per_round their latency */
-int abcdez_comm_selftest(abcdez_ctx* ctx, int rounds, uint64_t* checksum, double* us_per_round);
+/* `rounds` in-kernel exchanges (one histogram-sized and one scalar record each) through the fenced ring
+ * (mode 0: barriers, resampling) or the low-latency ring (mode 1: the per-iteration records); checksum is
+ * a known function of (world, rounds) -- tests/multi_gpu_worker.py -- and us_per_round their latency */
+int abcdez_comm_selftest(abcdez_ctx* ctx, int rounds, int mode, uint64_t* checksum, double* us_per_round);
 
 /* ---- prior: Factored(dists...) src/abcdez_priors.jl:18-61 ------------------------------ */
 int abcdez_prior_create(abcdez_ctx* ctx, int d, const int32_t* family, const double* params /* d x 4 */,

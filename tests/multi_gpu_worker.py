@@ -17,11 +17,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def selftest_checksum(world: int, rounds: int, nthreads: int = 256, bins: int = 2048) -> int:
+def selftest_checksum(world: int, rounds: int, bins: int = 2048) -> int:
+    """What xchg_selftest_kernel (comm.cu) accumulates, for either ring."""
     tot = 0
     for it in range(rounds):
         for r in range(world):
-            tot += nthreads * ((r + 1) * 1000 + it)
+            tot += (r + 1) * 1000 + it + (r + 1)        # header word 0 + the high half of header word 1
             tot += sum(r * 7 + b + it for b in range(bins))
             tot += 3 * r + it
     return tot & 0xFFFFFFFFFFFFFFFF
@@ -85,10 +86,11 @@ def gpu_main():
     ctx = A.Context(local)
     A.dist.init_sharded(ctx)
     assert (ctx.rank, ctx.world) == (rank, world)
-    chk, us = ctx.comm_selftest(64)
-    assert chk == selftest_checksum(world, 64), (chk, selftest_checksum(world, 64))
-    if rank == 0:
-        print(f"in-kernel exchange ok: {us:.2f} us per round (8 KB histogram all-gather + scalar all-gather), world {world}")
+    for mode, label in ((0, "fenced ring"), (1, "low-latency ring")):
+        chk, us = ctx.comm_selftest(64, mode)
+        assert chk == selftest_checksum(world, 64), (mode, chk, selftest_checksum(world, 64))
+        if rank == 0:
+            print(f"in-kernel exchange ok, {label}: {us:.2f} us per round (2048-bin histogram + scalar record), world {world}")
     O.build()
     fams = {"normal": A.host.Normal, "uniform": A.host.Uniform}
     for name, spec, data, eps_t, N, seed, kw in CASES:

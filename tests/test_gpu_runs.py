@@ -237,3 +237,91 @@ def test_blobs_travel_with_particles(A, gpu_ctx):
     y = r.blobs.view(np.float64)[:, 0]
     np.testing.assert_allclose(np.abs(y - 3.0), r.C, rtol=1e-12, atol=1e-12)
     assert np.all(r.C[r.Wns > 0] < 0.3)
+
+
+# ---------------------------------------------------------------------------------------------
+# config 3: g-and-k (CTA-cooperative simulator, FP32; csrc/gk.cu)
+# ---------------------------------------------------------------------------------------------
+GK_TRUE = (3.0, 1.0, 2.0, 0.5)
+GK_PRIOR = [("uniform", 0.0, 10.0)] * 4
+
+
+def _gk_octiles(theta, n=200000, seed=1):
+    A_, B_, g, k = theta
+    z = np.random.default_rng(seed).standard_normal(n)
+    x = A_ + B_ * (1 + 0.8 * np.tanh(0.5 * g * z)) * (1 + z * z) ** k * z
+    xs = np.sort(x)
+    return [float(xs[(n * j + 7) // 8 - 1]) for j in range(1, 8)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [10000, 16384, 1001, 8])
+def test_gk_simulate_parity(A, oracle, gpu_ctx, n):
+    """One dist! evaluation per row: same Philox blocks, FP32 arithmetic with the device libm vs glibc, and a
+    radix multi-select vs qsort for the octiles -> 1e-4 relative on the distance."""
+    data = [float(n)] + _gk_octiles(GK_TRUE)
+    N = 300
+    th = oracle.prior_sample(GK_PRIOR, N, seed=3)
+    th[:, 3] = th[:, 3] * 0.2                       # keep (1+z^2)^k finite in FP32
+    want, _ = oracle.simulate("gk", data, th, seed=11, epoch=2)
+    got, _ = A.Model("gk", data).simulate(th, seed=11, epoch=2)
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    f = np.isfinite(want)
+    np.testing.assert_allclose(got[f], want[f], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_gk_init_and_sweep_follow_oracle(A, oracle, gpu_ctx):
+    """abcde_init! and one injected-randomness abcdesmc_swarm! sweep of the cooperative kernels: distances
+    within the FP32 tolerance, accept decisions identical wherever the oracle's margin exceeds it."""
+    data = [2000.0] + _gk_octiles(GK_TRUE)
+    spec = [("uniform", 0.0, 10.0)] * 3 + [("uniform", 0.0, 1.0)]
+    N = 1500
+    wth, wlp, wdl, _, wred = oracle.init(spec, "gk", data, N, seed=21)
+    fam = {"uniform": A.host.Uniform}
+    prior = A.Factored(*[fam[s[0]](*s[1:]) for s in spec])
+    pop = A.Population(prior, A.Model("gk", data), N)
+    red = pop.init(seed=21)
+    g = pop.download()
+    assert red == wred
+    np.testing.assert_array_equal(g["theta"], wth)
+    np.testing.assert_allclose(g["delta"], wdl, rtol=1e-4, atol=1e-5)
+    # one sweep from the ORACLE's state so that both sides start bit-identical
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, N, N).astype(np.int32); b = rng.integers(0, N, N).astype(np.int32)
+    idx = np.arange(N)
+    a = np.where(a == idx, (a + 1) % N, a).astype(np.int32)
+    b = np.where((b == idx) | (b == a), (b + 2) % N, b).astype(np.int32)
+    b = np.where((b == idx) | (b == a), (b + 1) % N, b).astype(np.int32)
+    z = rng.standard_normal(N); u = rng.random(N)
+    eps = float(np.quantile(wdl, 0.6))
+    alive = np.ones(N, dtype=np.uint8)
+    w = oracle.smc_sweep(spec, "gk", data, wth, wlp, wdl, alive, eps, "indicator_strict", gamma0=2.38 / math.sqrt(8), gsig=1e-5,
+                         seed=4, epoch=1, a=a, b=b, z=z, u=u)
+    pop.upload(theta=wth, logpi=wlp, delta=wdl)
+    pop.set(eps=eps, kernel="indicator_strict", gamma0=2.38 / math.sqrt(8), seed=4, epoch=1)
+    flags = pop.smc_sweep(a=a, b=b, z=z, u=u, want_flags=True)["flags"]
+    got = pop.download()
+    wflags = w["flags"]
+    assert np.array_equal(flags & 1, wflags & 1)                       # the same proposals were simulated
+    disagree = np.flatnonzero((flags & 2) != (wflags & 2))
+    assert disagree.size <= max(2, N // 200), disagree.size            # only proposals within FP32 noise of eps may flip
+    same = (flags & 2) == (wflags & 2)
+    np.testing.assert_allclose(got["delta"][same], w["delta"][same], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(got["theta"][same], w["theta"][same])
+    pop.close()
+
+
+@pytest.mark.gpu
+def test_gk_posterior_recovers_parameters(A, gpu_ctx):
+    """Statistical tier: abcdesmc! on g-and-k octiles concentrates around the generating parameters."""
+    data = [10000.0] + _gk_octiles(GK_TRUE)
+    prior = A.Factored(*[A.host.Uniform(0.0, 10.0)] * 3, A.host.Uniform(0.0, 2.0))
+    r = A.abcdesmc(prior, A.Model("gk", data), 0.15, None, nparticles=2000, rng=8, verbose=False, nsims_max=400000)
+    assert r.eps <= 0.6
+    w = r.Wns / r.Wns.sum()
+    mean = (r.P * w[:, None]).sum(0)
+    assert abs(mean[0] - GK_TRUE[0]) < 0.25 and abs(mean[1] - GK_TRUE[1]) < 0.5
+    assert abs(mean[3] - GK_TRUE[3]) < 0.3
+    with pytest.raises(A.ABCdeZError):
+        A.abcdemc(prior, A.Model("gk", data), 1.0, None, nparticles=100, generations=2, verbose=False)
