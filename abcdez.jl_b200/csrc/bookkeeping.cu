@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(BK_THREADS) reweight_a_kernel(PopDev P)
     for (int k = 0; k < 4; ++k) {
         bool ok = ((al >> (8 * k)) & 0xff) && (i0 + k < P.N);
         double ws = 0.0;
-        if (ok) ws = pexp(abck_logpdf(kind, eps_new, v[k]) - abck_logpdf(kind, eps_old, v[k]));   // :75
+        if (ok) ws = abck_ws(kind, eps_new, eps_old, v[k]);                                       // :75
         w[k] = ok ? w[k] * ws : 0.0;                                                              // :308
         acc += w[k];
     }

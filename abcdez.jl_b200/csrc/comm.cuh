@@ -45,12 +45,13 @@ __device__ __forceinline__ unsigned long long* xchg_entry(char* mbox, unsigned s
 }
 
 // poll my own mailbox until rank `src` has published `seq` in `slot`; false on timeout
-__device__ __forceinline__ bool xchg_wait_one(const XchgDev& X, unsigned slot, int src, unsigned long long seq)
+static __device__ __noinline__ bool xchg_wait_one(const XchgDev& X, unsigned slot, int src, unsigned long long seq)
 {
     const unsigned long long* flag = xchg_entry(X.mbox[X.rank], slot, src);
     if (ld_acquire_sys(flag) == seq) return true;
     const unsigned long long t0 = xchg_now_ns();
     for (;;) {
+#pragma unroll 1
         for (int spin = 0; spin < 64; ++spin)
             if (ld_acquire_sys(flag) == seq) return true;
         if (xchg_now_ns() - t0 > XCHG_TIMEOUT_NS) return false;
@@ -150,12 +151,19 @@ __device__ __forceinline__ unsigned long long ll_pack(unsigned data, unsigned fl
     return ((unsigned long long)flag << 32) | (unsigned long long)data;
 }
 // spin until the word carries `flag`; returns its data half (ok = false on timeout)
+static __device__ __noinline__ unsigned ll_poll_slow(const unsigned long long* p, unsigned flag, bool& ok);
 __device__ __forceinline__ unsigned ll_poll(const unsigned long long* p, unsigned flag, bool& ok)
 {
     unsigned long long v = ld_relaxed_sys(p);
     if ((unsigned)(v >> 32) == flag) return (unsigned)v;
+    return ll_poll_slow(p, flag, ok);
+}
+static __device__ __noinline__ unsigned ll_poll_slow(const unsigned long long* p, unsigned flag, bool& ok)
+{
+    unsigned long long v;
     const unsigned long long t0 = xchg_now_ns();
     for (;;) {
+#pragma unroll 1
         for (int spin = 0; spin < 32; ++spin) {
             v = ld_relaxed_sys(p);
             if ((unsigned)(v >> 32) == flag) return (unsigned)v;
@@ -171,6 +179,7 @@ __device__ __forceinline__ void ll_poll_batch(const unsigned long long* p, int s
 {
     unsigned long long v[NB];
     unsigned long long t0 = 0ull;
+#pragma unroll 1
     for (int spin = 0;; ++spin) {
         bool all = true;
 #pragma unroll

@@ -40,7 +40,7 @@ __device__ inline void select_setup(Ctrl* c)
 }
 
 // end of an SMC iteration, src/abcdez_smc.jl:357-376 (called by the last CTA of the last sweep)
-__device__ inline void ctrl_end_iter(const PopDev& P, Ctrl* c)
+static __device__ __noinline__ void ctrl_end_iter(const PopDev& P, Ctrl* c)
 {
     c->facc = (double)c->naccs_iter / ((double)c->n_alive_g * (double)c->Ki);   // :357
     c->eps_k = c->eps;                                                         // :360
@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t load4_u8(const uint8_t* __restrict__ p, size
 // extrema(delta) of the generation that the previous iteration left behind: the sweeps no longer touch
 // every particle, so ranges_eps (src/abcdez_smc.jl:363) is taken from the first select pass of the next
 // iteration (same delta array) and written into the history record that iteration pushed
-__device__ inline void patch_extrema(const PopDev& P, Ctrl* c)
+static __device__ __noinline__ void patch_extrema(const PopDev& P, Ctrl* c)
 {
     c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
     c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
@@ -104,7 +104,7 @@ __device__ inline void patch_extrema(const PopDev& P, Ctrl* c)
 // reweight pass B + the decisions of :318-324.  Builds the sequential-sum tables for the
 // closed-form resampling when it will be needed.
 // n_alive: this rank's alive count; n_alive_g: the whole population's (equal on one GPU)
-__device__ inline void ctrl_after_reweight(const PopDev& P, Ctrl* c, double sumsq, unsigned n_alive, unsigned n_alive_g)
+static __device__ __noinline__ void ctrl_after_reweight(const PopDev& P, Ctrl* c, double sumsq, unsigned n_alive, unsigned n_alive_g)
 {
     c->n_alive = n_alive; c->n_alive_g = n_alive_g;
     c->ess = 1.0 / sumsq;                                                   // :8,:323

@@ -49,7 +49,7 @@ __device__ __forceinline__ unsigned long long pass_himask_after(int p) { return 
 
 // pick the bin holding rank `rank` in a SEL_BINS histogram (global: read through L2; else shared); every
 // thread of the CTA participates and gets the same answer.  bin == 0xffffffff: rank beyond the total.
-__device__ void pick_bin(const unsigned* h, bool global, int nbins, unsigned long long rank, HeadSmem* s,
+__device__ __noinline__ void pick_bin(const unsigned* h, bool global, int nbins, unsigned long long rank, HeadSmem* s,
                          unsigned& bin, unsigned long long& before)
 {
     const int per = SEL_BINS / HEAD_THREADS;
@@ -113,7 +113,7 @@ __device__ __forceinline__ double block_sum_all(double v, HeadSmem* s)
 
 // resolve v[j] (rank `rank` among the M listed keys, all of which match prefix/himask), the tie test and
 // v[j+1] with the digits from pass p0 on, entirely inside the CTA.  L: shared or global (L2) list.
-__device__ void tail_select(const unsigned long long* L, unsigned M, int p0, unsigned long long prefix,
+__device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M, int p0, unsigned long long prefix,
                             unsigned long long himask, unsigned long long rank, unsigned long long min_above,
                             HeadSmem* s, unsigned long long& akey, unsigned long long& bkey)
 {
@@ -156,7 +156,7 @@ __device__ void tail_select(const unsigned long long* L, unsigned M, int p0, uns
 // grid barriers.  Integer sums and rank-ordered FP64 sums: bit-identical on every rank.
 // ---------------------------------------------------------------------------------------
 // H[0..nbins) += every other rank's histogram; optionally global extrema(delta) and the sticky error
-__device__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins, bool first, HeadSmem* s)
+__device__ __noinline__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins, bool first, HeadSmem* s)
 {
     const unsigned tid = threadIdx.x;
     if (tid == 0 && first) {
@@ -180,7 +180,7 @@ __device__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins,
 // candidate-list bookkeeping of generation g: global count / extrema / min-above into c->acc.g_*; when the
 // global list fits the per-CTA tail (and is not all-equal) this rank's candidates are posted into every
 // rank's mailbox (XCHG_GCAND_OFF), where every CTA of every rank collects the same multiset for the tail
-__device__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
+__device__ __noinline__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
 {
     const unsigned tid = threadIdx.x;
     if (tid == 0) {
@@ -205,7 +205,7 @@ __device__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
 }
 
 // all-gather of the nw-word record the caller put into s->xh (thread 0): rank r's words at s->xall[nw*r ...]
-__device__ void head_xchg_rec(const PopDev& P, Ctrl* c, int nw, HeadSmem* s)
+__device__ __noinline__ void head_xchg_rec(const PopDev& P, Ctrl* c, int nw, HeadSmem* s)
 {
     __syncthreads();
     xchg_ll_block(P.x, c, s->xh, nw, nullptr, 0, s->xall, &s->xflag);
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         for (int k = 0; k < 4; ++k) {
             bool ok = ((al >> (8 * k)) & 0xff) && (i0 + k < N);
             double ws = 0.0;
-            if (ok) ws = pexp(abck_logpdf(kind, eps, v[k]) - abck_logpdf(kind, eps_old, v[k]));   // :75
+            if (ok) ws = abck_ws(kind, eps, eps_old, v[k]);                                              // :75
             w[k] = ok ? w[k] * ws : 0.0;                                                          // :308
             acc += w[k];
         }

@@ -17,7 +17,7 @@ constexpr int BK_THREADS = 256;
 #endif
 constexpr int SWEEP_THREADS = ABCDEZ_SWEEP_THREADS;    // thread-per-particle sweeps
 #ifndef ABCDEZ_SWEEP_MIN_BLOCKS
-#define ABCDEZ_SWEEP_MIN_BLOCKS 3
+#define ABCDEZ_SWEEP_MIN_BLOCKS 4      // 64 registers: 32 warps per SM beat 80 registers / 24 warps despite the spills (profiles/README.md)
 #endif
 constexpr int SWEEP_MIN_BLOCKS = ABCDEZ_SWEEP_MIN_BLOCKS;   // register cap of the fused sweep kernels
 constexpr int SEL_BINS = 2048;        // 11-bit radix-select digits

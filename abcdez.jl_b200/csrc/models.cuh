@@ -58,6 +58,42 @@ struct GaussCorr10 {
         }
         return sqrt(acc);
     }
+    // all five noise pairs in lockstep (box_muller_batch) together with one extra pair of the caller (the
+    // gamma jitter of the DE move): ua/ub[5] in, z1/z2[5] out
+    static constexpr int NOISE_PAIRS = 5;
+    __device__ static __forceinline__ void noise_uniforms(SimRng& r, double* ua, double* ub)
+    {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r.u2(ua[k], ub[k]);
+    }
+    __device__ static __forceinline__ void noise_store(const double* z1, const double* z2, double* col, int stride)
+    {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { col[(2 * k) * stride] = z1[k]; col[(2 * k + 1) * stride] = z2[k]; }
+    }
+    // the same two halves through a strided scratch column (shared memory): the AR(1) noise e_k is stored, the
+    // score reads it back one value at a time -- same operations in the same order as run()
+    __device__ static __forceinline__ void draw_to(SimRng& r, double* col, int stride)
+    {
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) {
+            double za, zb;
+            r.n2(za, zb);
+            col[k * stride] = za; col[(k + 1) * stride] = zb;
+        }
+    }
+    __device__ static __forceinline__ double score_from(const double* th, const double* data, const double* col, int stride, double*)
+    {
+        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            double z = col[k * stride];
+            e = (k == 0) ? z : rho * e + sr * z;
+            double dy = th[k] + e - data[k];
+            acc += dy * dy;
+        }
+        return sqrt(acc);
+    }
     // noise pairs are consumed as they are generated (same arithmetic as draw + score, 18 fewer live registers)
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
@@ -195,7 +231,7 @@ struct BirthDeath {
             while (n > 0.0 && events < maxev) {
                 double rate = lam_mu * n, u1, u2;
                 r.u2(u1, u2);
-                double tn = t + (-plog(1.0 - u1)) / rate;
+                double tn = t + (-plog_unit(1.0 - u1)) / rate;    // 1 - u1 in [2^-53, 1]
                 if (tn > tobs) break;
                 t = tn;
                 n += (u2 * lam_mu < th[0]) ? 1.0 : -1.0;
