@@ -920,18 +920,16 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
             launches += launch_compact(st, pop->dev);
         }
         launches += launch_resample(st, pop->dev, pop->DS, pop->NB, nullptr, (uint32_t)host_iters, mode, 0);   // :324-326
+        // profile: one CUDA-event pair around the iteration's sweep launches (skipped sweeps return at once)
+        if (o->profile) {
+            while (evs.size() < nev + 2) { cudaEvent_t e; RUN_CU(cudaEventCreate(&e)); evs.push_back(e); }
+            RUN_CU(cudaEventRecord(evs[nev], st));
+        }
         for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
-            if (o->profile) {
-                while (evs.size() < nev + 2) { cudaEvent_t e; RUN_CU(cudaEventCreate(&e)); evs.push_back(e); }
-                RUN_CU(cudaEventRecord(evs[nev], st));
-                pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
-                RUN_CU(cudaEventRecord(evs[nev + 1], st));
-                nev += 2;
-            } else {
-                pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
-            }
+            pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
             launches++;
         }
+        if (o->profile) { RUN_CU(cudaEventRecord(evs[nev + 1], st)); nev += 2; }
         if (host_iters % sync_every == 0) {
             RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
             RUN_CU(cudaStreamSynchronize(st));
@@ -1016,10 +1014,24 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
     CHECK_ARG(1 <= o->generations, "generations must be at least 1");        // :110
     if (!model->ops->mc_sweep) return fail(ABCDEZ_ERR_UNSUPPORTED, std::string("abcdemc!: model '") + model->ops->name + "' has no abcdemc! sweep in this build");
     CU(cudaSetDevice(ctx->device));
-    const int64_t N = o->nparticles;
+    // sharded run: nparticles is the whole population; base particle and partners are drawn inside the rank's
+    // block, extrema(delta) (:146) and the simulation count are global (in-kernel exchange after every sweep)
+    const bool shard = ctx->comm != nullptr && ctx->world > 1;
+    const int64_t Ng = o->nparticles;
+    int64_t lo = 0, hi = Ng;
+    if (shard) {
+        abcdez_shard_range(Ng, ctx->rank, ctx->world, &lo, &hi);
+        CHECK_ARG(Ng >= 5 * (int64_t)ctx->world, "sharded abcdemc!: need at least 5 particles per rank");
+        CHECK_ARG(Ng < (int64_t)0x7fffffff, "sharded abcdemc!: nparticles must be below 2^31");
+    }
+    const int64_t N = hi - lo;
     abcdez_pop* pop = nullptr;
-    int rc = pop_create_impl(ctx, prior, model, N, 0, 1, &pop);
+    int rc = pop_create_impl(ctx, prior, model, N, lo, 1, &pop, shard ? Ng : 0);
     if (rc) return rc;
+    if (shard) {
+        rc = comm_begin_run(ctx->comm, ctx->stream, pop->dev, &pop->dev.x, &pop->dev.peers);
+        if (rc) { abcdez_pop_destroy(pop); return fail(rc, std::string("sharded abcdemc!: ") + comm_error(ctx->comm)); }
+    }
     cudaStream_t st = ctx->stream;
     Ctrl* c = pop->h_ctrl;
     c->seed = o->seed; c->eps_target = eps_target;

@@ -186,8 +186,10 @@ gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDe
         }
     }
     if (threadIdx.x != 0) err = 0;
-    if (sweep_finish<true>(c, &s_red, redraws, 0u, kmn, kmx, err)) {
-        sweep_collect(c, true);
+    const bool last = sweep_finish<true>(c, &s_red, redraws, 0u, kmn, kmx, err);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, true);
+    if (last) {
+        if (P.x.world == 1) sweep_collect(c, true);
         c->redraws += (long long)c->last_nsims;
     }
 }

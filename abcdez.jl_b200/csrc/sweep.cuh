@@ -236,8 +236,10 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
         kdl = f64_key(dl);
     }
     // counters: reuse the sweep accumulators (nsims slot carries the redraw count)
-    if (sweep_finish<true>(c, &s_red, redraws, 0u, i < P.N ? kdl : ~0ull, i < P.N ? kdl : 0ull, err)) {
-        sweep_collect(c, true);
+    const bool last = sweep_finish<true>(c, &s_red, redraws, 0u, i < P.N ? kdl : ~0ull, i < P.N ? kdl : 0ull, err);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, true);   // global extrema, redraws, errors
+    if (last) {
+        if (P.x.world == 1) sweep_collect(c, true);
         c->redraws += (long long)c->last_nsims;
     }
 }

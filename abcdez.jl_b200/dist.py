@@ -53,8 +53,9 @@ def shard_bounds(N: int, world: int):
     return [host.shard_range(N, r, world) for r in range(world)]
 
 
-def gather_result(res: host.SMCResult, root: Optional[int] = None) -> Optional[host.SMCResult]:
-    """Assemble the whole population's (P, Wns, C, blobs) from the per-rank blocks (global particle order).
+def gather_result(res, root: Optional[int] = None):
+    """Assemble the whole population's (P, Wns, C, blobs) of an SMCResult / (P, C, blobs) of an MCResult from the
+    per-rank blocks (global particle order).
     root=None: every rank gets it (all_gather); else only `root` (others return None)."""
     import torch
     dist = _dist()
@@ -79,7 +80,10 @@ def gather_result(res: host.SMCResult, root: Optional[int] = None) -> Optional[h
         return full.reshape((N,) + a.shape[1:])
 
     blobs = gather(res.blobs) if res.blobs.ndim == 2 and res.blobs.shape[1] > 0 else np.empty((N, 0), dtype=np.uint8)
-    full = dataclasses.replace(res, P=gather(res.P), Wns=gather(res.Wns), C=gather(res.C), blobs=blobs)
+    if isinstance(res, host.MCResult):
+        full = dataclasses.replace(res, P=gather(res.P), C=gather(res.C), blobs=blobs)
+    else:
+        full = dataclasses.replace(res, P=gather(res.P), Wns=gather(res.Wns), C=gather(res.C), blobs=blobs)
     if root is not None and rank != root:
         return None
     return full

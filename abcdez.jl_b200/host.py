@@ -578,6 +578,10 @@ def abcdemc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 50, 
     fprior, scalar = _as_prior(prior)
     N, d, B = int(nparticles), len(fprior), dist.blob_bytes
     o = _McOpts(N, int(generations), _seed_from(rng))
+    Nglobal = N
+    if ctx.world > 1:                         # sharded: this rank returns the rows of its own block
+        lo, hi = shard_range(Nglobal, ctx.rank, ctx.world)
+        N = hi - lo
     Np = max(N, 1)
     P = np.empty((Np, d)); Cc = np.empty(Np); bl = np.zeros((Np, max(B, 1)), dtype=np.uint8)
     r = _McResult()
@@ -586,7 +590,8 @@ def abcdemc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 50, 
                                C.byref(r)))
     if verbose:
         print(f"End: converged = {bool(r.reached_eps)} nsim = {r.nsims} range_ϵ = ({r.dmin}, {r.dmax})")
-    stats = dict(total_ms=r.total_ms, n_launches=r.n_launches, seed=o.seed)
+    stats = dict(total_ms=r.total_ms, n_launches=r.n_launches, seed=o.seed, rank=ctx.rank, world=ctx.world,
+                 nparticles=Nglobal)
     return MCResult(P[:, 0] if scalar else P, Cc, bool(r.reached_eps), _blob_view(bl, B), nsims=r.nsims, stats=stats)
 
 

@@ -53,6 +53,16 @@ def peaks():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def sweep_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the sweep kernel, from the committed ncu --set full
+    capture of this same command (profiles/sweep_traffic.json); None when no capture is on record."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -266,9 +276,10 @@ def main():
                 "e2e": {"value": e2e_nsims_all / (e2e_ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "steps": ke, "ms_per_step": e2e_ms_all / ke},
                 "roofline": {"bound": "hbm", "kernel": "smc_sweep_kernel<GaussCorr10>", "achieved": ach, "peak": peak,
-                             "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+                             "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": sweep_traffic(),
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_eval": BYTES_PER_EVAL,
+                             "algorithmic_bytes_per_launch": BYTES_PER_EVAL * (nsims / world) / max(sweeps, 1),
                              "avg_launch_ms": sweep_ms / max(sweeps, 1),
                              "sweep_share_of_step": sweep_ms / ms if ms > 0 else None}}
         if world == 1 and not args.no_cpu_baseline:

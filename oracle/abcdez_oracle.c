@@ -1245,20 +1245,27 @@ static int cmp_di(const void* a, const void* b)
     return (x->i > y->i) - (x->i < y->i);
 }
 
-int orc_mc_sweep(int d, const int32_t* family, const double* params, int model, const double* data,
+/* islands > 1 (sharded runs): base particle and partners are drawn inside the particle's own contiguous
+ * block (rank-local subpopulations); eps_pop stays the caller's global value. */
+int orc_mc_sweep_islands(int d, const int32_t* family, const double* params, int model, const double* data,
                  int64_t N, const double* theta, const double* logpi, const double* delta,
                  const uint8_t* blobs, double eps_pop, double eps_target, double gamma0, double gsig,
                  uint64_t seed, uint32_t epoch, int64_t id0,
                  const int32_t* inj_s, const int32_t* inj_a, const int32_t* inj_b,
-                 const double* inj_z, const double* inj_u,
+                 const double* inj_z, const double* inj_u, int islands,
                  double* ntheta, double* nlogpi, double* ndelta, uint8_t* nblobs, uint8_t* flags,
                  int64_t* nsims_out)
 {
     prior_t pr; mk_prior(&pr, d, family, params);
     int B = MODELS[model].blob;
+    if (islands < 1) islands = 1;
+    if (islands > ORC_MAX_ISLANDS) return 1;
+    int64_t isl_lo[ORC_MAX_ISLANDS + 1];
+    for (int r = 0; r <= islands; ++r) isl_lo[r] = (int64_t)(((__int128)N * r) / islands);
     di_t* srt = (di_t*)malloc(sizeof(di_t) * (size_t)N);
     for (int64_t i = 0; i < N; ++i) { srt[i].d = delta[i]; srt[i].i = i; }
-    qsort(srt, (size_t)N, sizeof(di_t), cmp_di);
+    for (int r = 0; r < islands; ++r)           /* each block sorted on its own, in place */
+        qsort(srt + isl_lo[r], (size_t)(isl_lo[r + 1] - isl_lo[r]), sizeof(di_t), cmp_di);
     int64_t nsims = 0; int fail = 0;
     memcpy(ntheta, theta, sizeof(double) * (size_t)(N * d));
     memcpy(nlogpi, logpi, sizeof(double) * (size_t)N);
@@ -1269,18 +1276,21 @@ int orc_mc_sweep(int d, const int32_t* family, const double* params, int model, 
         if (flags) flags[i] = 0;
         uint32_t pid = (uint32_t)(id0 + i);
         stream_t cs = mk_stream(seed, pid, epoch, TAG_MC);
+        int isl = 0;
+        while (isl + 1 < islands && i >= isl_lo[isl + 1]) isl++;
+        const int64_t L0 = isl_lo[isl], NL = isl_lo[isl + 1] - isl_lo[isl];   /* the particle's block */
         int64_t s = i;                                                     /* :18 */
         double eps = (delta[i] <= eps_target) ? eps_target : eps_pop;      /* :19 */
         if (delta[i] > eps) {                                              /* :20-24 */
             if (inj_s) s = inj_s[i];
             else {
                 /* cnt = #{delta <= delta[i]} by upper-bound search on the sorted keys */
-                int64_t lo = 0, hi = N;
-                while (lo < hi) { int64_t m = (lo + hi) / 2; if (srt[m].d <= delta[i]) lo = m + 1; else hi = m; }
+                int64_t lo = 0, hi = NL;
+                while (lo < hi) { int64_t m = (lo + hi) / 2; if (srt[L0 + m].d <= delta[i]) lo = m + 1; else hi = m; }
                 double u1, u2; stream_u2(&cs, 0, &u1, &u2);
                 int64_t k = (int64_t)floor(u1 * (double)lo);
                 if (k >= lo) k = lo - 1;
-                s = srt[k].i;
+                s = srt[L0 + k].i;
             }
         }
         int64_t a, b;
@@ -1292,13 +1302,15 @@ int orc_mc_sweep(int d, const int32_t* family, const double* params, int model, 
             while (a == s) {                                               /* :25-28, rand(1:N) -> floor(u*N) */
                 if (att >= ORC_PARTNER_MAX_ATTEMPTS) { fail = 1; break; }
                 stream_u2(&ps, att++, &u1, &u2);
-                a = (int64_t)floor(u1 * (double)N); if (a >= N) a = N - 1;
+                a = (int64_t)floor(u1 * (double)NL); if (a >= NL) a = NL - 1;
+                a += L0;
             }
             att = 0; b = a;
             while (b == a || b == s) {                                     /* :29-32 */
                 if (att >= ORC_PARTNER_MAX_ATTEMPTS) { fail = 1; break; }
                 stream_u2(&ps, att++, &u1, &u2);
-                b = (int64_t)floor(u2 * (double)N); if (b >= N) b = N - 1;
+                b = (int64_t)floor(u2 * (double)NL); if (b >= NL) b = NL - 1;
+                b += L0;
             }
             if (fail) continue;
         }
@@ -1336,10 +1348,25 @@ int orc_mc_sweep(int d, const int32_t* family, const double* params, int model, 
     return fail ? 6 : 0;
 }
 
+int orc_mc_sweep(int d, const int32_t* family, const double* params, int model, const double* data,
+                 int64_t N, const double* theta, const double* logpi, const double* delta,
+                 const uint8_t* blobs, double eps_pop, double eps_target, double gamma0, double gsig,
+                 uint64_t seed, uint32_t epoch, int64_t id0,
+                 const int32_t* inj_s, const int32_t* inj_a, const int32_t* inj_b,
+                 const double* inj_z, const double* inj_u,
+                 double* ntheta, double* nlogpi, double* ndelta, uint8_t* nblobs, uint8_t* flags,
+                 int64_t* nsims_out)
+{
+    return orc_mc_sweep_islands(d, family, params, model, data, N, theta, logpi, delta, blobs, eps_pop, eps_target,
+                                gamma0, gsig, seed, epoch, id0, inj_s, inj_a, inj_b, inj_z, inj_u, 1,
+                                ntheta, nlogpi, ndelta, nblobs, flags, nsims_out);
+}
+
 typedef struct {
     int64_t nparticles;
     int32_t generations;
     uint64_t seed;
+    int32_t islands;            /* 0/1: global pools (the reference); R > 1: rank-local pools (sharded runs) */
 } orc_mc_opts;
 
 typedef struct {
@@ -1376,8 +1403,8 @@ int orc_mc_run(int d, const int32_t* family, const double* params, int model, co
         double eps_pop = fmax(eps_target, el + 0.0 * (eh - el));           /* :147, alpha = 0 (:107) */
         int64_t ns = 0;
         double t0 = now_s();
-        rc = orc_mc_sweep(d, family, params, model, data, N, th, lp, dl, bl, eps_pop, eps_target,
-                          gamma0, gsig, o->seed, (uint32_t)it, 0, NULL, NULL, NULL, NULL, NULL,
+        rc = orc_mc_sweep_islands(d, family, params, model, data, N, th, lp, dl, bl, eps_pop, eps_target,
+                          gamma0, gsig, o->seed, (uint32_t)it, 0, NULL, NULL, NULL, NULL, NULL, o->islands,
                           nth, nlp, ndl, nbl, NULL, &ns);
         res->sweep_seconds += now_s() - t0;
         nsims += ns;

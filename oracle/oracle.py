@@ -53,7 +53,7 @@ class _SmcResult(C.Structure):
 
 
 class _McOpts(C.Structure):
-    _fields_ = [("nparticles", C.c_int64), ("generations", C.c_int32), ("seed", C.c_uint64)]
+    _fields_ = [("nparticles", C.c_int64), ("generations", C.c_int32), ("seed", C.c_uint64), ("islands", C.c_int32)]
 
 
 class _McResult(C.Structure):
@@ -317,10 +317,10 @@ class McOut:
     sweep_seconds: float
 
 
-def mc_run(prior, model, data, eps_target, nparticles=50, generations=20, seed=1):
+def mc_run(prior, model, data, eps_target, nparticles=50, generations=20, seed=1, islands=1):
     d, fam, par = _prior_args(prior)
     mid = model_id(model); B = model_blob(model); N = nparticles
-    o = _McOpts(N, generations, seed); r = _McResult()
+    o = _McOpts(N, generations, seed, int(islands)); r = _McResult()
     P = np.empty((N, d)); Cc = np.empty(N); bl = np.zeros((N, max(B, 1)), dtype=np.uint8)
     rc = lib().orc_mc_run(d, _p(fam), _p(par), mid, _p(_data(data)), C.c_double(eps_target), C.byref(o),
                           C.byref(r), _p(P), _p(Cc), _p(bl))

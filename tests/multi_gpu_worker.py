@@ -115,6 +115,18 @@ def gpu_main():
             np.testing.assert_allclose(full.Wns, want.Wns, rtol=1e-9)
         if rank == 0:
             print(f"sharded {name} N={N} world={world}: iters {got.iters} nsims {got.nsims} logZ {got.logZ:.6f} == oracle(islands={world})")
+    # sharded abcdemc!: global extrema / counts, rank-local base particle and partners
+    for name, spec, data, eps_t, N, seed, gens in [("gauss1d", [("normal", 0.0, math.sqrt(10.0))], [3.0, 1.0], 0.5, 4003, 13, 12),
+                                                   ("twod", [("normal", 0.0, 5.0)] * 2, [], 1.0, 3000, 17, 8)]:
+        prior = A.Factored(*[fams[s_[0]](*s_[1:]) for s_ in spec])
+        got = A.abcdemc(prior, A.Model(name, data), eps_t, None, nparticles=N, generations=gens, rng=seed, verbose=False, ctx=ctx)
+        full = A.dist.gather_result(got)
+        want = O.mc_run(spec, name, data, eps_t, nparticles=N, generations=gens, seed=seed, islands=world)
+        assert got.nsims == want.nsims and got.reached_eps == want.reached_eps, (name, got.nsims, want.nsims)
+        np.testing.assert_allclose(full.P.reshape(N, -1), want.P, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(full.C, want.C, rtol=1e-9, atol=1e-12)
+        if rank == 0:
+            print(f"sharded abcdemc! {name} N={N} world={world}: nsims {got.nsims} reached {got.reached_eps} == oracle(islands={world})")
     # an unsupported configuration fails identically (and cleanly) on every rank
     try:
         A.abcdesmc(A.host.Normal(0, 1), A.Model("gauss1d", [3.0, 1.0]), 0.3, None, nparticles=1000, rng=1, verbose=False,
