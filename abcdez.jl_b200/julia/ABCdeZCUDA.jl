@@ -18,7 +18,7 @@ module ABCdeZCUDA
 using Distributions
 using Random
 
-export Factored, abcdesmc!, abcdemc!, DeviceModel
+export Factored, abcdesmc!, abcdemc!, DeviceModel, Context, nccl_unique_id, comm_init!, shard_range
 export Indicator0toϵ, IndicatorStrict0toϵ, Epa0toϵ, EpaStrict0toϵ
 
 const LIB = get(ENV, "ABCDEZ_LIB", joinpath(@__DIR__, "..", "libabcdez_cuda.so"))
@@ -71,14 +71,37 @@ end
 # ---- handles ---------------------------------------------------------------------------------------
 mutable struct Context
     h::Ptr{Cvoid}
+    rank::Int
+    world::Int
     function Context(device::Integer=0)
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:abcdez_init, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, r))
-        c = new(r[])
+        c = new(r[], 0, 1)
         finalizer(x -> ccall((:abcdez_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
         c
     end
 end
+# ---- sharded runs: one Julia process per GPU (include/abcdez_cuda.h "sharded runs") --------------------
+# Rank 0 calls nccl_unique_id() and ships the 128 bytes to the other ranks (Distributed.jl, MPI.jl, a file ...);
+# every rank then calls comm_init!(ctx, rank, world, id).  After that abcdesmc!/abcdemc! on `ctx` are collective:
+# `nparticles` is the whole population, each rank gets the rows of its block shard_range(nparticles, rank, world).
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:abcdez_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    id
+end
+function comm_init!(ctx::Context, rank::Integer, world::Integer, id::Vector{UInt8})
+    check(ccall((:abcdez_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, rank, world, id))
+    ctx.rank = rank; ctx.world = world
+    ctx
+end
+function shard_range(N::Integer, rank::Integer, world::Integer)     # 0-based [lo, hi)
+    lo = Ref{Int64}(0); hi = Ref{Int64}(0)
+    check(ccall((:abcdez_shard_range, LIB), Cint, (Int64, Cint, Cint, Ref{Int64}, Ref{Int64}), N, rank, world, lo, hi))
+    lo[], hi[]
+end
+local_count(ctx::Context, N::Integer) = ctx.world == 1 ? N : ((lo, hi) = shard_range(N, ctx.rank, ctx.world); hi - lo)
+
 const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
 default_context() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Context(parse(Int, get(ENV, "LOCAL_RANK", "0")))); DEFAULT_CTX[])
 
@@ -173,7 +196,7 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     o.nparticles = nparticles; o.alpha = α; o.delta_ess = δess; o.nsims_max = nsims_max; o.Kmcmc = Kmcmc
     o.Kmcmc_min = Kmcmc_min; o.kernel = kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
     o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout
-    N = nparticles
+    N = local_count(ctx, nparticles)                   # sharded: the rows of this rank's block
     P = Matrix{Float64}(undef, d, N); Wns = Vector{Float64}(undef, N); C = Vector{Float64}(undef, N)
     bl = zeros(UInt8, max(B, 1), N)
     h = [zeros(Float64, hist_cap) for _ in 1:7]; hK = zeros(Int32, hist_cap)
@@ -212,7 +235,7 @@ function abcdemc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     ph = prior_handle(ctx, prior)
     mh, d, B = model_handle(ctx, dist!)
     o = McOpts(nparticles, generations, seed_from(rng))
-    N = nparticles
+    N = local_count(ctx, nparticles)
     P = Matrix{Float64}(undef, d, N); C = Vector{Float64}(undef, N); bl = zeros(UInt8, max(B, 1), N)
     r = McResult()
     GC.@preserve P C bl begin
