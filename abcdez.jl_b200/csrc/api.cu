@@ -255,6 +255,26 @@ extern "C" int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, si
 }
 extern "C" int abcdez_model_destroy(abcdez_model* m) { delete m; return ABCDEZ_OK; }
 
+// runtime-supplied models (rtc.cu): compile the CUDA source of one model struct against the library's kernel
+// templates and register it; ctx == NULL compiles only (no GPU needed) and leaves *id = -1
+extern "C" int abcdez_model_compile(abcdez_ctx* ctx, const char* name, const char* struct_name, const char* cuda_src,
+                                    int d, int blob_bytes, int* id, char* log, size_t log_cap)
+{
+    CHECK_ARG(name && struct_name && cuda_src && id, "abcdez_model_compile: NULL argument");
+    CHECK_ARG(d >= 1 && d <= ABCDEZ_MAXD, "abcdez_model_compile: d must be in 1..16");
+    CHECK_ARG(blob_bytes >= 0 && blob_bytes <= ABCDEZ_MAXBLOB && blob_bytes % 8 == 0, "abcdez_model_compile: blob_bytes must be a multiple of 8 in 0..64");
+    if (ctx) {
+        for (int i = 0; i < model_count(); ++i)
+            if (strcmp(model_ops(i)->name, name) == 0) return fail(ABCDEZ_ERR_BAD_ARG, std::string("abcdez_model_compile: a model named '") + name + "' is already registered");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaFree(nullptr));                      // the primary context is current for the driver calls
+    }
+    std::string lg;
+    int rc = rtc_compile_model(name, struct_name, cuda_src, d, blob_bytes, ctx != nullptr, id, &lg);
+    if (log && log_cap) { size_t n = lg.size() < log_cap - 1 ? lg.size() : log_cap - 1; memcpy(log, lg.data(), n); log[n] = 0; }
+    return rc ? fail(rc, "abcdez_model_compile: " + lg) : ABCDEZ_OK;
+}
+
 extern "C" int abcdez_simulate(abcdez_ctx* ctx, const abcdez_model* m, int64_t N, const double* theta_pushed,
                                uint64_t seed, uint32_t epoch, uint32_t tag, int64_t id0, double* dist_out,
                                uint8_t* blobs_out)
@@ -267,7 +287,7 @@ extern "C" int abcdez_simulate(abcdez_ctx* ctx, const abcdez_model* m, int64_t N
     DevBuf dth, dd, db;
     CU(dth.alloc((size_t)N * d * 8)); CU(dd.alloc((size_t)N * 8)); CU(db.alloc((size_t)N * (B ? B : 8)));
     CU(cudaMemcpyAsync(dth.p, theta_pushed, (size_t)N * d * 8, cudaMemcpyHostToDevice, ctx->stream));
-    m->ops->simulate(ctx->stream, nullptr, m->data, N, dth.as<double>(), seed, epoch, tag, (uint32_t)id0,
+    m->ops->simulate(*m->ops, ctx->stream, nullptr, m->data, N, dth.as<double>(), seed, epoch, tag, (uint32_t)id0,
                      dd.as<double>(), B ? db.as<double>() : nullptr);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(dist_out, dd.p, (size_t)N * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -555,7 +575,7 @@ extern "C" int abcdez_pop_init(abcdez_pop* pop, uint64_t seed, int draw_prior, i
     CHECK_ARG(pop != nullptr, "abcdez_pop_init: pop is NULL");
     CU(cudaSetDevice(pop->ctx->device));
     TIME_BEGIN(pop);
-    pop->ops->init(pop->ctx->stream, pop->dev, pop->prior, pop->data, seed, draw_prior);
+    pop->ops->init(*pop->ops, pop->ctx->stream, pop->dev, pop->prior, pop->data, seed, draw_prior);
     CU(cudaGetLastError());
     TIME_END(pop, 1);
     int rc = pull_ctrl(pop); if (rc) return rc;
@@ -596,7 +616,7 @@ extern "C" int abcdez_pop_smc_sweep(abcdez_pop* pop, const int32_t* inj_a, const
     SweepInj inj;
     int rc = stage_inject(pop, nullptr, inj_a, inj_b, inj_z, inj_u, flags_out != nullptr, &inj); if (rc) return rc;
     TIME_BEGIN(pop);
-    pop->ops->smc_sweep(pop->ctx->stream, pop->dev, pop->prior, pop->data, inj);
+    pop->ops->smc_sweep(*pop->ops, pop->ctx->stream, pop->dev, pop->prior, pop->data, inj);
     CU(cudaGetLastError());
     TIME_END(pop, 1);
     if (flags_out) CU(cudaMemcpyAsync(flags_out, inj.flags, (size_t)pop->N, cudaMemcpyDeviceToHost, pop->ctx->stream));
@@ -636,7 +656,7 @@ extern "C" int abcdez_pop_mc_sweep(abcdez_pop* pop, double eps_pop, double eps_t
     if (!inj_s) nl += launch_mc_prepare(st, pop->dev.N, pop->dev.delta[pop->h_ctrl->cur], pop->sorted_delta, pop->order,
                                         pop->sort_tmp, pop->sort_tmp_bytes);
     McArgs mc{ eps_pop, eps_target, pop->sorted_delta, pop->order };
-    pop->ops->mc_sweep(st, pop->dev, pop->prior, pop->data, inj, mc);
+    pop->ops->mc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, inj, mc);
     CU(cudaGetLastError());
     TIME_END(pop, nl);
     if (flags_out) CU(cudaMemcpyAsync(flags_out, inj.flags, (size_t)pop->N, cudaMemcpyDeviceToHost, st));
@@ -807,7 +827,7 @@ extern "C" int abcdez_pop_bench_sweeps(abcdez_pop* pop, int sweeps, int64_t* nsi
     rc = push_ctrl(pop); if (rc) return rc;
     SweepInj inj; memset(&inj, 0, sizeof(inj));
     TIME_BEGIN(pop);
-    for (int s = 0; s < sweeps; ++s) pop->ops->smc_sweep(pop->ctx->stream, pop->dev, pop->prior, pop->data, inj);
+    for (int s = 0; s < sweeps; ++s) pop->ops->smc_sweep(*pop->ops, pop->ctx->stream, pop->dev, pop->prior, pop->data, inj);
     CU(cudaGetLastError());
     TIME_END(pop, sweeps);
     rc = pull_ctrl(pop); if (rc) return rc;
@@ -908,7 +928,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     if (rc) goto done;
     RUN_CU(cudaEventCreate(&e_init0)); RUN_CU(cudaEventCreate(&e_loop0)); RUN_CU(cudaEventCreate(&e_loop1));
     RUN_CU(cudaEventRecord(e_init0, st));
-    pop->ops->init(st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :242-252
+    pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :242-252
     launches += 1 + launch_begin_run(st, pop->dev);                          // :255-292
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
@@ -926,7 +946,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
             RUN_CU(cudaEventRecord(evs[nev], st));
         }
         for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
-            pop->ops->smc_sweep(st, pop->dev, pop->prior, pop->data, noinj);
+            pop->ops->smc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj);
             launches++;
         }
         if (o->profile) { RUN_CU(cudaEventRecord(evs[nev + 1], st)); nev += 2; }
@@ -1042,7 +1062,7 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
     rc = push_ctrl(pop); if (rc) goto done;
     rc = mc_prepare(pop); if (rc) goto done;
     RUN_CU(cudaEventCreate(&e0)); RUN_CU(cudaEventCreate(&e1));
-    pop->ops->init(st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :117-125
+    pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :117-125
     launches++;
     RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     RUN_CU(cudaStreamSynchronize(st));
@@ -1055,7 +1075,7 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
             launches += launch_mc_prepare(st, pop->dev.N, pop->dev.delta[c->cur], pop->sorted_delta, pop->order,
                                           pop->sort_tmp, pop->sort_tmp_bytes);
         McArgs mc{ eps_pop, eps_target, pop->sorted_delta, pop->order };
-        pop->ops->mc_sweep(st, pop->dev, pop->prior, pop->data, noinj, mc);   // :149
+        pop->ops->mc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj, mc);   // :149
         launches++;
         RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
         RUN_CU(cudaStreamSynchronize(st));

@@ -325,15 +325,15 @@ static unsigned gk_grid(int64_t N)
     return (unsigned)(N < g_gk_grid ? N : g_gk_grid);
 }
 
-static void gk_l_init(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
+static void gk_l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
     gk_init_kernel<<<gk_grid(P.N), GK_THREADS, gk_smem_bytes(), st>>>(P, pr, md, seed, dp);
 }
-static void gk_l_smc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
+static void gk_l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
 {
     gk_smc_sweep_kernel<<<gk_grid(P.N), GK_THREADS, gk_smem_bytes(), st>>>(P, pr, md, inj);
 }
-static void gk_l_sim(cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
+static void gk_l_sim(const ModelOps&, cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
                      uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double*)
 {
     gk_simulate_kernel<<<gk_grid(N), GK_THREADS, gk_smem_bytes(), st>>>(md, N, th, seed, epoch, tag, id0, dist);
@@ -341,7 +341,7 @@ static void gk_l_sim(cudaStream_t st, const PriorDev*, const ModelData& md, int6
 
 const ModelOps* ops_gk()
 {
-    static const ModelOps o = { GK::name, GK::D, GK::BLOB, &gk_l_init, &gk_l_smc, nullptr /* abcdemc!: not for this model */, &gk_l_sim };
+    static const ModelOps o = { GK::name, GK::D, GK::BLOB, &gk_l_init, &gk_l_smc, nullptr /* abcdemc!: not for this model */, &gk_l_sim, nullptr };
     return &o;
 }
 

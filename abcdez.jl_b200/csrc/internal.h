@@ -1,10 +1,12 @@
 // internal.h -- host-side objects behind the opaque handles of include/abcdez_cuda.h and the
 // launcher interface between api.cu, sweep.cu and bookkeeping.cu.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
+#endif
 #include "common.cuh"
 #include "models.cuh"
 
@@ -103,18 +105,29 @@ struct McArgs {
     const uint32_t* order;        // particle index per sorted position
 };
 
-// per-model launchers (sweep.cu)
+#ifdef __CUDACC_RTC__
+}  // namespace abcdez: runtime-compiled models (rtc.cu) see only the device-side declarations above
+#else                             // ---- host side from here on ----
+
+// per-model launchers: the static registry (inst_*.cu, gk.cu) and the runtime-compiled models (rtc.cu)
 struct ModelOps {
     const char* name;
     int d, blob;
-    void (*init)(cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, uint64_t seed, int draw_prior);
-    void (*smc_sweep)(cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, const SweepInj&);
-    void (*mc_sweep)(cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, const SweepInj&, const McArgs&);
-    void (*simulate)(cudaStream_t, const PriorDev*, const ModelData&, int64_t N, const double* theta_pushed,
+    void (*init)(const ModelOps&, cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, uint64_t seed, int draw_prior);
+    void (*smc_sweep)(const ModelOps&, cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, const SweepInj&);
+    void (*mc_sweep)(const ModelOps&, cudaStream_t, const PopDev&, const PriorDev&, const ModelData&, const SweepInj&, const McArgs&);
+    void (*simulate)(const ModelOps&, cudaStream_t, const PriorDev*, const ModelData&, int64_t N, const double* theta_pushed,
                      uint64_t seed, uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs);
+    void* dyn;                    // runtime-compiled models: their loaded module (rtc.cu); nullptr for the static registry
 };
 const ModelOps* model_ops(int id);
 int model_count();
+
+// runtime-compiled models (rtc.cu): CUDA source of one model struct -> NVRTC -> module -> a registry entry
+int rtc_compile_model(const char* name, const char* struct_name, const char* cuda_src, int d, int blob_bytes, int load,
+                      int* id, std::string* log);
+const ModelOps* rtc_model_ops(int id);            // id >= M_COUNT
+int rtc_model_count();
 
 // dimension-only launchers for the prior stage calls (sweep.cu)
 void launch_prior_op(cudaStream_t, int d, const PriorDev&, int64_t N, int op, const double* in, double* out,
@@ -199,3 +212,5 @@ struct abcdez_pop {
     cudaEvent_t ev0, ev1;
     double last_ms; int64_t last_launches;
 };
+
+#endif  // __CUDACC_RTC__

@@ -27,9 +27,9 @@ const ModelOps* model_ops(int id)
     case M_GK: return ops_gk();            // CTA-cooperative simulator (gk.cu)
     case M_SOCKS: return ops_socks();
     }
-    return nullptr;
+    return rtc_model_ops(id);          // runtime-compiled models (rtc.cu) follow the static ones
 }
-int model_count() { return M_COUNT; }
+int model_count() { return M_COUNT + rtc_model_count(); }
 
 static inline unsigned grid_for(int64_t N, int threads) { return (unsigned)((N + threads - 1) / threads); }
 

@@ -545,6 +545,7 @@ simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* _
     }
 }
 
+#ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------------------------------
 // launchers + registry
 // ---------------------------------------------------------------------------------------
@@ -559,12 +560,12 @@ static inline bool prior_has_discrete(const PriorDev& pr)
 }
 
 template <class M>
-static void l_init(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
+static void l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
     init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, seed, dp);
 }
 template <class M>
-static void l_smc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
+static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
 {
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     bool all_normal = true, all_uniform = true;
@@ -575,7 +576,7 @@ static void l_smc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const Mo
     else smc_sweep_kernel<M, false, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
 }
 template <class M>
-static void l_mc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
+static void l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
                  const McArgs& mc)
 {
     if (prior_has_discrete<M::D>(pr))
@@ -584,7 +585,7 @@ static void l_mc(cudaStream_t st, const PopDev& P, const PriorDev& pr, const Mod
         mc_sweep_kernel<M, false><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj, mc);
 }
 template <class M>
-static void l_sim(cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
+static void l_sim(const ModelOps&, cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
                   uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs)
 {
     simulate_kernel<M><<<grid_for(N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(md, N, th, seed, epoch, tag, id0, dist, blobs);
@@ -595,11 +596,12 @@ static ModelOps make_ops()
 {
     ModelOps o;
     o.name = M::name; o.d = M::D; o.blob = M::BLOB;
-    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>;
+    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr;
     return o;
 }
 
 // one accessor per model, defined in the inst_*.cu translation units (compiled in parallel)
 #define ABCDEZ_DEFINE_MODEL(fn, M) const ModelOps* fn() { static const ModelOps o = make_ops<M>(); return &o; }
+#endif  // __CUDACC_RTC__
 
 }  // namespace abcdez

@@ -73,7 +73,7 @@ EXPORTS = [
     "abcdez_nccl_unique_id", "abcdez_comm_init", "abcdez_shard_range", "abcdez_comm_selftest",
     "abcdez_prior_create", "abcdez_prior_destroy", "abcdez_prior_sample", "abcdez_prior_logpdf", "abcdez_prior_push",
     "abcdez_model_count", "abcdez_model_name", "abcdez_model_lookup", "abcdez_model_info", "abcdez_model_bind",
-    "abcdez_model_destroy", "abcdez_simulate", "abcdez_kernel_pdf", "abcdez_kernel_logpdf",
+    "abcdez_model_destroy", "abcdez_model_compile", "abcdez_simulate", "abcdez_kernel_pdf", "abcdez_kernel_logpdf",
     "abcdez_smc_opts_default", "abcdez_smc_run", "abcdez_mc_opts_default", "abcdez_mc_run",
     "abcdez_pop_create", "abcdez_pop_destroy", "abcdez_pop_upload", "abcdez_pop_download", "abcdez_pop_set",
     "abcdez_pop_init", "abcdez_pop_smc_sweep", "abcdez_pop_mc_sweep", "abcdez_pop_eps_quantile",
@@ -407,6 +407,22 @@ def _kernel_kind(k) -> int:
 def model_names():
     L = lib()
     return [L.abcdez_model_name(i).decode() for i in range(L.abcdez_model_count())]
+
+
+def compile_model(name: str, struct_name: str, cuda_src: str, d: int, blob_bytes: int = 0,
+                  ctx: Optional["Context"] = None, load: bool = True) -> str:
+    """Runtime-supplied `dist!`: compile the CUDA source of one model struct (include/abcdez_cuda.h,
+    abcdez_model_compile) and register it under `name`; afterwards `Model(name, data)` works like a built-in.
+    load=False: compile only (no GPU needed).  Returns the NVRTC log."""
+    log = C.create_string_buffer(1 << 16)
+    mid = C.c_int(-1)
+    h = None
+    if load:
+        ctx = ctx or default_context()
+        h = ctx._h
+    _check(lib().abcdez_model_compile(h, name.encode(), struct_name.encode(), cuda_src.encode(), int(d), int(blob_bytes),
+                                      C.byref(mid), log, C.c_size_t(len(log))))
+    return log.value.decode("utf-8", "replace")
 
 
 class Model:

@@ -18,7 +18,7 @@ module ABCdeZCUDA
 using Distributions
 using Random
 
-export Factored, abcdesmc!, abcdemc!, DeviceModel, Context, nccl_unique_id, comm_init!, shard_range
+export Factored, abcdesmc!, abcdemc!, DeviceModel, compile_model, Context, nccl_unique_id, comm_init!, shard_range
 export Indicator0toϵ, IndicatorStrict0toϵ, Epa0toϵ, EpaStrict0toϵ
 
 const LIB = get(ENV, "ABCDEZ_LIB", joinpath(@__DIR__, "..", "libabcdez_cuda.so"))
@@ -109,6 +109,22 @@ default_context() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Context(parse
 struct DeviceModel
     name::String
     data::Vector{Float64}
+end
+
+"""
+    compile_model(name, struct_name, cuda_src, d; blob_bytes=0, ctx=default_context())
+
+Runtime-supplied `dist!`: the CUDA source of one model struct (see include/abcdez_cuda.h, abcdez_model_compile) is
+compiled with NVRTC against the library's kernel templates and registered; `DeviceModel(name, data)` then works
+like a built-in model.  Throws with the NVRTC log on a compile error.
+"""
+function compile_model(name::String, struct_name::String, cuda_src::String, d::Integer; blob_bytes::Integer=0,
+                       ctx::Context=default_context())
+    id = Ref{Cint}(-1); log = zeros(UInt8, 1 << 16)
+    check(ccall((:abcdez_model_compile, LIB), Cint,
+                (Ptr{Cvoid}, Cstring, Cstring, Cstring, Cint, Cint, Ref{Cint}, Ptr{UInt8}, Csize_t),
+                ctx.h, name, struct_name, cuda_src, d, blob_bytes, id, log, length(log)))
+    Int(id[])
 end
 
 function prior_handle(ctx::Context, prior)

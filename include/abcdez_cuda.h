@@ -16,8 +16,10 @@
 #ifndef ABCDEZ_CUDA_H
 #define ABCDEZ_CUDA_H
 
+#ifndef __CUDACC_RTC__          /* runtime-compiled models (abcdez_model_compile): NVRTC has no system headers */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -119,6 +121,21 @@ int abcdez_model_info(int id, int* d, int* blob_bytes);
 /* bind observed data (<= ABCDEZ_MAXDATA doubles; the `data` captured by the Julia closure) */
 int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, size_t ndata, abcdez_model** out);
 int abcdez_model_destroy(abcdez_model* m);
+/* Runtime-supplied model: the closest analogue of passing an arbitrary Julia `dist!` (src/abcdez_smc.jl:215).
+ * cuda_src is the CUDA C++ source of one struct (placed in namespace abcdez, so Philox streams, the portable
+ * math and the helpers of csrc/common.cuh are in scope):
+ *     struct MyModel {
+ *         static constexpr int D = 2, BLOB = 0, NOISE = 0;           // length(prior), blob bytes (multiple of 8)
+ *         static constexpr const char* name = "my_model";
+ *         __device__ static double run(const double* theta, const double* data, SimRng& rng, double* blob) {...}
+ *     };
+ * It is compiled with NVRTC for sm_100a against the library's own kernel templates (the init, abcdesmc_swarm!,
+ * abcdemc_swarm! and simulate kernels are instantiated for it at run time) and registered under `name`:
+ * abcdez_model_lookup / _bind and both run calls then treat it like a built-in model.  d / blob_bytes must equal
+ * the struct's D / BLOB (checked at compile time).  log (optional, log_cap bytes) receives the NVRTC log.
+ * ctx == NULL: compile only -- validates a model on a machine without a GPU; *id = -1. */
+int abcdez_model_compile(abcdez_ctx* ctx, const char* name, const char* struct_name, const char* cuda_src,
+                         int d, int blob_bytes, int* id, char* log, size_t log_cap);
 /* one dist! evaluation per row of theta_pushed with stream (seed, id0+i, epoch, tag) */
 int abcdez_simulate(abcdez_ctx* ctx, const abcdez_model* m, int64_t N, const double* theta_pushed,
                     uint64_t seed, uint32_t epoch, uint32_t tag, int64_t id0, double* dist_out,
