@@ -155,7 +155,7 @@ extern "C" int abcdez_prior_create(abcdez_ctx* ctx, int d, const int32_t* family
         for (int j = 0; j < 4; ++j) p->dev.p[k][j] = q[j];
         bool ok = true; double c = 0.0;
         switch (family[k]) {
-        case ABCDEZ_NORMAL: ok = q[1] > 0.0; c = log(q[1]); break;
+        case ABCDEZ_NORMAL: ok = q[1] > 0.0; c = log(q[1]); p->dev.p[k][2] = ok ? pdiv_host_reciprocal(q[1]) : 0.0; break;
         case ABCDEZ_UNIFORM: ok = q[0] < q[1]; c = -log(q[1] - q[0]); break;
         case ABCDEZ_DISCRETE_UNIFORM: ok = q[0] <= q[1] && q[0] == rint(q[0]) && q[1] == rint(q[1]);
             c = log(1.0 / (q[1] - q[0] + 1.0)); break;
@@ -237,6 +237,16 @@ extern "C" int abcdez_model_info(int id, int* d, int* blob_bytes)
     if (blob_bytes) *blob_bytes = o->blob;
     return ABCDEZ_OK;
 }
+// derived constants a simulator would otherwise recompute per particle (the same IEEE operations, done once)
+static void model_prepare_data(int id, double* v)
+{
+    if (id == M_GAUSS_CORR10) {                     // sqrt(1 - rho^2) of the AR(1) noise, models.cuh
+        volatile double r2 = v[10] * v[10];         // (volatile: never contracted into an fma)
+        volatile double om = 1.0 - r2;
+        v[11] = sqrt(om);
+    }
+}
+
 extern "C" int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, size_t ndata, abcdez_model** out)
 {
     CHECK_ARG(ctx && out, "abcdez_model_bind: NULL argument");
@@ -250,6 +260,7 @@ extern "C" int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, si
     m->id = id; m->ops = o;
     memset(&m->data, 0, sizeof(m->data));
     for (size_t i = 0; i < ndata; ++i) m->data.v[i] = data[i];
+    model_prepare_data(id, m->data.v);
     *out = m;
     return ABCDEZ_OK;
 }
@@ -534,6 +545,7 @@ extern "C" int abcdez_pop_set(abcdez_pop* pop, double eps, double eps_kernel_pre
     Ctrl* c = pop->h_ctrl;
     c->eps = eps; c->eps_k = eps_kernel_prev; c->kind = kernel; c->gamma0 = gamma0; c->gsig = gamma_sigma;
     c->seed = seed; c->sweep_epoch = sweep_epoch;
+    pop->dev.keys = philox_keys(seed);
     c->stop = 0; c->sweeps_done = 0; c->sweep_idx = 0; c->Kmcmc = 0x7fffffff; c->Ki = 1;
     c->Kmcmc_min = INFINITY; c->naccs_iter = 0; c->err = 0; c->acc.err = 0;
     rc = push_ctrl(pop); if (rc) return rc;
@@ -915,6 +927,7 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     c->nsims_max = o->nsims_max; c->Kmcmc = o->Kmcmc; c->Ki = o->Kmcmc; c->Kmcmc_min = o->Kmcmc_min;
     c->kind = o->kernel; c->facc_stop = o->facc_stop; c->facc_min = o->facc_min; c->facc_tune = o->facc_tune;
     c->seed = o->seed; c->max_iters = o->max_iters; c->hist_cap = hist_cap;
+    pop->dev.keys = philox_keys(o->seed);
     rc = push_ctrl(pop);
     std::vector<cudaEvent_t>& evs = ctx->ev_pool;
     size_t nev = 0;
@@ -1055,6 +1068,7 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
     cudaStream_t st = ctx->stream;
     Ctrl* c = pop->h_ctrl;
     c->seed = o->seed; c->eps_target = eps_target;
+    pop->dev.keys = philox_keys(o->seed);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int64_t launches = 0;
     SweepInj noinj; memset(&noinj, 0, sizeof(noinj));

@@ -147,7 +147,7 @@ static inline size_t gk_smem_bytes() { return sizeof(GkSmem) + (size_t)GK_MAXN *
 // ---- abcde_init! (src/abcdez_init.jl:2-22), one CTA per particle ----------------------------------------
 __global__ void __launch_bounds__(GK_THREADS)
 gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
-               uint64_t seed, int draw_prior)
+               const __grid_constant__ PhiloxKeys seed, int draw_prior)
 {
     constexpr int D = GK::D;
     GK_SMEM_DECL
@@ -228,7 +228,7 @@ gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pr
         }
         uint8_t flag = 0; unsigned acc_now = 0;
         const uint32_t pid = P.id0 + i;
-        const uint64_t seed = c->seed;
+        const PhiloxKeys& seed = P.keys;
         const uint32_t epoch = c->sweep_epoch;
         uint32_t a, b; int perr = 0;
         if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
@@ -295,7 +295,7 @@ gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pr
 
 // ---- one dist! evaluation per row (stage-level model parity) ------------------------------------------------
 __global__ void __launch_bounds__(GK_THREADS)
-gk_simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, uint64_t seed,
+gk_simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, const __grid_constant__ PhiloxKeys seed,
                    uint32_t epoch, uint32_t tag, uint32_t id0, double* __restrict__ dist)
 {
     GK_SMEM_DECL
@@ -327,7 +327,7 @@ static unsigned gk_grid(int64_t N)
 
 static void gk_l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
-    gk_init_kernel<<<gk_grid(P.N), GK_THREADS, gk_smem_bytes(), st>>>(P, pr, md, seed, dp);
+    gk_init_kernel<<<gk_grid(P.N), GK_THREADS, gk_smem_bytes(), st>>>(P, pr, md, philox_keys(seed), dp);
 }
 static void gk_l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
 {
@@ -336,7 +336,7 @@ static void gk_l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Pr
 static void gk_l_sim(const ModelOps&, cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
                      uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double*)
 {
-    gk_simulate_kernel<<<gk_grid(N), GK_THREADS, gk_smem_bytes(), st>>>(md, N, th, seed, epoch, tag, id0, dist);
+    gk_simulate_kernel<<<gk_grid(N), GK_THREADS, gk_smem_bytes(), st>>>(md, N, th, philox_keys(seed), epoch, tag, id0, dist);
 }
 
 const ModelOps* ops_gk()

@@ -91,6 +91,7 @@ struct PopDev {
     uint32_t Ng;                  // particles of the whole (sharded) population; == N on one GPU
     XchgDev x;
     const PeerTable* peers;       // device table, sharded runs only
+    PhiloxKeys keys;              // round keys of the run's seed (== philox_keys(ctrl->seed)); constant-bank operands of the streams
 };
 
 struct SweepInj {

@@ -37,6 +37,7 @@ struct Gauss1DBlob {
 };
 
 // config 2: y ~ N(theta, Sigma), Sigma_ij = rho^|i-j| (stationary AR(1) noise), d = ||y - y_obs||_2
+// data = y_obs[10], rho, and data[11] = sqrt(1 - rho^2), filled in by abcdez_model_bind (model_prepare_data, api.cu)
 // NOISE > 0: the simulator's random input does not depend on theta, so the sweep kernel may draw it
 // (draw) while the partner rows are still in flight and score it afterwards (score); run == draw + score.
 struct GaussCorr10 {
@@ -49,7 +50,7 @@ struct GaussCorr10 {
     }
     __device__ static __forceinline__ double score(const double* th, const double* data, const double* nz, double*)
     {
-        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0;
+        double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
             e = (k == 0) ? nz[0] : rho * e + sr * nz[k];
@@ -84,7 +85,7 @@ struct GaussCorr10 {
     }
     __device__ static __forceinline__ double score_from(const double* th, const double* data, const double* col, int stride, double*)
     {
-        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0;
+        double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
             double z = col[k * stride];
@@ -97,7 +98,7 @@ struct GaussCorr10 {
     // noise pairs are consumed as they are generated (same arithmetic as draw + score, 18 fewer live registers)
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
-        double rho = data[10], sr = sqrt(1.0 - rho * rho), e = 0.0, acc = 0.0;
+        double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; k += 2) {
             double za, zb;

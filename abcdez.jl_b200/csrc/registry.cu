@@ -38,7 +38,7 @@ static inline unsigned grid_for(int64_t N, int threads) { return (unsigned)((N +
 // ---------------------------------------------------------------------------------------
 template <int D>
 __global__ void prior_op_kernel(const __grid_constant__ PriorDev pr, int64_t N, int op, const double* __restrict__ in,
-                                double* __restrict__ out, uint64_t seed, uint32_t epoch, uint32_t id0)
+                                double* __restrict__ out, const __grid_constant__ PhiloxKeys seed, uint32_t epoch, uint32_t id0)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -64,7 +64,7 @@ template <int D>
 static void l_prior(cudaStream_t st, const PriorDev& pr, int64_t N, int op, const double* in, double* out,
                     uint64_t seed, uint32_t epoch, uint32_t id0)
 {
-    prior_op_kernel<D><<<grid_for(N, 128), 128, 0, st>>>(pr, N, op, in, out, seed, epoch, id0);
+    prior_op_kernel<D><<<grid_for(N, 128), 128, 0, st>>>(pr, N, op, in, out, philox_keys(seed), epoch, id0);
 }
 
 void launch_prior_op(cudaStream_t st, int d, const PriorDev& pr, int64_t N, int op, const double* in, double* out,

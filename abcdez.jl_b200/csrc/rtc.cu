@@ -106,7 +106,8 @@ static bool has_discrete(const PriorDev& pr)
 static void dyn_init(const ModelOps& o, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
     DynModel* m = (DynModel*)o.dyn;
-    void* params[] = { (void*)&P, (void*)&pr, (void*)&md, (void*)&seed, (void*)&dp };
+    const PhiloxKeys keys = philox_keys(seed);
+    void* params[] = { (void*)&P, (void*)&pr, (void*)&md, (void*)&keys, (void*)&dp };
     dyn_launch(m->fn[K_INIT], grid_of(P.N, SWEEP_THREADS), st, params);
 }
 static void dyn_smc(const ModelOps& o, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
@@ -129,7 +130,8 @@ static void dyn_sim(const ModelOps& o, cudaStream_t st, const PriorDev*, const M
                     uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs)
 {
     DynModel* m = (DynModel*)o.dyn;
-    void* params[] = { (void*)&md, (void*)&N, (void*)&th, (void*)&seed, (void*)&epoch, (void*)&tag, (void*)&id0, (void*)&dist, (void*)&blobs };
+    const PhiloxKeys keys = philox_keys(seed);
+    void* params[] = { (void*)&md, (void*)&N, (void*)&th, (void*)&keys, (void*)&epoch, (void*)&tag, (void*)&id0, (void*)&dist, (void*)&blobs };
     dyn_launch(m->fn[K_SIM], grid_of(N, SWEEP_THREADS), st, params);
 }
 

@@ -27,6 +27,9 @@
 #ifndef ABCDEZ_SWEEP_PREFETCH
 #define ABCDEZ_SWEEP_PREFETCH 0         // L2 prefetch of the partner rows: measured slower (more LSU work than it hides)
 #endif
+#ifndef ABCDEZ_SWEEP_ASYNC_ROWS
+#define ABCDEZ_SWEEP_ASYNC_ROWS 0       // partner rows staged through shared memory with cp.async (requested as soon as the
+#endif                                  // partner indices are known, consumed after the jitter's Box-Muller pair)
 #ifndef ABCDEZ_SWEEP_EARLY_NOISE
 #define ABCDEZ_SWEEP_EARLY_NOISE 0      // 1: noise in registers before the gathers; 2: parked in shared memory; 3: all pairs in
 #endif                                  // lockstep (box_muller_batch) + shared memory -- all measured slower than consuming pairs as drawn
@@ -189,7 +192,7 @@ __device__ __forceinline__ void copy_scalars(const PopDev& P, int cur, int nxt, 
 template <class M>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
-            uint64_t seed, int draw_prior)
+            const __grid_constant__ PhiloxKeys seed, int draw_prior)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
@@ -249,7 +252,12 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // DISC: the prior has discrete marginals (push_p rounds a copy of the proposal); the common
 // all-continuous case passes the proposal registers straight to the simulator.
 // ---------------------------------------------------------------------------------------
-template <class M, bool DISC, int PK>
+// ASYNC: the partner rows travel through dynamic shared memory (2 * row bytes per thread, sweep_async_smem<D>());
+// the launchers of the static registry use it for d >= 2, runtime-compiled models keep the direct gathers.
+template <int D>
+constexpr size_t sweep_async_smem() { return (size_t)2 * row_stride(D) * 8 * SWEEP_THREADS; }
+
+template <class M, bool DISC, int PK, bool ASYNC = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                  const __grid_constant__ SweepInj inj)
@@ -262,6 +270,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
     const double* __restrict__ th = P.theta[cur];
     __shared__ SweepSmem s_red;
     sweep_smem_init(&s_red);
+    extern __shared__ double2 s_rows[];                    // ASYNC: [2 * DS/2 pieces][SWEEP_THREADS]
 
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
@@ -270,7 +279,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
 #endif
 #if ABCDEZ_SWEEP_CTRL_BATCH
     // every schedule scalar the particle work needs, loaded back to back (one L2 round trip, not six)
-    const uint64_t seed = c->seed;
+    const PhiloxKeys& seed = P.keys;
     const uint32_t epoch = c->sweep_epoch;
     const double gamma0 = c->gamma0, gsig = c->gsig, eps = c->eps;
     const int kind = c->kind;
@@ -291,7 +300,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
             uint8_t flag = 0;
             const uint32_t pid = P.id0 + i;
 #if !ABCDEZ_SWEEP_CTRL_BATCH
-            const uint64_t seed = c->seed;
+            const PhiloxKeys& seed = P.keys;
             const uint32_t epoch = c->sweep_epoch;
 #endif
             // (1) partners: integer work only (plus list lookups while some particles are dead)
@@ -313,6 +322,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                     b = wsample_alive(P.alive_list, n_alive, N, u2);
                 }
             }
+            if constexpr (ASYNC) { if (!err) rows_async_issue<D>(th, a, b, s_rows + threadIdx.x, SWEEP_THREADS); }
 #if ABCDEZ_SWEEP_PREFETCH
             // the two partner rows are random gathers (DRAM latency): request their sectors now, consume them
             // after the random-number work below
@@ -359,7 +369,8 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                 copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
             }
             if (!err) {
-                de_proposal<D>(th, a, b, g, thp);                          // :128
+                if constexpr (ASYNC) { rows_async_wait(); de_proposal_staged<D>(s_rows + threadIdx.x, SWEEP_THREADS, g, thp); }
+                else de_proposal<D>(th, a, b, g, thp);                     // :128
                 double xs[DISC ? D : 1];
                 const double* x = thp;
                 if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
@@ -439,7 +450,7 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
         }
         uint8_t flag = 0;
         const uint32_t pid = P.id0 + i;
-        const uint64_t seed = c->seed;
+        const PhiloxKeys& seed = P.keys;
         const uint32_t epoch = c->sweep_epoch;
         uint32_t s = i;                                                    // :18
         const double eps = (dli <= mc.eps_target) ? mc.eps_target : mc.eps_pop;   // :19
@@ -528,7 +539,7 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
 // one dist! evaluation per row (stage-level model parity); dense N x D input
 template <class M>
 __global__ void __launch_bounds__(SWEEP_THREADS)
-simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, uint64_t seed,
+simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, const __grid_constant__ PhiloxKeys seed,
                 uint32_t epoch, uint32_t tag, uint32_t id0, double* __restrict__ dist, double* __restrict__ blobs)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
@@ -562,7 +573,7 @@ static inline bool prior_has_discrete(const PriorDev& pr)
 template <class M>
 static void l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
-    init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, seed, dp);
+    init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, philox_keys(seed), dp);
 }
 template <class M>
 static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
@@ -570,10 +581,21 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     bool all_normal = true, all_uniform = true;
     for (int k = 0; k < M::D; ++k) { all_normal = all_normal && pr.family[k] == ABCDEZ_NORMAL; all_uniform = all_uniform && pr.family[k] == ABCDEZ_UNIFORM; }
-    if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
-    else if (all_normal) smc_sweep_kernel<M, false, PK_NORMAL><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
-    else if (all_uniform) smc_sweep_kernel<M, false, PK_UNIFORM><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
-    else smc_sweep_kernel<M, false, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    constexpr bool A = ABCDEZ_SWEEP_ASYNC_ROWS && M::D >= 2;
+    constexpr size_t sm = A ? sweep_async_smem<M::D>() : 0;
+    if constexpr (sm > 48 * 1024) {                       // opt in once per instantiation (d > 12)
+        static const bool once = [] {
+            cudaFuncSetAttribute(smc_sweep_kernel<M, true, PK_GENERIC, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(smc_sweep_kernel<M, false, PK_NORMAL, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(smc_sweep_kernel<M, false, PK_UNIFORM, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(smc_sweep_kernel<M, false, PK_GENERIC, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            return true; }();
+        (void)once;
+    }
+    if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
+    else if (all_normal) smc_sweep_kernel<M, false, PK_NORMAL, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
+    else if (all_uniform) smc_sweep_kernel<M, false, PK_UNIFORM, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
+    else smc_sweep_kernel<M, false, PK_GENERIC, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
 }
 template <class M>
 static void l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
@@ -588,7 +610,7 @@ template <class M>
 static void l_sim(const ModelOps&, cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
                   uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs)
 {
-    simulate_kernel<M><<<grid_for(N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(md, N, th, seed, epoch, tag, id0, dist, blobs);
+    simulate_kernel<M><<<grid_for(N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(md, N, th, philox_keys(seed), epoch, tag, id0, dist, blobs);
 }
 
 template <class M>

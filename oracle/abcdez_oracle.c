@@ -216,6 +216,34 @@ double orc_pexp(double x) { return pexp(x); }
 double orc_plgamma(double x) { return plgamma(x); }
 void orc_psincos2pi(double u, double* s, double* c) { psincos2pi(u, s, c); }
 
+/* Checker for an evaluation shortcut of the CUDA library (csrc/common.cuh pdiv_r): the z-score of a Normal
+ * marginal, (x - mu) / sigma, is evaluated there through the host-rounded reciprocal rb = RN(1/sigma) as
+ * q = RN(a*rb); r = fma(-sigma, q, a); z = RN(q + r*rb)  (Markstein's correction step; correctly rounded when
+ * rb is).  The oracle itself keeps the plain division; this routine counts, over n pseudo-random numerators
+ * (xorshift64*, magnitudes spread over 2^-40..2^40, including values just below powers of two), how often
+ * the shortcut differs from a / sigma.  Expected: 0. */
+int64_t orc_pdiv_mismatches(int64_t n, uint64_t seed, double sigma)
+{
+    const double rb = 1.0 / sigma;
+    uint64_t st = seed ? seed : 0x9E3779B97F4A7C15ull;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        st ^= st >> 12; st ^= st << 25; st ^= st >> 27;
+        uint64_t r = st * 0x2545F4914F6CDD1Dull;
+        uint64_t mant = r & 0x000fffffffffffffull;
+        if ((i & 7) == 7) mant |= 0x000ffffffffff000ull;            /* significand close to 2 */
+        if ((i & 15) == 8) mant &= 0x0000000000000fffull;           /* significand close to 1 */
+        uint64_t ex = 1023u - 40u + ((r >> 52) % 81u);
+        uint64_t bits = (r & 0x8000000000000000ull) | (ex << 52) | mant;
+        double a; memcpy(&a, &bits, 8);
+        double q = a * rb;
+        double rr = fma(-sigma, q, a);
+        double z = fma(rr, rb, q);
+        if (z != a / sigma) bad++;
+    }
+    return bad;
+}
+
 /* Randomness contract: stream tags (DESIGN.md "Randomness contract"). */
 enum {
     TAG_PRIOR = 1,      /* prior draws; c3 = (dim<<16) | block              */

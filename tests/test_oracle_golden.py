@@ -280,3 +280,16 @@ def test_portable_math_accuracy(oracle):
         err = max(err, abs(s.value - math.sin(2 * math.pi * u)), abs(c.value - math.cos(2 * math.pi * u)))
         assert abs(s.value ** 2 + c.value ** 2 - 1.0) < 1e-15
     assert err < 2e-15
+
+
+# ---- the library's division shortcut for Normal z-scores (csrc/common.cuh pdiv_r) equals a / sigma --------------
+def test_reciprocal_division_shortcut_is_exact(oracle):
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_pdiv_mismatches.restype = C.c_int64
+    L.orc_pdiv_mismatches.argtypes = [C.c_int64, C.c_uint64, C.c_double]
+    sigmas = [1.0, 2.0, 3.0, 10.0, math.sqrt(10.0), 0.1, 0.01, 1.0 / 3.0, 5.0, 1e-3, 123.456, 2.0 ** 0.5, 7.0, 1e5]
+    rng = np.random.default_rng(7)
+    sigmas += list(10 ** rng.uniform(-6, 6, 26))
+    for k, s in enumerate(sigmas):
+        assert L.orc_pdiv_mismatches(500_000, 1234 + k, float(s)) == 0, s
