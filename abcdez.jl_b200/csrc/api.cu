@@ -400,7 +400,7 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
         { (void**)&P.W, n * 8 }, { (void**)&P.alive, n + 4 }, { (void**)&P.moved, n + 4 },
         { (void**)&P.alive_list, n * 4 }, { (void**)&P.ctrl, sizeof(Ctrl) },
         { (void**)&P.partial, (size_t)P.ntiles * 2 * 8 + 64 }, { (void**)&P.tile_cnt, (size_t)P.ntiles * 4 + 64 },
-        { (void**)&P.sel_hist, 6 * SEL_BINS * 4 }, { (void**)&P.cumsum, n * 8 }, { (void**)&P.inds, n * 4 },
+        { (void**)&P.sel_hist, 7 * SEL_BINS * 4 }, { (void**)&P.cumsum, n * 8 }, { (void**)&P.inds, n * 4 },
         { (void**)&P.hist, (size_t)(hist_cap > 0 ? hist_cap : 1) * 8 * 8 }, { (void**)&P.tabs, 2 * sizeof(SeqTab) },
         { (void**)&pop->scratch, scratch_need },
     };
@@ -445,7 +445,7 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     }
     CU(cudaEventCreateWithFlags(&pop->ev0, cudaEventDefault)); CU(cudaEventCreateWithFlags(&pop->ev1, cudaEventDefault));
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(P.sel_hist, 0, 6 * SEL_BINS * 4, st));
+    CU(cudaMemsetAsync(P.sel_hist, 0, 7 * SEL_BINS * 4, st));
     CU(cudaMemsetAsync(P.alive, 1, n, st));
     CU(cudaMemsetAsync(P.moved, 1, n, st));
     CU(cudaMemsetAsync(P.theta[0], 0, n * pop->DS * 8, st));

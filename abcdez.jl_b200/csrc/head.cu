@@ -37,7 +37,7 @@ struct HeadSmem {
     unsigned wcnt[32];
     unsigned long long wmin[32];
     unsigned long long mn, mx, mab;
-    unsigned found_bin, found_before, flag;
+    unsigned found_bin, found_before, found_cnt, flag;
     unsigned long long xh[8];                     // sharded runs: this rank's header record of an exchange
     unsigned long long xall[XCHG_MAXR * 8];       // ... and every rank's, after it
     int xflag;
@@ -60,16 +60,21 @@ __device__ __noinline__ void pick_bin(const unsigned* h, bool global, int nbins,
         loc[k] = (b < nbins) ? (global ? __ldcg(&h[b]) : h[b]) : 0u;
         tot += loc[k];
     }
+    // exclusive prefix of the per-thread totals: shuffle scan inside the warps, then the warp totals
+    const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    unsigned incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
     __syncthreads();
-    s->part[threadIdx.x] = tot;
-    if (threadIdx.x == 0) { s->found_bin = 0xffffffffu; s->found_before = 0; }
+    if (lane == 31) s->part[wp] = incl;
+    if (threadIdx.x == 0) { s->found_bin = 0xffffffffu; s->found_before = 0; s->found_cnt = 0xffffffffu; }
     __syncthreads();
-    unsigned bef = 0;
-    for (int t = 0; t < (int)threadIdx.x; ++t) bef += s->part[t];
+    unsigned bef = incl - tot;
+    for (unsigned q = 0; q < wp; ++q) bef += s->part[q];
     unsigned cum = bef;
 #pragma unroll
     for (int k = 0; k < per; ++k) {
-        if (loc[k] && rank >= cum && rank < (unsigned long long)cum + loc[k]) { s->found_bin = threadIdx.x * per + k; s->found_before = cum; }
+        if (loc[k] && rank >= cum && rank < (unsigned long long)cum + loc[k]) { s->found_bin = threadIdx.x * per + k; s->found_before = cum; s->found_cnt = loc[k]; }
         cum += loc[k];
     }
     __syncthreads();
@@ -128,9 +133,36 @@ __device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M
         __syncthreads();
         unsigned bin; unsigned long long before;
         pick_bin(s->hist, false, nbins, rank, s, bin, before);
+        const unsigned in_bin = s->found_cnt;       // keys in the picked bin (read like found_bin: stable until the next pick_bin)
         prefix |= (unsigned long long)bin << shift;
         himask = pass_himask_after(p);
         rank -= before;
+        if (in_bin <= 32u && p < 5) {
+            // few keys left (the usual case after one digit): gather them and rank them directly instead of
+            // running the remaining digit passes; same key, the exact select does not depend on how it is found
+            __syncthreads();
+            if (threadIdx.x == 0) s->flag = 0u;
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < M; i += HEAD_THREADS) {
+                unsigned long long key = L[i];
+                if ((key & himask) == prefix) s->wmin[atomicAdd(&s->flag, 1u)] = key;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const unsigned n = s->flag;
+                const unsigned long long my = threadIdx.x < n ? s->wmin[threadIdx.x] : ~0ull;
+                unsigned r = 0;
+                for (unsigned k = 0; k < n; ++k) {
+                    const unsigned long long o = s->wmin[k];
+                    r += (o < my || (o == my && k < threadIdx.x)) ? 1u : 0u;
+                }
+                if (threadIdx.x < n && (unsigned long long)r == rank) s->mn = my;
+            }
+            __syncthreads();
+            prefix = s->mn;
+            __syncthreads();
+            break;
+        }
     }
     akey = prefix;
     // #{keys <= v[j]} and min{key > v[j]} on the list
@@ -227,12 +259,23 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
     const unsigned n_alive_prev = c->n_alive_g;
     const bool sharded = P.x.world > 1;
     const double* __restrict__ dl = P.delta[cur];
-    unsigned* H1 = P.sel_hist; unsigned* H2 = P.sel_hist + SEL_BINS;
+    unsigned* H1 = P.sel_hist; unsigned* H2 = P.sel_hist + SEL_BINS; unsigned* HW = P.sel_hist + 6 * SEL_BINS;
     unsigned long long rank = c->sel_rank;
+    const unsigned long long rank_all = rank;
 
-    // ---- pass 1: digit 53..63 of every alive key; extrema(delta) over all particles; NaN check --------
-    hist_clear(&s);
-    {
+    // ---- first pass over every alive key (+ extrema(delta) over all particles, NaN check) --------------
+    // Windowed digit: every alive distance lies in the support of the previous kernel, i.e. at or below eps_prev,
+    // and the alpha-quantile sits in the top two binades below it in all but degenerate populations.  So the
+    // first digit is the 22-bit key prefix (sign, exponent, 10 mantissa bits) RELATIVE to eps_prev's: bins
+    // 1..2046 are the 2046 prefixes up to and including eps_prev's own, bin 0 collects everything below the
+    // window and bin 2047 everything above it.  The map is monotone, so the select stays exact: when the rank
+    // falls into one of the single-prefix bins, 22 bits of v[j] are known after ONE pass (the generic scheme
+    // needs two: its leading 11-bit digit is the same for almost all distances); when it falls into a
+    // collecting bin (or eps_prev is not finite: first iteration) the generic two passes run instead.
+    const bool windowed = isfinite(eps_prev) && eps_prev > 0.0;
+    const unsigned long long wbase = (f64_key(windowed ? eps_prev : 1.0) >> 42) - 2046ull;
+    auto first_pass = [&](bool win, unsigned* H) {
+        hist_clear(&s);
         unsigned long long kmn = ~0ull, kmx = 0ull; int nan_seen = 0;
         for (unsigned tile = t0; tile < t1; ++tile) {
             size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
@@ -245,7 +288,12 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
                 unsigned long long key = f64_key(v[k]);
                 if (i0 + k < N) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
                 if (ok && isnan(v[k])) nan_seen = 1;
-                hist_add(s.hist, ok, (unsigned)(key >> 53));
+                unsigned digit;
+                if (win) {
+                    const unsigned long long d = key >> 42;
+                    digit = d <= wbase ? 0u : (d - wbase >= 2047ull ? 2047u : (unsigned)(d - wbase));
+                } else digit = (unsigned)(key >> 53);
+                hist_add(s.hist, ok, digit);
             }
         }
         if (tid == 0) { s.mn = ~0ull; s.mx = 0ull; }
@@ -253,43 +301,68 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
         kmn = warp_min_u64(kmn); kmx = warp_max_u64(kmx);
         if (lane == 0) { atomicMin(&s.mn, kmn); atomicMax(&s.mx, kmx); }
         if (nan_seen) atomicMax(&c->acc.err, (int)ABCDEZ_ERR_NAN_DISTANCE);
-        hist_flush(&s, H1, 2048);
+        hist_flush(&s, H, 2048);
         if (tid == 0) { atomicMin(&c->acc.dmin_key, s.mn); atomicMax(&c->acc.dmax_key, s.mx); }
-    }
-    grid.sync();
-    if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H1, 2048, true, &s); grid.sync(); }
+    };
     unsigned bin; unsigned long long before;
-    pick_bin(H1, true, 2048, rank, &s, bin, before);
-    if (blockIdx.x == 0 && tid == 0) patch_extrema(P, c);   // ranges_eps of the previous record, :363
-    if (bin == 0xffffffffu) {                               // empty alive set (uniform decision)
-        grid.sync();                                        // every CTA has read H1
-        if (blockIdx.x == 0 && tid == 0 && !c->err) c->err = ABCDEZ_ERR_NO_ALIVE;
-        if (blockIdx.x == 0) for (int b = tid; b < SEL_BINS; b += HEAD_THREADS) P.sel_hist[b] = 0u;
-        return;
-    }
-    unsigned long long prefix = (unsigned long long)bin << 53, himask = ~0ull << 53;
-    rank -= before;
-
-    // ---- pass 2: digit 42..52 among the keys of that bin -------------------------------------------
-    hist_clear(&s);
-    for (unsigned tile = t0; tile < t1; ++tile) {
-        size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-        double v[4];
-        load4_f64(dl, i0, N, v);
-        uint32_t al = load4_u8(P.alive, i0, N);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            unsigned long long key = f64_key(v[k]);
-            bool ok = ((al >> (8 * k)) & 0xff) && ((key & himask) == prefix);
-            hist_add(s.hist, ok, (unsigned)((key >> 42) & 2047ull));
+    unsigned long long prefix = 0ull, himask = 0ull;
+    bool have22 = false;
+    if (windowed) {
+        first_pass(true, HW);
+        grid.sync();
+        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, HW, 2048, true, &s); grid.sync(); }
+        pick_bin(HW, true, 2048, rank, &s, bin, before);
+        if (blockIdx.x == 0 && tid == 0) patch_extrema(P, c);   // ranges_eps of the previous record, :363
+        if (bin == 0xffffffffu) {                           // empty alive set (uniform decision)
+            grid.sync();                                    // every CTA has read HW
+            if (blockIdx.x == 0 && tid == 0 && !c->err) c->err = ABCDEZ_ERR_NO_ALIVE;
+            if (blockIdx.x == 0) for (int b = tid; b < SEL_BINS; b += HEAD_THREADS) HW[b] = 0u;
+            return;
+        }
+        if (bin >= 1u && bin <= 2046u) {
+            prefix = (wbase + (unsigned long long)bin) << 42; himask = ~0ull << 42;
+            rank -= before;
+            have22 = true;
         }
     }
-    hist_flush(&s, H2, 2048);
-    grid.sync();
-    if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H2, 2048, false, &s); grid.sync(); }
-    pick_bin(H2, true, 2048, rank, &s, bin, before);
-    prefix |= (unsigned long long)bin << 42; himask = ~0ull << 42;
-    rank -= before;
+    if (!have22) {
+        // ---- generic pass 1: digit 53..63 --------------------------------------------------------------
+        rank = rank_all;
+        first_pass(false, H1);
+        grid.sync();
+        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H1, 2048, !windowed, &s); grid.sync(); }
+        pick_bin(H1, true, 2048, rank, &s, bin, before);
+        if (!windowed && blockIdx.x == 0 && tid == 0) patch_extrema(P, c);   // ranges_eps of the previous record, :363
+        if (bin == 0xffffffffu) {                           // empty alive set (uniform decision)
+            grid.sync();                                    // every CTA has read H1
+            if (blockIdx.x == 0 && tid == 0 && !c->err) c->err = ABCDEZ_ERR_NO_ALIVE;
+            if (blockIdx.x == 0) for (int b = tid; b < SEL_BINS; b += HEAD_THREADS) { P.sel_hist[b] = 0u; HW[b] = 0u; }
+            return;
+        }
+        prefix = (unsigned long long)bin << 53; himask = ~0ull << 53;
+        rank -= before;
+
+        // ---- generic pass 2: digit 42..52 among the keys of that bin -----------------------------------
+        hist_clear(&s);
+        for (unsigned tile = t0; tile < t1; ++tile) {
+            size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
+            double v[4];
+            load4_f64(dl, i0, N, v);
+            uint32_t al = load4_u8(P.alive, i0, N);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned long long key = f64_key(v[k]);
+                bool ok = ((al >> (8 * k)) & 0xff) && ((key & himask) == prefix);
+                hist_add(s.hist, ok, (unsigned)((key >> 42) & 2047ull));
+            }
+        }
+        hist_flush(&s, H2, 2048);
+        grid.sync();
+        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H2, 2048, false, &s); grid.sync(); }
+        pick_bin(H2, true, 2048, rank, &s, bin, before);
+        prefix |= (unsigned long long)bin << 42; himask = ~0ull << 42;
+        rank -= before;
+    }
 
     // ---- pass 3: compact the keys sharing the 22-bit prefix; min key above the prefix ----------------
     unsigned long long* cand = P.cand[0];
@@ -456,7 +529,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
             for (int q = 0; q < 6; ++q) { c->acc.cand_count[q] = 0ull; c->acc.cand_min[q] = ~0ull; c->acc.cand_max[q] = 0ull; }
             c->acc.min_above = ~0ull;
         }
-        for (int b = tid; b < 6 * SEL_BINS; b += HEAD_THREADS) P.sel_hist[b] = 0u;              // every reader is past them
+        for (int b = tid; b < 7 * SEL_BINS; b += HEAD_THREADS) P.sel_hist[b] = 0u;              // every reader is past them
     }
 
     // ---- reweight pass B: Wns, alive, sum(Wns^2), alive counts per tile ------------------------------

@@ -15,11 +15,12 @@ namespace abcdez {
 constexpr int TILE = 1024;            // particles per CTA in the bookkeeping kernels (256 thr x 4)
 constexpr int BK_THREADS = 256;
 #ifndef ABCDEZ_SWEEP_THREADS
-#define ABCDEZ_SWEEP_THREADS 256
+#define ABCDEZ_SWEEP_THREADS 128
 #endif
 constexpr int SWEEP_THREADS = ABCDEZ_SWEEP_THREADS;    // thread-per-particle sweeps
 #ifndef ABCDEZ_SWEEP_MIN_BLOCKS
-#define ABCDEZ_SWEEP_MIN_BLOCKS 4      // 64 registers: 32 warps per SM beat 80 registers / 24 warps despite the spills (profiles/README.md)
+#define ABCDEZ_SWEEP_MIN_BLOCKS 7      // 7 x 128 threads, 72 registers (28 warps per SM): measured best of 24 / 28 / 32 warps, and
+                                       // 128-thread CTAs retire in finer grains than 256-thread ones (profiles/README.md)
 #endif
 constexpr int SWEEP_MIN_BLOCKS = ABCDEZ_SWEEP_MIN_BLOCKS;   // register cap of the fused sweep kernels
 constexpr int SEL_BINS = 2048;        // 11-bit radix-select digits
@@ -79,7 +80,7 @@ struct PopDev {
     Ctrl* ctrl;
     double* partial;              // per-CTA reduction partials (2 x nblocks)
     uint32_t* tile_cnt;           // per-tile alive counts -> exclusive offsets
-    uint32_t* sel_hist;           // 6 x SEL_BINS radix-select histograms (one per digit pass)
+    uint32_t* sel_hist;           // 7 x SEL_BINS radix-select histograms (one per digit pass + the head's windowed first pass)
     unsigned long long* cand[2];  // head.cu candidate lists (alias cumsum / scratch)
     double* cumsum;               // N inclusive cumulative weights (general-weight resampling)
     int32_t* inds;                // N resampling indices (0-based)

@@ -28,8 +28,12 @@
 #define ABCDEZ_SWEEP_PREFETCH 0         // L2 prefetch of the partner rows: measured slower (more LSU work than it hides)
 #endif
 #ifndef ABCDEZ_SWEEP_ASYNC_ROWS
-#define ABCDEZ_SWEEP_ASYNC_ROWS 0       // partner rows staged through shared memory with cp.async (requested as soon as the
-#endif                                  // partner indices are known, consumed after the jitter's Box-Muller pair)
+#define ABCDEZ_SWEEP_ASYNC_ROWS 0       // 1: partner rows staged through shared memory with cp.async (requested as soon as the
+#endif                                  // partner indices are known, consumed after the jitter's Box-Muller pair); 2: the
+                                        // particle's own row, logpi and delta too (requested before the partner draw)
+#ifndef ABCDEZ_SWEEP_EARLY_OWN
+#define ABCDEZ_SWEEP_EARLY_OWN 0        // 1: logpi / delta, 2: and the particle's own row, loaded before the partner draw
+#endif
 #ifndef ABCDEZ_SWEEP_EARLY_NOISE
 #define ABCDEZ_SWEEP_EARLY_NOISE 0      // 1: noise in registers before the gathers; 2: parked in shared memory; 3: all pairs in
 #endif                                  // lockstep (box_muller_batch) + shared memory -- all measured slower than consuming pairs as drawn
@@ -255,9 +259,9 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // ASYNC: the partner rows travel through dynamic shared memory (2 * row bytes per thread, sweep_async_smem<D>());
 // the launchers of the static registry use it for d >= 2, runtime-compiled models keep the direct gathers.
 template <int D>
-constexpr size_t sweep_async_smem() { return (size_t)2 * row_stride(D) * 8 * SWEEP_THREADS; }
+constexpr size_t sweep_async_smem(int level) { return (size_t)((level >= 2 ? 3 : 2) * row_stride(D) * 8 + (level >= 2 ? 16 : 0)) * SWEEP_THREADS; }
 
-template <class M, bool DISC, int PK, bool ASYNC = false>
+template <class M, bool DISC, int PK, int ASYNC = 0>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                  const __grid_constant__ SweepInj inj)
@@ -270,7 +274,10 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
     const double* __restrict__ th = P.theta[cur];
     __shared__ SweepSmem s_red;
     sweep_smem_init(&s_red);
-    extern __shared__ double2 s_rows[];                    // ASYNC: [2 * DS/2 pieces][SWEEP_THREADS]
+    extern __shared__ double2 s_rows[];                    // ASYNC: [2 * DS/2 partner pieces][T], then [DS/2 own pieces][T], [T] scalars
+    constexpr int NPIECE = row_stride(D) / 2;
+    double2* const s_own = s_rows + (size_t)2 * NPIECE * SWEEP_THREADS + threadIdx.x;
+    double2* const s_sc = s_rows + (size_t)3 * NPIECE * SWEEP_THREADS + threadIdx.x;
 
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
@@ -299,6 +306,16 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
         } else {
             uint8_t flag = 0;
             const uint32_t pid = P.id0 + i;
+            if constexpr (ASYNC >= 2) own_async_issue<D>(th, P.logpi[cur], P.delta[cur], i, s_own, s_sc, SWEEP_THREADS);
+#if ABCDEZ_SWEEP_EARLY_OWN >= 1
+            const double lpi_e = ld_early_f64(P.logpi[cur] + i), dli_e = ld_early_f64(P.delta[cur] + i);
+#endif
+#if ABCDEZ_SWEEP_EARLY_OWN >= 2
+            double thp_e[D];
+            load_row_early<D>(th, i, thp_e);
+#elif ABCDEZ_SWEEP_EARLY_OWN == 1 && ABCDEZ_SWEEP_PREFETCH
+            prefetch_row<D>(th, i);
+#endif
 #if !ABCDEZ_SWEEP_CTRL_BATCH
             const PhiloxKeys& seed = P.keys;
             const uint32_t epoch = c->sweep_epoch;
@@ -322,7 +339,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                     b = wsample_alive(P.alive_list, n_alive, N, u2);
                 }
             }
-            if constexpr (ASYNC) { if (!err) rows_async_issue<D>(th, a, b, s_rows + threadIdx.x, SWEEP_THREADS); }
+            if constexpr (ASYNC >= 1) { if (!err) rows_async_issue<D>(th, a, b, s_rows + threadIdx.x, SWEEP_THREADS); }
 #if ABCDEZ_SWEEP_PREFETCH
             // the two partner rows are random gathers (DRAM latency): request their sectors now, consume them
             // after the random-number work below
@@ -362,14 +379,27 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
 #endif
             // (3) own state; repair the stale row in g+1
             double thp[D];
-            load_row<D>(th, i, thp);
-            const double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
+            double lpi, dli;
+            if constexpr (ASYNC >= 2) { rows_async_wait(); own_staged_load<D>(s_own, s_sc, SWEEP_THREADS, thp, lpi, dli); }
+            else {
+#if ABCDEZ_SWEEP_EARLY_OWN >= 2
+#pragma unroll
+                for (int k = 0; k < D; ++k) thp[k] = thp_e[k];
+#else
+                load_row<D>(th, i, thp);
+#endif
+#if ABCDEZ_SWEEP_EARLY_OWN >= 1
+                lpi = lpi_e; dli = dli_e;
+#else
+                lpi = P.logpi[cur][i]; dli = P.delta[cur][i];
+#endif
+            }
             if (mv) {
                 store_row<D>(P.theta[nxt], i, thp);
                 copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
             }
             if (!err) {
-                if constexpr (ASYNC) { rows_async_wait(); de_proposal_staged<D>(s_rows + threadIdx.x, SWEEP_THREADS, g, thp); }
+                if constexpr (ASYNC >= 1) { rows_async_wait(); de_proposal_staged<D>(s_rows + threadIdx.x, SWEEP_THREADS, g, thp); }
                 else de_proposal<D>(th, a, b, g, thp);                     // :128
                 double xs[DISC ? D : 1];
                 const double* x = thp;
@@ -581,8 +611,8 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     bool all_normal = true, all_uniform = true;
     for (int k = 0; k < M::D; ++k) { all_normal = all_normal && pr.family[k] == ABCDEZ_NORMAL; all_uniform = all_uniform && pr.family[k] == ABCDEZ_UNIFORM; }
-    constexpr bool A = ABCDEZ_SWEEP_ASYNC_ROWS && M::D >= 2;
-    constexpr size_t sm = A ? sweep_async_smem<M::D>() : 0;
+    constexpr int A = M::D >= 2 ? ABCDEZ_SWEEP_ASYNC_ROWS : 0;
+    constexpr size_t sm = A ? sweep_async_smem<M::D>(A) : 0;
     if constexpr (sm > 48 * 1024) {                       // opt in once per instantiation (d > 12)
         static const bool once = [] {
             cudaFuncSetAttribute(smc_sweep_kernel<M, true, PK_GENERIC, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
