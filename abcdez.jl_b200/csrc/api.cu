@@ -868,8 +868,58 @@ extern "C" void abcdez_smc_opts_default(abcdez_smc_opts* o)
     o->sync_every = 1; o->fused_head = 1;
 }
 
+// ---- run state snapshots (the reference has no equivalent) -------------------------------
+// Everything abcdesmc! carries from one iteration to the next lives in the device control block, the history
+// buffer and the live generation of the particle arrays, so a snapshot taken between two iterations is those
+// bytes, and a restored run continues decision by decision like the uninterrupted one (the random streams are
+// counter based: particle id, sweep epoch and iteration number are part of the state).
+namespace {
+struct SmcStateHdr {
+    uint64_t magic; uint32_t version, d, ds, nb; int64_t N; int32_t hist_cap, model_id; uint64_t ctrl_bytes, total_bytes;
+    char model[32];
+};
+constexpr uint64_t SMC_STATE_MAGIC = 0x3174535a65644342ull;   // "BCdeZSt1"
+size_t smc_state_size(int64_t N, int ds, int nb, int hist_cap)
+{
+    size_t n = (size_t)N;
+    return sizeof(SmcStateHdr) + ((sizeof(Ctrl) + 7) & ~(size_t)7) + (size_t)hist_cap * 64 + n * ds * 8 + 2 * n * 8 + n * nb * 8 + n * 8
+           + ((n + 7) & ~(size_t)7);
+}
+}  // namespace
+
+extern "C" int64_t abcdez_smc_state_bytes(const abcdez_prior* prior, const abcdez_model* model, int64_t nparticles, int32_t hist_cap)
+{
+    if (!prior || !model || nparticles < 1) return -1;
+    const int d = model->ops->d;
+    return (int64_t)smc_state_size(nparticles, row_stride(d), model->ops->blob / 8, hist_cap > 0 ? hist_cap : 1);
+}
+
+static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                        const abcdez_smc_opts* o, abcdez_smc_result* res, const void* state_in, size_t state_in_bytes,
+                        void* state_out, size_t state_out_cap, size_t* state_out_bytes);
+
 extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
                               const abcdez_smc_opts* o, abcdez_smc_result* res)
+{
+    return smc_run_impl(ctx, prior, model, eps_target, o, res, nullptr, 0, nullptr, 0, nullptr);
+}
+
+extern "C" int abcdez_smc_run_state(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                                    const abcdez_smc_opts* o, abcdez_smc_result* res, const void* state_in,
+                                    int64_t state_in_bytes, void* state_out, int64_t state_out_cap, int64_t* state_out_bytes)
+{
+    CHECK_ARG(state_in_bytes >= 0 && state_out_cap >= 0, "abcdez_smc_run_state: negative size");
+    CHECK_ARG(!state_out || state_out_bytes, "abcdez_smc_run_state: state_out needs state_out_bytes");
+    size_t ob = 0;
+    int rc = smc_run_impl(ctx, prior, model, eps_target, o, res, state_in, (size_t)state_in_bytes, state_out, (size_t)state_out_cap,
+                          &ob);
+    if (state_out_bytes) *state_out_bytes = (int64_t)ob;
+    return rc;
+}
+
+static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                        const abcdez_smc_opts* o, abcdez_smc_result* res, const void* state_in, size_t state_in_bytes,
+                        void* state_out, size_t state_out_cap, size_t* state_out_bytes)
 {
     CHECK_ARG(ctx && prior && model && o && res, "abcdez_smc_run: NULL argument");
     // argument validation with the reference's messages, src/abcdez_smc.jl:223-235
@@ -913,6 +963,19 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     const int64_t N = hi - lo;
     int hist_cap = o->verboseout ? (res->hist_cap > 0 ? res->hist_cap : 0) : 0;
     int dev_hist = hist_cap > 0 ? hist_cap : 1;
+    if (state_in || state_out) {
+        if (shard) return fail(ABCDEZ_ERR_UNSUPPORTED, "abcdez_smc_run_state: run-state snapshots are single-GPU in this build");
+        const size_t need = smc_state_size(N, row_stride(prior->dev.d), model->ops->blob / 8, dev_hist);
+        if (state_out && state_out_cap < need) return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: state_out is smaller than abcdez_smc_state_bytes()");
+        if (state_in) {
+            const SmcStateHdr* h = (const SmcStateHdr*)state_in;
+            const bool ok = state_in_bytes >= sizeof(SmcStateHdr) && h->magic == SMC_STATE_MAGIC && h->version == 1 &&
+                            h->ctrl_bytes == sizeof(Ctrl) && h->N == N && (int)h->d == prior->dev.d &&
+                            (int)h->nb == model->ops->blob / 8 && strncmp(h->model, model->ops->name, sizeof(h->model) - 1) == 0 &&
+                            h->total_bytes == need && state_in_bytes >= need;
+            if (!ok) return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: state_in is not a snapshot of this model / prior / nparticles / history capacity");
+        }
+    }
     abcdez_pop* pop = nullptr;
     int rc = pop_create_impl(ctx, prior, model, N, lo, dev_hist, &pop, shard ? Ng : 0);
     if (rc) return rc;
@@ -927,7 +990,24 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     c->nsims_max = o->nsims_max; c->Kmcmc = o->Kmcmc; c->Ki = o->Kmcmc; c->Kmcmc_min = o->Kmcmc_min;
     c->kind = o->kernel; c->facc_stop = o->facc_stop; c->facc_min = o->facc_min; c->facc_tune = o->facc_tune;
     c->seed = o->seed; c->max_iters = o->max_iters; c->hist_cap = hist_cap;
-    pop->dev.keys = philox_keys(o->seed);
+    if (state_in) {
+        // the snapshot's control block, with this call's targets: eps_target, nsims_max, facc_stop and the iteration
+        // budget (max_iters counts the iterations of THIS call); every other option must be the snapshot's
+        const SmcStateHdr* h = (const SmcStateHdr*)state_in;
+        Ctrl s0; memcpy(&s0, (const char*)state_in + sizeof(SmcStateHdr), sizeof(Ctrl));
+        const bool same = s0.alpha == o->alpha && s0.ess_min == (double)Ng * o->delta_ess && s0.Kmcmc == o->Kmcmc &&
+                          s0.Kmcmc_min == o->Kmcmc_min && s0.kind == o->kernel && s0.facc_min == o->facc_min &&
+                          s0.facc_tune == o->facc_tune && h->hist_cap == dev_hist && s0.hist_cap == hist_cap;
+        if (!same) { abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: options differ from the snapshot's (only eps_target, nsims_max, facc_stop and max_iters may change)"); }
+        *c = s0;
+        c->eps_target = eps_target; c->nsims_max = o->nsims_max; c->facc_stop = o->facc_stop;
+        c->max_iters = o->max_iters > 0 ? c->iters + o->max_iters : 0;
+        c->status = 0;
+        const bool no_alive = c->n_alive_g == 0;
+        c->stop = (no_alive || c->eps <= c->eps_target || c->nsims_total >= c->nsims_max || c->facc < c->facc_stop || c->err) ? 1 : 0;   // :375-376
+        if (no_alive) c->status = ABCDEZ_ERR_NO_ALIVE;
+    }
+    pop->dev.keys = philox_keys(c->seed);
     rc = push_ctrl(pop);
     std::vector<cudaEvent_t>& evs = ctx->ev_pool;
     size_t nev = 0;
@@ -941,8 +1021,24 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
     if (rc) goto done;
     RUN_CU(cudaEventCreate(&e_init0)); RUN_CU(cudaEventCreate(&e_loop0)); RUN_CU(cudaEventCreate(&e_loop1));
     RUN_CU(cudaEventRecord(e_init0, st));
-    pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :242-252
-    launches += 1 + launch_begin_run(st, pop->dev);                          // :255-292
+    if (state_in) {
+        // restore: control block (with this call's targets), history, live generation; the other generation is stale
+        const char* p = (const char*)state_in + sizeof(SmcStateHdr) + ((sizeof(Ctrl) + 7) & ~(size_t)7);
+        const size_t n = (size_t)N; const int cur = c->cur;
+        RUN_CU(cudaMemcpyAsync(pop->dev.hist, p, (size_t)dev_hist * 64, cudaMemcpyHostToDevice, st)); p += (size_t)dev_hist * 64;
+        RUN_CU(cudaMemcpyAsync(pop->dev.theta[cur], p, n * pop->DS * 8, cudaMemcpyHostToDevice, st)); p += n * pop->DS * 8;
+        RUN_CU(cudaMemcpyAsync(pop->dev.logpi[cur], p, n * 8, cudaMemcpyHostToDevice, st)); p += n * 8;
+        RUN_CU(cudaMemcpyAsync(pop->dev.delta[cur], p, n * 8, cudaMemcpyHostToDevice, st)); p += n * 8;
+        if (pop->NB) RUN_CU(cudaMemcpyAsync(pop->dev.blob[cur], p, n * pop->NB * 8, cudaMemcpyHostToDevice, st));
+        p += n * pop->NB * 8;
+        RUN_CU(cudaMemcpyAsync(pop->dev.W, p, n * 8, cudaMemcpyHostToDevice, st)); p += n * 8;
+        RUN_CU(cudaMemcpyAsync(pop->dev.alive, p, n, cudaMemcpyHostToDevice, st));
+        RUN_CU(cudaMemsetAsync(pop->dev.moved, 1, n, st));
+        host_iters = c->iters;
+    } else {
+        pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);     // :242-252
+        launches += 1 + launch_begin_run(st, pop->dev);                      // :255-292
+    }
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
         host_iters++;
@@ -971,6 +1067,31 @@ extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const 
         if (host_iters > 10000000) break;
     }
     RUN_CU(cudaEventRecord(e_loop1, st));
+    if (state_out) {
+        // snapshot between two iterations (before the final extrema pass touches the accumulators)
+        RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        RUN_CU(cudaStreamSynchronize(st));
+        const size_t n = (size_t)N; const int cur = c->cur;
+        SmcStateHdr h; memset(&h, 0, sizeof h);
+        h.magic = SMC_STATE_MAGIC; h.version = 1; h.d = (uint32_t)pop->D; h.ds = (uint32_t)pop->DS; h.nb = (uint32_t)pop->NB;
+        h.N = N; h.hist_cap = dev_hist; h.model_id = model->id; h.ctrl_bytes = sizeof(Ctrl);
+        h.total_bytes = smc_state_size(N, pop->DS, pop->NB, dev_hist);
+        strncpy(h.model, model->ops->name, sizeof(h.model) - 1);
+        char* p = (char*)state_out;
+        memcpy(p, &h, sizeof h); p += sizeof h;
+        memset(p, 0, (sizeof(Ctrl) + 7) & ~(size_t)7); memcpy(p, c, sizeof(Ctrl)); p += (sizeof(Ctrl) + 7) & ~(size_t)7;
+        RUN_CU(cudaMemcpyAsync(p, pop->dev.hist, (size_t)dev_hist * 64, cudaMemcpyDeviceToHost, st)); p += (size_t)dev_hist * 64;
+        RUN_CU(cudaMemcpyAsync(p, pop->dev.theta[cur], n * pop->DS * 8, cudaMemcpyDeviceToHost, st)); p += n * pop->DS * 8;
+        RUN_CU(cudaMemcpyAsync(p, pop->dev.logpi[cur], n * 8, cudaMemcpyDeviceToHost, st)); p += n * 8;
+        RUN_CU(cudaMemcpyAsync(p, pop->dev.delta[cur], n * 8, cudaMemcpyDeviceToHost, st)); p += n * 8;
+        if (pop->NB) RUN_CU(cudaMemcpyAsync(p, pop->dev.blob[cur], n * pop->NB * 8, cudaMemcpyDeviceToHost, st));
+        p += n * pop->NB * 8;
+        RUN_CU(cudaMemcpyAsync(p, pop->dev.W, n * 8, cudaMemcpyDeviceToHost, st)); p += n * 8;
+        memset(p, 0, (n + 7) & ~(size_t)7);
+        RUN_CU(cudaMemcpyAsync(p, pop->dev.alive, n, cudaMemcpyDeviceToHost, st));
+        RUN_CU(cudaStreamSynchronize(st));
+        *state_out_bytes = h.total_bytes;
+    }
     launches += launch_minmax(st, pop->dev);      // extrema(delta) of the final generation -> last history record
     RUN_CU(cudaGetLastError());
     RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));

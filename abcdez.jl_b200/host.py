@@ -74,7 +74,8 @@ EXPORTS = [
     "abcdez_prior_create", "abcdez_prior_destroy", "abcdez_prior_sample", "abcdez_prior_logpdf", "abcdez_prior_push",
     "abcdez_model_count", "abcdez_model_name", "abcdez_model_lookup", "abcdez_model_info", "abcdez_model_bind",
     "abcdez_model_destroy", "abcdez_model_compile", "abcdez_simulate", "abcdez_kernel_pdf", "abcdez_kernel_logpdf",
-    "abcdez_smc_opts_default", "abcdez_smc_run", "abcdez_mc_opts_default", "abcdez_mc_run",
+    "abcdez_smc_opts_default", "abcdez_smc_run", "abcdez_smc_state_bytes", "abcdez_smc_run_state",
+    "abcdez_mc_opts_default", "abcdez_mc_run",
     "abcdez_pop_create", "abcdez_pop_destroy", "abcdez_pop_upload", "abcdez_pop_download", "abcdez_pop_set",
     "abcdez_pop_init", "abcdez_pop_smc_sweep", "abcdez_pop_mc_sweep", "abcdez_pop_eps_quantile",
     "abcdez_pop_reweight", "abcdez_pop_head", "abcdez_pop_resample", "abcdez_wsample_stratified", "abcdez_pop_last_timing",
@@ -481,6 +482,7 @@ class SMCResult:
     nsims: int = 0
     status: int = 0
     stats: dict = field(default_factory=dict)
+    state: Optional[bytes] = None          # run-state snapshot (return_state=True), see abcdesmc
 
     ϵ = property(lambda s: s.eps)
     ϵs = property(lambda s: s.eps_hist)
@@ -528,11 +530,15 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
              facc_min=0.0, facc_tune=0.975, verbose: bool = True, verboseout: bool = True, rng=None,
              parallel: bool = False, ctx: Optional[Context] = None, max_iters: int = 0, exact_scan: bool = False,
              profile: bool = False, sync_every: int = 1, hist_cap: int = 8192, fused_head: bool = True,
-             **greek) -> SMCResult:
+             state=None, return_state: bool = False, **greek) -> SMCResult:
     """`abcdesmc!(prior, dist!, ϵ_target, varexternal; kwargs...)`, src/abcdez_smc.jl:215-394.
 
     `dist` is a :class:`Model`; `varexternal` is accepted for signature compatibility (the device
     functors keep their scratch in registers); `parallel` is ignored (the GPU is always parallel).
+
+    Run-state snapshots (not in the reference): `return_state=True` attaches the state the run ended in
+    (`result.state`, bytes; typically after `max_iters` iterations) and `state=<bytes>` continues from one --
+    with this call's `eps_target`, `nsims_max`, `facc_stop`, `max_iters` and the snapshot's seed.
     """
     kw = _greek(dict(greek), {"α": "alpha", "δess": "delta_ess"})
     alpha = kw.pop("alpha", alpha); delta_ess = kw.pop("delta_ess", delta_ess)
@@ -565,8 +571,24 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     r.hist_cap = hist_cap if verboseout else 0
     r.h_eps, r.h_dmin, r.h_dmax, r.h_logZ = _p(h["eps"]), _p(h["dmin"]), _p(h["dmax"]), _p(h["logZ"])
     r.h_ess, r.h_facc, r.h_gamma0, r.h_Kmcmc = _p(h["ess"]), _p(h["facc"]), _p(h["gamma0"]), _p(hK)
-    _check(lib().abcdez_smc_run(ctx._h, fprior.handle(ctx), dist.handle(ctx), C.c_double(eps_target), C.byref(o),
-                                C.byref(r)))
+    state_out = None
+    if state is None and not return_state:
+        _check(lib().abcdez_smc_run(ctx._h, fprior.handle(ctx), dist.handle(ctx), C.c_double(eps_target), C.byref(o),
+                                    C.byref(r)))
+    else:
+        L = lib()
+        L.abcdez_smc_state_bytes.restype = C.c_int64
+        need = L.abcdez_smc_state_bytes(fprior.handle(ctx), dist.handle(ctx), C.c_int64(N), C.c_int32(r.hist_cap))
+        sin = np.frombuffer(state, dtype=np.uint8) if state is not None else None
+        sout = np.empty(need, dtype=np.uint8) if return_state else None
+        nout = C.c_int64(0)
+        _check(L.abcdez_smc_run_state(ctx._h, fprior.handle(ctx), dist.handle(ctx), C.c_double(eps_target), C.byref(o),
+                                      C.byref(r), _p(sin) if sin is not None else None,
+                                      C.c_int64(sin.size if sin is not None else 0),
+                                      _p(sout) if sout is not None else None, C.c_int64(need if return_state else 0),
+                                      C.byref(nout)))
+        if return_state:
+            state_out = sout[:nout.value].tobytes()
     if r.status == ERR_NO_ALIVE and verbose:
         print("Warning: No alive particles")                                 # src/abcdez_smc.jl:375
     stats = dict(n_resamples=r.n_resamples, n_sweeps=r.n_sweeps, n_launches=r.n_launches, sweep_ms=r.sweep_ms,
@@ -575,6 +597,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     Pout = P[:, 0] if scalar else P
     out = SMCResult(Pout, W, Cc, r.eps, r.logZ, _blob_view(bl, B), iters=r.iters, nsims=r.nsims, status=r.status,
                     stats=stats)
+    out.state = state_out
     if verboseout:
         n = r.hist_len
         out.eps_hist = h["eps"][:n]; out.ranges_eps = np.stack([h["dmin"][:n], h["dmax"][:n]], axis=1)

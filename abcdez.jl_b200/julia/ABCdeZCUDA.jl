@@ -203,7 +203,10 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
                    nparticles::Int=100, α=0.95, δess=0.5, nsims_max::Int=10^7, Kmcmc::Int=3, Kmcmc_min=1.0,
                    ABCk=IndicatorStrict0toϵ, facc_stop=0.0, facc_min=0.0, facc_tune=0.975,
                    verbose::Bool=true, verboseout::Bool=true, rng=Random.default_rng(), parallel::Bool=false,
-                   ctx::Context=default_context(), hist_cap::Int=8192)
+                   ctx::Context=default_context(), hist_cap::Int=8192,
+                   max_iters::Int=0, state::Union{Nothing,Vector{UInt8}}=nothing, return_state::Bool=false)
+    # max_iters / state / return_state are not in the reference: run-state snapshots (abcdez_smc_run_state); the
+    # returned NamedTuple gains a `state` field when return_state=true
     Kmcmc_min > facc_min || @warn("Kmcmc_min should be larger than facc_min")         # src/abcdez_smc.jl:232
     ph = prior_handle(ctx, prior)
     mh, d, B = model_handle(ctx, dist!)
@@ -211,26 +214,40 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     ccall((:abcdez_smc_opts_default, LIB), Cvoid, (Ref{SmcOpts},), o)
     o.nparticles = nparticles; o.alpha = α; o.delta_ess = δess; o.nsims_max = nsims_max; o.Kmcmc = Kmcmc
     o.Kmcmc_min = Kmcmc_min; o.kernel = kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
-    o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout
+    o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout; o.max_iters = max_iters
     N = local_count(ctx, nparticles)                   # sharded: the rows of this rank's block
     P = Matrix{Float64}(undef, d, N); Wns = Vector{Float64}(undef, N); C = Vector{Float64}(undef, N)
     bl = zeros(UInt8, max(B, 1), N)
     h = [zeros(Float64, hist_cap) for _ in 1:7]; hK = zeros(Int32, hist_cap)
     r = SmcResult()
+    state_out = nothing
     GC.@preserve P Wns C bl h hK begin
         r.P = pointer(P); r.Wns = pointer(Wns); r.C = pointer(C); r.blobs = pointer(bl)
         r.hist_cap = verboseout ? hist_cap : 0
         r.h_eps, r.h_dmin, r.h_dmax, r.h_logZ, r.h_ess, r.h_facc, r.h_gamma0 = pointer.(h)
         r.h_Kmcmc = pointer(hK)
         # argument errors come back with the reference's messages (src/abcdez_smc.jl:223-235)
-        check(ccall((:abcdez_smc_run, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{SmcOpts}, Ref{SmcResult}),
-                    ctx.h, ph, mh, ϵ_target, o, r))
+        if state === nothing && !return_state
+            check(ccall((:abcdez_smc_run, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{SmcOpts}, Ref{SmcResult}),
+                        ctx.h, ph, mh, ϵ_target, o, r))
+        else
+            need = ccall((:abcdez_smc_state_bytes, LIB), Int64, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32), ph, mh, N, r.hist_cap)
+            sout = return_state ? Vector{UInt8}(undef, need) : UInt8[]
+            sin = state === nothing ? UInt8[] : state
+            nout = Ref{Int64}(0)
+            GC.@preserve sin sout check(ccall((:abcdez_smc_run_state, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{SmcOpts}, Ref{SmcResult}, Ptr{UInt8}, Int64, Ptr{UInt8}, Int64, Ref{Int64}),
+                ctx.h, ph, mh, ϵ_target, o, r, state === nothing ? C_NULL : pointer(sin), length(sin),
+                return_state ? pointer(sout) : C_NULL, length(sout), nout))
+            return_state && resize!(sout, nout[])
+            state_out = return_state ? sout : nothing
+        end
     end
     ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph); ccall((:abcdez_model_destroy, LIB), Cint, (Ptr{Cvoid},), mh)
     r.status == ABCDEZ_ERR_NO_ALIVE && @warn("No alive particles")                      # src/abcdez_smc.jl:375
     verbose && (@info "Final run:" iteration = r.iters nsim = r.nsims ϵ = r.eps logZ = r.logZ)
     θs = particles(prior, P); blobs = blobs_out(bl, B)
-    if verboseout                                                                       # src/abcdez_smc.jl:388-393
+    out = if verboseout                                                                 # src/abcdez_smc.jl:388-393
         n = r.hist_len
         (P = θs, Wns = Wns, C = C, ϵ = r.eps, logZ = r.logZ, blobs = blobs,
          ϵs = h[1][1:n], ranges_ϵ = collect(zip(h[2][1:n], h[3][1:n])), logZs = h[4][1:n], esss = h[5][1:n],
@@ -238,6 +255,7 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     else
         (P = θs, Wns = Wns, C = C, ϵ = r.eps, logZ = r.logZ, blobs = blobs)
     end
+    return_state ? merge(out, (state = state_out,)) : out
 end
 
 """

@@ -193,6 +193,18 @@ void abcdez_smc_opts_default(abcdez_smc_opts* o);
 int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
                    const abcdez_smc_opts* opts, abcdez_smc_result* res);
 
+/* Run-state snapshots (no equivalent in the reference): abcdez_smc_run that can stop between two
+ * iterations and continue later, decision by decision like the uninterrupted run.  state_out (host, capacity >=
+ * abcdez_smc_state_bytes(prior, model, nparticles, result.hist_cap or 1)) receives the state the run ended in --
+ * typically after opts.max_iters iterations; state_in restores one instead of drawing from the prior.  On a
+ * restored run eps_target, nsims_max, facc_stop and max_iters (iterations of THIS call) are taken from the call,
+ * the seed from the snapshot, and every other option must equal the snapshot's; histories cover the whole run.
+ * Either pointer may be NULL (both NULL == abcdez_smc_run).  Single-GPU contexts only. */
+int64_t abcdez_smc_state_bytes(const abcdez_prior* prior, const abcdez_model* model, int64_t nparticles, int32_t hist_cap);
+int abcdez_smc_run_state(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                         const abcdez_smc_opts* opts, abcdez_smc_result* res, const void* state_in, int64_t state_in_bytes,
+                         void* state_out, int64_t state_out_cap, int64_t* state_out_bytes);
+
 /* kwargs of abcdemc!, src/abcdez_mc.jl:102-104 */
 typedef struct {
     int64_t nparticles;      /* 50 */

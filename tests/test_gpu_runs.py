@@ -141,6 +141,28 @@ def test_evidence_tight_at_large_N(A, gpu_ctx):
     assert abs(x.mean() - 30 / 11) < 0.01 and abs(x.var() - 10 / 11) < 0.05
 
 
+def test_config2_logZ_against_analytic(A, gpu_ctx):
+    """BASELINE.json configs[1]: 10-d correlated Gaussian model, 10^6 particles, logZ vs the analytic evidence.
+    Z = P(||Y - y_obs|| < eps), Y ~ N(0, Sigma + sigma0^2 I), evaluated by integrating the Gaussian density over the
+    eps-ball (4*10^6 uniform points in the ball, relative standard error 3e-5): log Z = -16.45296.  Run-to-run
+    sd(logZ) at N = 10^6 is 0.04 (bench.py logZ_sd), so 0.2 is a five-sigma band.  Posterior mean for eps -> 0:
+    sigma0^2 (Sigma + sigma0^2 I)^-1 y_obs; after ~320 iterations of 5 % selection with three DE-MCMC sweeps each the
+    particles are strongly correlated (that is the algorithm, the oracle does the same), so the mean of one run is
+    only good to a few tenths of a posterior standard deviation (~0.9)."""
+    d, rho, s0 = 10, 0.5, 2.0
+    y = np.array([0.5 * math.sin(1.0 + k) for k in range(d)])
+    pr = A.Factored(*[A.host.Normal(0.0, s0)] * d)
+    r = A.abcdesmc(pr, A.Model("gauss_corr10", list(y) + [rho]), 1.0, None, nparticles=1_000_000, nsims_max=10**11,
+                   verbose=False, rng=20261017)
+    assert r.eps == 1.0
+    assert abs(r.logZ - (-16.45296)) < 0.2
+    S = np.array([[rho ** abs(i - j) for j in range(d)] for i in range(d)]) + s0 ** 2 * np.eye(d)
+    want = s0 ** 2 * np.linalg.solve(S, y)
+    P = np.asarray(r.P)[np.asarray(r.Wns) > 0]
+    assert np.max(np.abs(P.mean(axis=0) - want)) < 0.4
+    assert 0.5 < P.std(axis=0).mean() < 1.2
+
+
 def test_bayes_factor_uniform_priors(A, gpu_ctx):
     """test/runtests.jl:220-266."""
     m = A.Model("gauss1d", [3.0, 1.0])
@@ -325,3 +347,47 @@ def test_gk_posterior_recovers_parameters(A, gpu_ctx):
     assert abs(mean[3] - GK_TRUE[3]) < 0.3
     with pytest.raises(A.ABCdeZError):
         A.abcdemc(prior, A.Model("gk", data), 1.0, None, nparticles=100, generations=2, verbose=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# run-state snapshots (abcdez_smc_run_state): stop between two iterations, continue later
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,eps_target,N,cut", [("gauss1d", 0.3, 2000, 7), ("gauss_corr10", 2.5, 20000, 25),
+                                                  ("birth_death", 3.0, 1500, 5), ("gauss1d_blob", 0.3, 1000, 1)])
+def test_run_state_resume_is_the_uninterrupted_run(A, gpu_ctx, name, eps_target, N, cut):
+    spec, data = MODEL_CASES[name]
+    pr, m = to_prior(A, spec), A.Model(name, data)
+    kw = dict(nparticles=N, nsims_max=10**9, verbose=False, rng=77)
+    full = A.abcdesmc(pr, m, eps_target, None, **kw)
+    assert full.iters >= 5
+    cut = max(1, min(cut, full.iters - 3))
+    part = A.abcdesmc(pr, m, eps_target, None, max_iters=cut, return_state=True, **kw)
+    assert part.iters == cut and part.state is not None and len(part.state) > 8 * N
+    assert np.array_equal(part.eps_hist, full.eps_hist[:cut + 1])
+    mid = A.abcdesmc(pr, m, eps_target, None, state=part.state, max_iters=2, return_state=True, **kw)
+    assert mid.iters == cut + 2
+    rest = A.abcdesmc(pr, m, eps_target, None, state=mid.state, **kw)
+    assert (rest.iters, rest.nsims, rest.eps, rest.logZ) == (full.iters, full.nsims, full.eps, full.logZ)
+    for a, b in ((rest.P, full.P), (rest.Wns, full.Wns), (rest.C, full.C), (rest.eps_hist, full.eps_hist),
+                 (rest.logZs, full.logZs), (rest.esss, full.esss), (rest.faccs, full.faccs), (rest.Kmcmcs, full.Kmcmcs),
+                 (rest.ranges_eps, full.ranges_eps)):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+    if m.blob_bytes:
+        assert np.array_equal(rest.blobs, full.blobs)
+
+
+def test_run_state_continue_to_a_smaller_target_and_errors(A, gpu_ctx):
+    pr, m = A.host.Normal(0, SQ10), A.Model("gauss1d", [3.0, 1.0])
+    kw = dict(nparticles=3000, verbose=False, rng=5)
+    direct = A.abcdesmc(pr, m, 0.3, None, **kw)
+    first = A.abcdesmc(pr, m, 1.0, None, return_state=True, **kw)
+    assert first.eps == 1.0 and first.iters < direct.iters
+    more = A.abcdesmc(pr, m, 0.3, None, state=first.state, **kw)          # same schedule below eps = 1, clamped later
+    assert more.eps == 0.3 and more.iters >= first.iters
+    assert abs(more.logZ - direct.logZ) < 0.25
+    with pytest.raises(A.ABCdeZError):                                     # not a snapshot of this population size
+        A.abcdesmc(pr, m, 0.3, None, state=first.state, nparticles=2999, verbose=False, rng=5)
+    with pytest.raises(A.ABCdeZError):                                     # options other than the targets must match
+        A.abcdesmc(pr, m, 0.3, None, state=first.state, alpha=0.9, **kw)
+    with pytest.raises(A.ABCdeZError):
+        A.abcdesmc(pr, m, 0.3, None, state=first.state[:100], **kw)
