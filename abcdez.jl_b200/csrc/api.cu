@@ -955,8 +955,6 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     int64_t lo = 0, hi = Ng;
     if (shard) {
         abcdez_shard_range(Ng, ctx->rank, ctx->world, &lo, &hi);
-        if (!abck_is_indicator(o->kernel))
-            return fail(ABCDEZ_ERR_UNSUPPORTED, "sharded abcdesmc!: only the indicator kernels are supported across GPUs in this build");
         CHECK_ARG(Ng >= 4 * (int64_t)ctx->world, "sharded abcdesmc!: need at least 4 particles per rank");
         CHECK_ARG(Ng < (int64_t)0x7fffffff, "sharded abcdesmc!: nparticles must be below 2^31");
     }

@@ -474,6 +474,125 @@ resample_uniform_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
     }
 }
 
+__device__ __forceinline__ uint32_t search_cumsum(const double* __restrict__ cs, uint32_t N, double r);
+
+// ---- sharded runs, general weights (Epanechnikov kernels) ------------------------------------------------------
+// wsample_stratified! (src/abcdez_smc.jl:15-56) walks ONE running sum over the whole population, so rank r's
+// cumulative weights must continue where rank r-1's end.  Exact mode (2): a chain of `world` exchange rounds --
+// in round q rank q runs the reference's sequential FP64 sum over its block, starting from the end value of rank
+// q-1, and posts its own end value; every rank leaves with all end values (Ctrl::rank_end).  Parallel mode (1):
+// every rank scans its block in parallel, the block totals are exchanged once and added up in rank order to give
+// the carry-in of every block (rounds like the single-GPU parallel scan: differs from the sequential sum in the
+// last bits).  Then every rank resolves its own output strata: owner = first rank whose end value
+// reaches r, source = first particle of that rank whose cumulative weight reaches r (binary search in the owner's
+// HBM over NVLink), row gathered from the owner like in the uniform-weight kernel above.
+__global__ void __launch_bounds__(BK_THREADS) scan_sequential_sharded_kernel(const __grid_constant__ PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ double buf[2048];
+    const uint32_t N = P.N;
+    double carry = 0.0;                                   // thread 0: end value of the previous rank
+    for (int q = 0; q < P.x.world; ++q) {
+        double s = carry;
+        if (q == P.x.rank) {
+            for (size_t base = 0; base < N; base += 2048) {
+                for (int t = threadIdx.x; t < 2048; t += blockDim.x) buf[t] = (base + t < N) ? P.W[base + t] : 0.0;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int lim = (N - base) < 2048 ? (int)(N - base) : 2048;
+                    for (int t = 0; t < lim; ++t) { s = __dadd_rn(s, buf[t]); buf[t] = s; }
+                }
+                __syncthreads();
+                for (int t = threadIdx.x; t < 2048; t += blockDim.x) if (base + t < N) P.cumsum[base + t] = buf[t];
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            unsigned long long rec[1] = { (unsigned long long)__double_as_longlong(s) };
+            __threadfence_system();                       // this rank's cumsum is visible to its peers before the flag
+            const unsigned slot = xchg_small(P.x, c, rec, 1);
+            carry = __longlong_as_double((long long)xchg_word(P.x, slot, q, 0));
+            c->rank_end[q] = carry;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seqtab_build(&P.tabs[1], 1.0 / (double)P.Ng, (unsigned long long)P.Ng);
+}
+
+// parallel mode, step 2 of 3 (after scan_tile_sums_pop_kernel, before scan_apply_pop_kernel): block total ->
+// exchange -> carry-in -> exclusive tile offsets
+__global__ void scan_tile_offsets_sharded_kernel(const __grid_constant__ PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double tot = 0.0;
+        for (unsigned b = 0; b < P.ntiles; ++b) tot += P.partial[b];
+        unsigned long long rec[1] = { (unsigned long long)__double_as_longlong(tot) };
+        const unsigned slot = xchg_small(P.x, c, rec, 1);
+        double s = 0.0;
+        for (int q = 0; q < P.x.rank; ++q) s += __longlong_as_double((long long)xchg_word(P.x, slot, q, 0));
+        for (unsigned b = 0; b < P.ntiles; ++b) { double t = P.partial[b]; P.partial[b] = s; s += t; }
+        seqtab_build(&P.tabs[1], 1.0 / (double)P.Ng, (unsigned long long)P.Ng);
+    }
+}
+
+// parallel mode, after scan_apply_pop_kernel: the end values of all blocks; also the barrier "every rank's cumulative
+// weights and particle rows are final"
+__global__ void scan_ends_sharded_kernel(const __grid_constant__ PopDev P, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    unsigned long long rec[1] = { (unsigned long long)__double_as_longlong(P.cumsum[P.N - 1]) };
+    __threadfence_system();
+    const unsigned slot = xchg_small(P.x, c, rec, 1);
+    for (int q = 0; q < P.x.world; ++q) c->rank_end[q] = __longlong_as_double((long long)xchg_word(P.x, slot, q, 0));
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+resample_general_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB, uint32_t epoch, int force)
+{
+    Ctrl* c = P.ctrl;
+    if (c->stop || !(c->do_resample || force)) return;
+    __shared__ double s_end[XCHG_MAXR];
+    if (threadIdx.x < XCHG_MAXR) s_end[threadIdx.x] = (int)threadIdx.x < P.x.world ? c->rank_end[threadIdx.x] : 0.0;
+    __syncthreads();
+    const int cur = c->cur;
+    const uint32_t N = P.N;
+    const double sval = 1.0 / (double)P.Ng;                                  // :34
+    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si < N) {
+        const uint32_t sg = P.id0 + si;                                      // global stratum
+        double u, u2;
+        Stream rs(P.keys, sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
+        const double r = stratum_draw(&P.tabs[1], sval, sg, u);
+        int q = 0; uint32_t src = 0u;                                        // r <= 0: global particle 0 (the "i = 0" quirk, clamped)
+        if (r > 0.0) {
+            while (q < P.x.world - 1 && s_end[q] < r) ++q;                   // first block whose end value reaches r
+            src = search_cumsum(P.peers->p[q].cumsum, P.peers->p[q].N, r);   // (r beyond the total: the last particle)
+        }
+        const PeerPop& pp = P.peers->p[q];
+        {
+            const double* s = pp.theta[cur] + (size_t)src * DS;
+            double* d = P.theta[cur ^ 1] + (size_t)si * DS;
+            if (DS & 1) { for (int e = 0; e < DS; ++e) d[e] = s[e]; }
+            else { for (int e = 0; e < DS; e += 2) *reinterpret_cast<double2*>(d + e) = *reinterpret_cast<const double2*>(s + e); }
+            P.logpi[cur ^ 1][si] = pp.logpi[cur][src];
+            P.delta[cur ^ 1][si] = pp.delta[cur][src];
+            for (int e = 0; e < NB; ++e) P.blob[cur ^ 1][(size_t)si * NB + e] = pp.blob[cur][(size_t)src * NB + e];
+        }
+        P.inds[si] = (int32_t)(pp.id0 + src);                                // global source index
+        P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1;                    // :102-103 (peers read cumsum and the old rows, not these)
+    }
+    if (last_block(&c->acc.ticket[3], gridDim.x)) {
+        if (threadIdx.x == 0) {
+            xchg_small(P.x, c, nullptr, 0);      // nobody reads this rank's old generation or cumulative weights any more
+            ctrl_after_resample(P, c);
+        }
+    }
+}
+
 // general weights (Epanechnikov kernels): inclusive scan of W, then a search per stratum.
 // mode 1: parallel three-phase scan (tile sums, tile offsets, tile rescan) -- rounds differently
 // from the reference's sequential sum, documented in DESIGN.md; mode 2: sequential scan, exact.
@@ -655,10 +774,23 @@ int launch_resample(cudaStream_t st, const PopDev& P, int DS, int NB, const doub
                     int mode, int force)
 {
     unsigned gt = tiles_for(P.N), gp = (unsigned)((P.N + BK_THREADS - 1) / BK_THREADS);
-    if (P.x.world > 1) {             // sharded: indicator kernels only (checked by abcdez_smc_run)
-        peer_barrier_kernel<<<1, 1, 0, st>>>(P, force);
-        resample_uniform_sharded_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, epoch, force);
-        return 2;
+    if (P.x.world > 1) {             // sharded: global resampling over peer memory
+        if (mode == 0) {
+            peer_barrier_kernel<<<1, 1, 0, st>>>(P, force);
+            resample_uniform_sharded_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, epoch, force);
+            return 2;
+        }
+        int n = 0;
+        if (mode == 2) { scan_sequential_sharded_kernel<<<1, BK_THREADS, 0, st>>>(P, force); n = 1; }
+        else {
+            scan_tile_sums_pop_kernel<<<gt, BK_THREADS, 0, st>>>(P, force);
+            scan_tile_offsets_sharded_kernel<<<1, 32, 0, st>>>(P, force);
+            scan_apply_pop_kernel<<<gt, BK_THREADS, 0, st>>>(P, force);
+            scan_ends_sharded_kernel<<<1, 1, 0, st>>>(P, force);
+            n = 4;
+        }
+        resample_general_sharded_kernel<<<gp, BK_THREADS, 0, st>>>(P, DS, NB, epoch, force);
+        return n + 1;
     }
     if (mode == 0) {
         if (force) build_tabs_kernel<<<1, 1, 0, st>>>(P);

@@ -207,7 +207,7 @@ int comm_shared_slab(Comm* cm, cudaStream_t st, size_t need, char** slab)
 // Collective, at the start of a sharded run: publish where this rank's arrays live inside its slab, build
 // the device PeerTable, and reset the mailbox ring (zeroed flags, sequence 0) between two barriers so
 // that a run aborted on one rank cannot desynchronise the next one.
-struct SlabLayout { unsigned long long theta[2], logpi[2], delta[2], blob[2], alive_list; unsigned N, id0; };
+struct SlabLayout { unsigned long long theta[2], logpi[2], delta[2], blob[2], alive_list, cumsum; unsigned N, id0; };
 
 int comm_begin_run(Comm* cm, cudaStream_t st, const PopDev& P, XchgDev* x, const PeerTable** d_peers)
 {
@@ -217,7 +217,7 @@ int comm_begin_run(Comm* cm, cudaStream_t st, const PopDev& P, XchgDev* x, const
         mine.theta[g] = off(P.theta[g]); mine.logpi[g] = off(P.logpi[g]); mine.delta[g] = off(P.delta[g]);
         mine.blob[g] = off(P.blob[g]);
     }
-    mine.alive_list = off(P.alive_list); mine.N = P.N; mine.id0 = P.id0;
+    mine.alive_list = off(P.alive_list); mine.cumsum = off(P.cumsum); mine.N = P.N; mine.id0 = P.id0;
     int rc = comm_allgather(cm, st, &mine, all, sizeof mine);      // also a barrier: everyone left the previous run
     if (rc) return rc;
     PeerTable t; memset(&t, 0, sizeof t);
@@ -228,6 +228,7 @@ int comm_begin_run(Comm* cm, cudaStream_t st, const PopDev& P, XchgDev* x, const
             t.p[q].delta[g] = (const double*)(base + all[q].delta[g]); t.p[q].blob[g] = (const double*)(base + all[q].blob[g]);
         }
         t.p[q].alive_list = (const uint32_t*)(base + all[q].alive_list);
+        t.p[q].cumsum = (const double*)(base + all[q].cumsum);
         t.p[q].N = all[q].N; t.p[q].id0 = all[q].id0;
     }
     CM_CU(cudaMemcpyAsync(cm->d_peers, &t, sizeof t, cudaMemcpyHostToDevice, st));

@@ -63,6 +63,7 @@ struct XchgDev {
 struct PeerPop {
     const double* theta[2]; const double* logpi[2]; const double* delta[2]; const double* blob[2];
     const uint32_t* alive_list;
+    const double* cumsum;         // inclusive GLOBAL cumulative weights of the rank's block (general-weight resampling)
     uint32_t N, id0;
 };
 struct PeerTable { PeerPop p[XCHG_MAXR]; };

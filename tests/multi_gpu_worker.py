@@ -127,13 +127,27 @@ def gpu_main():
         np.testing.assert_allclose(full.C, want.C, rtol=1e-9, atol=1e-12)
         if rank == 0:
             print(f"sharded abcdemc! {name} N={N} world={world}: nsims {got.nsims} reached {got.reached_eps} == oracle(islands={world})")
-    # an unsupported configuration fails identically (and cleanly) on every rank
-    try:
-        A.abcdesmc(A.host.Normal(0, 1), A.Model("gauss1d", [3.0, 1.0]), 0.3, None, nparticles=1000, rng=1, verbose=False,
-                   ctx=ctx, ABCk="epa")
-        raise AssertionError("expected UNSUPPORTED")
-    except A.ABCdeZError as e:
-        assert e.code == A.host.ERR_UNSUPPORTED
+    # Epanechnikov kernels (general weights): the cumulative weights continue from rank to rank.  exact_scan: the
+    # reference's sequential sum as a chain over the ranks == oracle(islands); default: parallel scans + one exchange
+    for name, spec, data, eps_t, N, seed, kind in [("gauss1d", [("normal", 0.0, math.sqrt(10.0))], [3.0, 1.0], 0.3, 3001, 21, "epa"),
+                                                   ("twod", [("normal", 0.0, 5.0)] * 2, [], 0.1, 6000, 23, "epa_strict")]:
+        prior = A.Factored(*[fams[s_[0]](*s_[1:]) for s_ in spec])
+        got = A.abcdesmc(prior, A.Model(name, data), eps_t, None, nparticles=N, rng=seed, verbose=False, ctx=ctx, ABCk=kind,
+                         nsims_max=10**9, exact_scan=True)
+        full = A.dist.gather_result(got)
+        want = O.smc_run(spec, name, data, eps_t, nparticles=N, seed=seed, kind=kind, nsims_max=10**9, islands=world)
+        assert (got.iters, got.nsims) == (want.iters, want.nsims), (name, kind, got.iters, got.nsims, want.iters, want.nsims)
+        assert got.eps == want.eps and got.stats["n_resamples"] >= 1
+        assert abs(got.logZ - want.logZ) <= 1e-9 * max(1.0, abs(want.logZ)), (got.logZ, want.logZ)
+        np.testing.assert_allclose(full.P.reshape(N, -1), want.P, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(full.C, want.C, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(full.Wns, want.Wns, rtol=1e-9)
+        fast = A.abcdesmc(prior, A.Model(name, data), eps_t, None, nparticles=N, rng=seed, verbose=False, ctx=ctx, ABCk=kind,
+                          nsims_max=10**9)
+        assert fast.eps == want.eps and abs(fast.logZ - want.logZ) < 0.5 and fast.stats["n_resamples"] >= 1
+        if rank == 0:
+            print(f"sharded {name} {kind} N={N} world={world}: iters {got.iters} nsims {got.nsims} logZ {got.logZ:.6f} == oracle(islands={world}); "
+                  f"parallel scan: iters {fast.iters} logZ {fast.logZ:.6f}")
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
