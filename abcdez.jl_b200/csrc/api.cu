@@ -81,6 +81,7 @@ extern "C" int abcdez_destroy(abcdez_ctx* ctx)
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->h_ctrl_pool) cudaFreeHost(ctx->h_ctrl_pool);
+    for (int b = 0; b < 2; ++b) { if (ctx->h_poll[b]) cudaFreeHost(ctx->h_poll[b]); if (ctx->poll_ev[b]) cudaEventDestroy(ctx->poll_ev[b]); }
     delete ctx;
     return ABCDEZ_OK;
 }
@@ -1015,6 +1016,11 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     const int sync_every = o->sync_every > 0 ? o->sync_every : 1;
     const int mode = abck_is_indicator(o->kernel) ? 0 : (o->exact_scan ? 2 : 1);
     SweepInj noinj; memset(&noinj, 0, sizeof(noinj));
+    int pb = 0; bool have_prev = false;
+    for (int b = 0; b < 2 && !rc; ++b) {
+        if (!ctx->h_poll[b] && cudaMallocHost((void**)&ctx->h_poll[b], sizeof(Ctrl)) != cudaSuccess) rc = fail(ABCDEZ_ERR_CUDA, "cudaMallocHost(poll buffer) failed");
+        if (!rc && !ctx->poll_ev[b] && cudaEventCreateWithFlags(&ctx->poll_ev[b], cudaEventDisableTiming) != cudaSuccess) rc = fail(ABCDEZ_ERR_CUDA, "cudaEventCreate(poll event) failed");
+    }
 #define RUN_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ABCDEZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); goto done; } } while (0)
     if (rc) goto done;
     RUN_CU(cudaEventCreate(&e_init0)); RUN_CU(cudaEventCreate(&e_loop0)); RUN_CU(cudaEventCreate(&e_loop1));
@@ -1058,9 +1064,17 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         }
         if (o->profile) { RUN_CU(cudaEventRecord(evs[nev + 1], st)); nev += 2; }
         if (host_iters % sync_every == 0) {
-            RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-            RUN_CU(cudaStreamSynchronize(st));
-            if (c->stop || c->err || c->acc.err) break;
+            // pipelined stop poll: request a copy of the control block behind this batch, then look at the copy
+            // requested behind the PREVIOUS batch -- the host stays one batch ahead of the device, so the device
+            // never idles while the host waits and re-enqueues (kernels behind a stop return at once)
+            RUN_CU(cudaMemcpyAsync(ctx->h_poll[pb], pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+            RUN_CU(cudaEventRecord(ctx->poll_ev[pb], st));
+            if (have_prev) {
+                RUN_CU(cudaEventSynchronize(ctx->poll_ev[pb ^ 1]));
+                const Ctrl* pc = ctx->h_poll[pb ^ 1];
+                if (pc->stop || pc->err || pc->acc.err) break;
+            }
+            have_prev = true; pb ^= 1;
         }
         if (host_iters > 10000000) break;
     }

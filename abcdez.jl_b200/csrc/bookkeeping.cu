@@ -17,6 +17,8 @@
 namespace abcdez {
 
 static inline unsigned tiles_for(int64_t N) { return (unsigned)((N + TILE - 1) / TILE); }
+// grid of the resampling gathers (grid-stride kernels): enough CTAs to fill a B200, few enough that a skipped launch is cheap
+static inline unsigned resample_grid(int64_t N) { unsigned g = (unsigned)((N + BK_THREADS - 1) / BK_THREADS); return g < 1184u ? g : 1184u; }
 
 __global__ void end_iter_kernel(PopDev P)
 {
@@ -383,8 +385,9 @@ resample_uniform_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
     const int cur = c->cur;
     const uint32_t N = P.N, n_alive = c->n_alive;
     const double sval = 1.0 / (double)N;                                     // :34
-    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si < N) {
+    // grid-stride over a capped grid (resample_grid): the kernel is launched every iteration and returns at the flag
+    // test above in all but ~1 of 14, so the launch must be cheap when it has nothing to do
+    for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         double u, u2;
         if (inj_u) u = inj_u[si];
         else { Stream rs(P.keys, P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }
@@ -398,9 +401,8 @@ resample_uniform_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
         }
         gather_particle(P, cur, DS, NB, si, src);                            // :96-99
         P.inds[si] = (int32_t)src;
+        P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1;                    // :102-103; the old buffer is stale (nobody gathers from these)
     }
-    __syncthreads();
-    if (si < N) { P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1; }        // :102-103; the old buffer is stale
     if (last_block(&c->acc.ticket[3], gridDim.x)) {
         if (threadIdx.x == 0) ctrl_after_resample(P, c);
     }
@@ -438,8 +440,7 @@ resample_uniform_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
     const int cur = c->cur;
     const uint32_t N = P.N, n_alive_g = c->n_alive_g;
     const double sval = 1.0 / (double)P.Ng;                                  // :34
-    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si < N) {
+    for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         const uint32_t sg = P.id0 + si;                                      // global stratum
         double u, u2;
         Stream rs(P.keys, sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
@@ -561,8 +562,7 @@ resample_general_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
     const int cur = c->cur;
     const uint32_t N = P.N;
     const double sval = 1.0 / (double)P.Ng;                                  // :34
-    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si < N) {
+    for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         const uint32_t sg = P.id0 + si;                                      // global stratum
         double u, u2;
         Stream rs(P.keys, sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
@@ -674,8 +674,7 @@ resample_general_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
     const int cur = c->cur;
     const uint32_t N = P.N;
     const double sval = 1.0 / (double)N;
-    uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si < N) {
+    for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         double u, u2;
         if (inj_u) u = inj_u[si];
         else { Stream rs(P.keys, P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }
@@ -683,9 +682,8 @@ resample_general_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
         uint32_t src = search_cumsum(P.cumsum, N, r);
         gather_particle(P, cur, DS, NB, si, src);
         P.inds[si] = (int32_t)src;
+        P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1;                    // (the search reads cumsum, not W)
     }
-    __syncthreads();
-    if (si < N) { P.W[si] = sval; P.alive[si] = 1; P.moved[si] = 1; }
     if (last_block(&c->acc.ticket[3], gridDim.x)) {
         if (threadIdx.x == 0) ctrl_after_resample(P, c);
     }
@@ -773,7 +771,7 @@ __global__ void build_tabs_kernel(PopDev P)
 int launch_resample(cudaStream_t st, const PopDev& P, int DS, int NB, const double* inj_u, uint32_t epoch,
                     int mode, int force)
 {
-    unsigned gt = tiles_for(P.N), gp = (unsigned)((P.N + BK_THREADS - 1) / BK_THREADS);
+    unsigned gt = tiles_for(P.N), gp = resample_grid(P.N);
     if (P.x.world > 1) {             // sharded: global resampling over peer memory
         if (mode == 0) {
             peer_barrier_kernel<<<1, 1, 0, st>>>(P, force);

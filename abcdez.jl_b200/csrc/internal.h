@@ -184,6 +184,8 @@ struct abcdez_ctx {
     char* arena; size_t arena_bytes; bool arena_busy;
     abcdez::Ctrl* h_ctrl_pool;          // pinned control-block mirror, reused like the arena
     bool h_ctrl_busy;
+    abcdez::Ctrl* h_poll[2];            // pinned copies of the control block for the pipelined stop poll of abcdez_smc_run
+    cudaEvent_t poll_ev[2];
 };
 
 struct abcdez_prior {

@@ -38,64 +38,11 @@ struct Gauss1DBlob {
 
 // config 2: y ~ N(theta, Sigma), Sigma_ij = rho^|i-j| (stationary AR(1) noise), d = ||y - y_obs||_2
 // data = y_obs[10], rho, and data[11] = sqrt(1 - rho^2), filled in by abcdez_model_bind (model_prepare_data, api.cu)
-// NOISE > 0: the simulator's random input does not depend on theta, so the sweep kernel may draw it
-// (draw) while the partner rows are still in flight and score it afterwards (score); run == draw + score.
 struct GaussCorr10 {
-    static constexpr int D = 10, BLOB = 0, NOISE = 10;
+    static constexpr int D = 10, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "gauss_corr10";
-    __device__ static __forceinline__ void draw(SimRng& r, double* nz)
-    {
-#pragma unroll
-        for (int k = 0; k < 10; k += 2) r.n2(nz[k], nz[k + 1]);
-    }
-    __device__ static __forceinline__ double score(const double* th, const double* data, const double* nz, double*)
-    {
-        double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            e = (k == 0) ? nz[0] : rho * e + sr * nz[k];
-            double dy = th[k] + e - data[k];
-            acc += dy * dy;
-        }
-        return sqrt(acc);
-    }
-    // all five noise pairs in lockstep (box_muller_batch) together with one extra pair of the caller (the
-    // gamma jitter of the DE move): ua/ub[5] in, z1/z2[5] out
-    static constexpr int NOISE_PAIRS = 5;
-    __device__ static __forceinline__ void noise_uniforms(SimRng& r, double* ua, double* ub)
-    {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) r.u2(ua[k], ub[k]);
-    }
-    __device__ static __forceinline__ void noise_store(const double* z1, const double* z2, double* col, int stride)
-    {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { col[(2 * k) * stride] = z1[k]; col[(2 * k + 1) * stride] = z2[k]; }
-    }
-    // the same two halves through a strided scratch column (shared memory): the AR(1) noise e_k is stored, the
-    // score reads it back one value at a time -- same operations in the same order as run()
-    __device__ static __forceinline__ void draw_to(SimRng& r, double* col, int stride)
-    {
-#pragma unroll
-        for (int k = 0; k < 10; k += 2) {
-            double za, zb;
-            r.n2(za, zb);
-            col[k * stride] = za; col[(k + 1) * stride] = zb;
-        }
-    }
-    __device__ static __forceinline__ double score_from(const double* th, const double* data, const double* col, int stride, double*)
-    {
-        double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            double z = col[k * stride];
-            e = (k == 0) ? z : rho * e + sr * z;
-            double dy = th[k] + e - data[k];
-            acc += dy * dy;
-        }
-        return sqrt(acc);
-    }
-    // noise pairs are consumed as they are generated (same arithmetic as draw + score, 18 fewer live registers)
+    // noise pairs are consumed as they are generated: drawing all ten first and scoring afterwards (in registers or
+    // parked in shared memory, also with the five Box-Muller pairs in lockstep) was measured slower, profiles/README.md
     __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
     {
         double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;

@@ -20,24 +20,6 @@
 #include "ctrl.cuh"
 #include "comm.cuh"
 
-// structure knobs of smc_sweep_kernel (profiles/README.md has the measurements behind the defaults)
-#ifndef ABCDEZ_SWEEP_CTRL_BATCH
-#define ABCDEZ_SWEEP_CTRL_BATCH 1
-#endif
-#ifndef ABCDEZ_SWEEP_PREFETCH
-#define ABCDEZ_SWEEP_PREFETCH 0         // L2 prefetch of the partner rows: measured slower (more LSU work than it hides)
-#endif
-#ifndef ABCDEZ_SWEEP_ASYNC_ROWS
-#define ABCDEZ_SWEEP_ASYNC_ROWS 0       // 1: partner rows staged through shared memory with cp.async (requested as soon as the
-#endif                                  // partner indices are known, consumed after the jitter's Box-Muller pair); 2: the
-                                        // particle's own row, logpi and delta too (requested before the partner draw)
-#ifndef ABCDEZ_SWEEP_EARLY_OWN
-#define ABCDEZ_SWEEP_EARLY_OWN 0        // 1: logpi / delta, 2: and the particle's own row, loaded before the partner draw
-#endif
-#ifndef ABCDEZ_SWEEP_EARLY_NOISE
-#define ABCDEZ_SWEEP_EARLY_NOISE 0      // 1: noise in registers before the gathers; 2: parked in shared memory; 3: all pairs in
-#endif                                  // lockstep (box_muller_batch) + shared memory -- all measured slower than consuming pairs as drawn
-
 namespace abcdez {
 
 // ---------------------------------------------------------------------------------------
@@ -256,12 +238,7 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // DISC: the prior has discrete marginals (push_p rounds a copy of the proposal); the common
 // all-continuous case passes the proposal registers straight to the simulator.
 // ---------------------------------------------------------------------------------------
-// ASYNC: the partner rows travel through dynamic shared memory (2 * row bytes per thread, sweep_async_smem<D>());
-// the launchers of the static registry use it for d >= 2, runtime-compiled models keep the direct gathers.
-template <int D>
-constexpr size_t sweep_async_smem(int level) { return (size_t)((level >= 2 ? 3 : 2) * row_stride(D) * 8 + (level >= 2 ? 16 : 0)) * SWEEP_THREADS; }
-
-template <class M, bool DISC, int PK, int ASYNC = 0>
+template <class M, bool DISC, int PK>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                  const __grid_constant__ SweepInj inj)
@@ -274,23 +251,14 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
     const double* __restrict__ th = P.theta[cur];
     __shared__ SweepSmem s_red;
     sweep_smem_init(&s_red);
-    extern __shared__ double2 s_rows[];                    // ASYNC: [2 * DS/2 partner pieces][T], then [DS/2 own pieces][T], [T] scalars
-    constexpr int NPIECE = row_stride(D) / 2;
-    double2* const s_own = s_rows + (size_t)2 * NPIECE * SWEEP_THREADS + threadIdx.x;
-    double2* const s_sc = s_rows + (size_t)3 * NPIECE * SWEEP_THREADS + threadIdx.x;
 
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
-#if ABCDEZ_SWEEP_EARLY_NOISE >= 2
-    __shared__ double s_noise[(M::NOISE > 0 ? M::NOISE : 1) * (M::NOISE > 0 ? SWEEP_THREADS : 1)];
-#endif
-#if ABCDEZ_SWEEP_CTRL_BATCH
     // every schedule scalar the particle work needs, loaded back to back (one L2 round trip, not six)
     const PhiloxKeys& seed = P.keys;
     const uint32_t epoch = c->sweep_epoch;
     const double gamma0 = c->gamma0, gsig = c->gsig, eps = c->eps;
     const int kind = c->kind;
-#endif
     if (j < N) {
         const uint32_t i = (n_alive == N) ? j : P.alive_list[j];
         const uint8_t mv = P.moved[i];
@@ -306,20 +274,6 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
         } else {
             uint8_t flag = 0;
             const uint32_t pid = P.id0 + i;
-            if constexpr (ASYNC >= 2) own_async_issue<D>(th, P.logpi[cur], P.delta[cur], i, s_own, s_sc, SWEEP_THREADS);
-#if ABCDEZ_SWEEP_EARLY_OWN >= 1
-            const double lpi_e = ld_early_f64(P.logpi[cur] + i), dli_e = ld_early_f64(P.delta[cur] + i);
-#endif
-#if ABCDEZ_SWEEP_EARLY_OWN >= 2
-            double thp_e[D];
-            load_row_early<D>(th, i, thp_e);
-#elif ABCDEZ_SWEEP_EARLY_OWN == 1 && ABCDEZ_SWEEP_PREFETCH
-            prefetch_row<D>(th, i);
-#endif
-#if !ABCDEZ_SWEEP_CTRL_BATCH
-            const PhiloxKeys& seed = P.keys;
-            const uint32_t epoch = c->sweep_epoch;
-#endif
             // (1) partners: integer work only (plus list lookups while some particles are dead)
             uint32_t a, b;
             if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
@@ -339,88 +293,30 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                     b = wsample_alive(P.alive_list, n_alive, N, u2);
                 }
             }
-            if constexpr (ASYNC >= 1) { if (!err) rows_async_issue<D>(th, a, b, s_rows + threadIdx.x, SWEEP_THREADS); }
-#if ABCDEZ_SWEEP_PREFETCH
-            // the two partner rows are random gathers (DRAM latency): request their sectors now, consume them
-            // after the random-number work below
-            if (!err) { prefetch_row<D>(th, a); prefetch_row<D>(th, b); }
-#endif
             SimRng r(seed, pid, epoch, TAG_MODEL);
-#if ABCDEZ_SWEEP_EARLY_NOISE == 1
-            // simulators whose random input does not depend on theta draw it while the gathers are in flight
-            double nz[M::NOISE > 0 ? M::NOISE : 1];
-            if constexpr (M::NOISE > 0) M::draw(r, nz);
-#elif ABCDEZ_SWEEP_EARLY_NOISE == 2
-            // ... and park it in shared memory (column per thread, conflict-free) so that the register-hungry
-            // Box-Muller code and the proposal / scoring code never hold their state at the same time
-            if constexpr (M::NOISE > 0) M::draw_to(r, &s_noise[threadIdx.x], SWEEP_THREADS);
-#endif
             // (2) the gamma jitter (:128)
             Stream ms(seed, pid, epoch, TAG_MOVE);
             double z, z2;
-#if ABCDEZ_SWEEP_EARLY_NOISE == 3
-            // the model's noise pairs and the jitter pair in lockstep (independent FP64 chains overlap), noise parked
-            // in shared memory
-            if constexpr (M::NOISE > 0) {
-                constexpr int NP = M::NOISE_PAIRS + 1;
-                double ua[NP], ub[NP], g1[NP], g2[NP];
-                M::noise_uniforms(r, ua, ub);
-                ms.u2(0u, ua[NP - 1], ub[NP - 1]);
-                box_muller_batch<NP>(ua, ub, g1, g2);
-                M::noise_store(g1, g2, &s_noise[threadIdx.x], SWEEP_THREADS);
-                z = inj.z ? inj.z[i] : g1[NP - 1];
-            } else
-#endif
             if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
-#if ABCDEZ_SWEEP_CTRL_BATCH
             const double g = gamma0 * (1.0 + z * gsig);                    // :128
-#else
-            const double g = c->gamma0 * (1.0 + z * c->gsig);              // :128
-#endif
             // (3) own state; repair the stale row in g+1
             double thp[D];
-            double lpi, dli;
-            if constexpr (ASYNC >= 2) { rows_async_wait(); own_staged_load<D>(s_own, s_sc, SWEEP_THREADS, thp, lpi, dli); }
-            else {
-#if ABCDEZ_SWEEP_EARLY_OWN >= 2
-#pragma unroll
-                for (int k = 0; k < D; ++k) thp[k] = thp_e[k];
-#else
-                load_row<D>(th, i, thp);
-#endif
-#if ABCDEZ_SWEEP_EARLY_OWN >= 1
-                lpi = lpi_e; dli = dli_e;
-#else
-                lpi = P.logpi[cur][i]; dli = P.delta[cur][i];
-#endif
-            }
+            load_row<D>(th, i, thp);
+            const double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
             if (mv) {
                 store_row<D>(P.theta[nxt], i, thp);
                 copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
             }
             if (!err) {
-                if constexpr (ASYNC >= 1) { rows_async_wait(); de_proposal_staged<D>(s_rows + threadIdx.x, SWEEP_THREADS, g, thp); }
-                else de_proposal<D>(th, a, b, g, thp);                     // :128
+                de_proposal<D>(th, a, b, g, thp);                          // :128
                 double xs[DISC ? D : 1];
                 const double* x = thp;
                 if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
                 double lp = prior_logpdf_k<D, PK>(pr, x);                  // :134
                 if (!(lp < 0.0 && isinf(lp))) {                            // :135
                     double blp[NB > 0 ? NB : 1];
-                    double dp;                                             // :137
-#if ABCDEZ_SWEEP_EARLY_NOISE == 1
-                    if constexpr (M::NOISE > 0) dp = M::score(x, md.v, nz, blp);
-                    else dp = M::run(x, md.v, r, blp);
-#elif ABCDEZ_SWEEP_EARLY_NOISE >= 2
-                    if constexpr (M::NOISE > 0) dp = M::score_from(x, md.v, &s_noise[threadIdx.x], SWEEP_THREADS, blp);
-                    else dp = M::run(x, md.v, r, blp);
-#else
-                    dp = M::run(x, md.v, r, blp);
-#endif
+                    const double dp = M::run(x, md.v, r, blp);             // :137
                     nsim = 1; flag |= ABCDEZ_FLAG_SIM;                     // :138
-#if !ABCDEZ_SWEEP_CTRL_BATCH
-                    const double eps = c->eps; const int kind = c->kind;
-#endif
                     double w = lp - lpi;                                   // :140-141, left to right
                     w = w + abck_logpdf(kind, eps, dp);
                     w = w - abck_logpdf(kind, eps, dli);
@@ -611,21 +507,10 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     bool all_normal = true, all_uniform = true;
     for (int k = 0; k < M::D; ++k) { all_normal = all_normal && pr.family[k] == ABCDEZ_NORMAL; all_uniform = all_uniform && pr.family[k] == ABCDEZ_UNIFORM; }
-    constexpr int A = M::D >= 2 ? ABCDEZ_SWEEP_ASYNC_ROWS : 0;
-    constexpr size_t sm = A ? sweep_async_smem<M::D>(A) : 0;
-    if constexpr (sm > 48 * 1024) {                       // opt in once per instantiation (d > 12)
-        static const bool once = [] {
-            cudaFuncSetAttribute(smc_sweep_kernel<M, true, PK_GENERIC, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(smc_sweep_kernel<M, false, PK_NORMAL, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(smc_sweep_kernel<M, false, PK_UNIFORM, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(smc_sweep_kernel<M, false, PK_GENERIC, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            return true; }();
-        (void)once;
-    }
-    if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
-    else if (all_normal) smc_sweep_kernel<M, false, PK_NORMAL, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
-    else if (all_uniform) smc_sweep_kernel<M, false, PK_UNIFORM, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
-    else smc_sweep_kernel<M, false, PK_GENERIC, A><<<g, SWEEP_THREADS, sm, st>>>(P, pr, md, inj);
+    if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    else if (all_normal) smc_sweep_kernel<M, false, PK_NORMAL><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    else if (all_uniform) smc_sweep_kernel<M, false, PK_UNIFORM><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    else smc_sweep_kernel<M, false, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
 }
 template <class M>
 static void l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,

@@ -650,6 +650,60 @@ def wsample_stratified(weights, uniforms, mode: int = 1, ctx: Optional[Context] 
 
 
 # ---------------------------------------------------------------------------------------------
+# after the run: what the reference's tests, example and docs do with a result
+# ---------------------------------------------------------------------------------------------
+def weightinds(weights, rng=None, ctx: Optional[Context] = None):
+    """`weightinds` of test/runtests.jl:13-19: stratified resampling indices (0-based here) of normalised weights,
+    through the library's `wsample_stratified!` kernel; `rng` seeds the per-stratum uniforms."""
+    w = _f64(weights)
+    if not abs(w.sum() - 1.0) < 1e-8:
+        raise ABCdeZError(ERR_BAD_ARG, "Sum of weights expected to be 1.0 (approximately)")
+    u = np.random.default_rng(_seed_from(rng)).random(w.size)
+    return np.clip(wsample_stratified(w, u, ctx=ctx), 1, w.size) - 1
+
+
+def posterior_sample(result: "SMCResult", rng=None, ctx: Optional[Context] = None):
+    """Equally weighted posterior sample of an `abcdesmc!` result: `P[weightinds(Wns)]` (test/runtests.jl:287-291)."""
+    return np.asarray(result.P)[weightinds(result.Wns, rng, ctx)]
+
+
+def evidence_at(result: "SMCResult", eps: float) -> float:
+    """log evidence of a `verboseout` run at tolerance `eps` from its ladder (`logZs`, `ϵs`): the record with the
+    smallest ϵ >= eps, i.e. the docs' workaround 1 for comparing models whose runs ended at different ϵ
+    (docs/src/index.md:282-284)."""
+    if result.eps_hist is None:
+        raise ABCdeZError(ERR_BAD_ARG, "evidence_at needs a run with verboseout=true")
+    e = np.asarray(result.eps_hist); ok = np.nonzero(e >= eps)[0]
+    if ok.size == 0:
+        raise ABCdeZError(ERR_BAD_ARG, "eps is above the whole ladder of this run")
+    return float(np.asarray(result.logZs)[ok[-1]])
+
+
+def model_probabilities(results_or_logZs, prior_probs=None, eps: Optional[float] = None):
+    """Posterior model probabilities (examples/minimal_example.jl:58-65) from log evidences or `abcdesmc!` results.
+    Results are compared at a common tolerance: `eps`, default the largest final ϵ among them (evidences at
+    different ϵ carry different kernel normalisations, docs/src/index.md:202-212)."""
+    items = list(results_or_logZs)
+    if items and isinstance(items[0], SMCResult):
+        at = max(r.eps for r in items) if eps is None else eps
+        lz = np.array([r.logZ if (r.eps == at and eps is None) else evidence_at(r, at) for r in items])
+    else:
+        lz = np.asarray(items, dtype=float)
+    pri = np.full(lz.size, 1.0 / lz.size) if prior_probs is None else np.asarray(prior_probs, dtype=float)
+    w = np.exp(lz - lz.max()) * pri
+    return w / w.sum()
+
+
+def evidence_uncertainty(prior, dist, eps_target, repeats: int = 8, rng=None, **kw):
+    """The docs' advice (docs/src/index.md:214-220): repeat `abcdesmc!` and summarise the log evidences.
+    Returns (mean, std, list of logZ); each repeat uses its own Philox key."""
+    base = _seed_from(rng)
+    lz = [abcdesmc(prior, dist, eps_target, None, rng=(base + 0x9E3779B97F4A7C15 * (k + 1)) % 2**64, verbose=False, **kw).logZ
+          for k in range(int(repeats))]
+    return float(np.mean(lz)), float(np.std(lz, ddof=1)) if len(lz) > 1 else 0.0, lz
+
+
+# ---------------------------------------------------------------------------------------------
 # device-resident population: the stage-level entry points
 # ---------------------------------------------------------------------------------------------
 class Population:

@@ -391,3 +391,26 @@ def test_run_state_continue_to_a_smaller_target_and_errors(A, gpu_ctx):
         A.abcdesmc(pr, m, 0.3, None, state=first.state, alpha=0.9, **kw)
     with pytest.raises(A.ABCdeZError):
         A.abcdesmc(pr, m, 0.3, None, state=first.state[:100], **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# after the run: weightinds / posterior sample / model probabilities at a matched tolerance / repeated evidences
+# ---------------------------------------------------------------------------------------------
+def test_post_run_helpers(A, gpu_ctx):
+    """examples/minimal_example.jl:10-65 end to end: two priors on the same data, posterior model probabilities
+    0.678 / 0.322 analytically; the resampled posterior has the weighted posterior's moments."""
+    m = A.Model("gauss1d", [3.0, 1.0])
+    r1 = A.abcdesmc(A.host.Normal(0, SQ10), m, 0.3, None, nparticles=20000, verbose=False, rng=101)
+    r2 = A.abcdesmc(A.host.Normal(0, 10.0), m, 0.3, None, nparticles=20000, verbose=False, rng=102)
+    p = A.host.model_probabilities([r1, r2])
+    assert abs(p[0] - 0.678) < 0.03 and abs(p.sum() - 1.0) < 1e-12
+    assert np.allclose(A.host.model_probabilities([r1.logZ, r2.logZ]), p)
+    # a run stopped at a larger tolerance is compared on the ladders (docs/src/index.md:282-284)
+    r2b = A.abcdesmc(A.host.Normal(0, 10.0), m, 0.5, None, nparticles=20000, verbose=False, rng=103)
+    pb = A.host.model_probabilities([r1, r2b])
+    assert A.host.evidence_at(r1, r2b.eps) > r1.logZ and 0.55 < pb[0] < 0.8
+    post = A.host.posterior_sample(r1, rng=7)
+    w = r1.Wns > 0
+    assert post.shape == r1.P.shape and abs(post.mean() - r1.P[w].mean()) < 0.02 and abs(post.std() - r1.P[w].std()) < 0.02
+    mean, sd, lz = A.host.evidence_uncertainty(A.host.Normal(0, SQ10), m, 0.3, repeats=6, rng=9, nparticles=5000)
+    assert len(lz) == 6 and len(set(lz)) == 6 and abs(mean - math.log(0.047940112540007955)) < 0.1 and 0.0 < sd < 0.15
