@@ -41,23 +41,31 @@ struct Gauss1DBlob {
 struct GaussCorr10 {
     static constexpr int D = 10, BLOB = 0, NOISE = 0;
     static constexpr const char* name = "gauss_corr10";
-    // noise pairs are consumed as they are generated: drawing all ten first and scoring afterwards (in registers or
-    // parked in shared memory, also with the five Box-Muller pairs in lockstep) was measured slower, profiles/README.md
-    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double*)
+    // the five noise pairs, then the AR(1) recursion and the distance as one straight loop: written this way the
+    // compiler schedules the (branch-free) Box-Muller pairs and the scoring freely -- 102.7 us per sweep against 108.3
+    // with the scoring statements interleaved by hand after every pair; explicit two-pair lockstep code 103.5, drawing
+    // the noise before the partner gathers 106.8-115.8, parking it in shared memory slower still (profiles/README.md)
+    __device__ static __forceinline__ void draw(SimRng& r, double* z)
+    {
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) r.n2(z[k], z[k + 1]);
+    }
+    __device__ static __forceinline__ double score(const double* th, const double* data, const double* z, double*)
     {
         double rho = data[10], sr = data[11], e = 0.0, acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < 10; k += 2) {
-            double za, zb;
-            r.n2(za, zb);
-            e = (k == 0) ? za : rho * e + sr * za;
+        for (int k = 0; k < 10; ++k) {
+            e = (k == 0) ? z[0] : rho * e + sr * z[k];
             double dy = th[k] + e - data[k];
-            acc += dy * dy;
-            e = rho * e + sr * zb;
-            dy = th[k + 1] + e - data[k + 1];
             acc += dy * dy;
         }
         return sqrt(acc);
+    }
+    __device__ static __forceinline__ double run(const double* th, const double* data, SimRng& r, double* blob)
+    {
+        double z[10];
+        draw(r, z);
+        return score(th, data, z, blob);
     }
 };
 

@@ -278,15 +278,19 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
             uint32_t a, b;
             if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
             else {
+                // attempt k of either loop reads block k of the partner stream (u1 -> a, u2 -> b), so the first attempts
+                // of both share ONE Philox block; the rejection loops continue from block 1
                 Stream ps(seed, pid, epoch, TAG_PARTNER);
-                double u1, u2; uint32_t att = 0;
-                a = i;
+                double u1, u2, ua, ub; uint32_t att = 1;
+                ps.u2(0u, ua, ub);
+                a = wsample_alive(P.alive_list, n_alive, N, ua);
                 while (a == i) {                                           // :119-122
                     if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
                     ps.u2(att++, u1, u2);
                     a = wsample_alive(P.alive_list, n_alive, N, u1);
                 }
-                att = 0; b = a;
+                att = 1;
+                b = wsample_alive(P.alive_list, n_alive, N, ub);
                 while (b == a || b == i) {                                 // :123-126
                     if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
                     ps.u2(att++, u1, u2);
@@ -396,21 +400,22 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
         uint32_t a, b;
         if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
         else {
-            Stream ps(seed, pid, epoch, TAG_PARTNER);
-            double u1, u2; uint32_t att = 0;
-            a = s;
+            Stream ps(seed, pid, epoch, TAG_PARTNER);                      // (first attempts share block 0, see smc_sweep_kernel)
+            double u1, u2, ua, ub; uint32_t att = 1;
+            auto pick = [N](double u) { long long k = (long long)floor(u * (double)N); if (k >= (long long)N) k = (long long)N - 1; return (uint32_t)k; };
+            ps.u2(0u, ua, ub);
+            a = pick(ua);
             while (a == s) {                                               // :25-28
                 if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
                 ps.u2(att++, u1, u2);
-                long long k = (long long)floor(u1 * (double)N); if (k >= (long long)N) k = (long long)N - 1;
-                a = (uint32_t)k;
+                a = pick(u1);
             }
-            att = 0; b = a;
+            att = 1;
+            b = pick(ub);
             while (b == a || b == s) {                                     // :29-32
                 if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
                 ps.u2(att++, u1, u2);
-                long long k = (long long)floor(u2 * (double)N); if (k >= (long long)N) k = (long long)N - 1;
-                b = (uint32_t)k;
+                b = pick(u2);
             }
         }
         if (!err) {

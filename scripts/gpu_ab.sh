@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 ) > gpurun_out/pytest_gpu.log
 for lib in abcdez.jl_b200/libabcdez_cuda*.so; do
-  for args in "gauss_corr10 1000000 0.0" "gauss_corr10 1000000 0.3" "lotka_volterra 1000000 0.0" "twod 1000000 0.0"; do
+  for args in "gauss_corr10 1000000 0.0" "gauss_corr10 1000000 0.3" "twod 1000000 0.0"; do
     ABCDEZ_LIB=$PWD/$lib timeout 120 python scripts/bench_sweep.py $args 2>&1 | tail -1 | sed "s#.*/libabcdez_cuda##"
   done
   ABCDEZ_LIB=$PWD/$lib timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "

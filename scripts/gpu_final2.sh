@@ -1,0 +1,11 @@
+#!/bin/bash
+# Final evidence of the round on one GPU: tests, smoke, bench, micro-benchmarks, launch list, full ncu capture of the sweep kernel
+set -u
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 ) > gpurun_out/pytest_gpu.log
+( timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -5 ) > gpurun_out/smoke.log
+( timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 ) > gpurun_out/bench.log
+for m in gauss_corr10 gauss1d twod; do timeout 120 python scripts/bench_sweep.py $m 1000000 2>&1 | tail -1; done > gpurun_out/sweep_micro.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:smc_sweep_kernel -s 20 -c 3 -o gpurun_out/prof_sweep -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.log gpurun_out/sweep_micro.log
