@@ -1,14 +1,11 @@
 #!/bin/bash
-# One gpurun call: GPU tests, the bench, the launch list and one full ncu capture of the sweep kernel.
+# One gpurun call on one GPU: tests, smoke, bench, micro-benchmarks, launch list, full ncu capture of the sweep kernel
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_gpu.log
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 ) > gpurun_out/pytest_gpu.log
 ( timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -5 ) > gpurun_out/smoke.log
-( timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -5 ) > gpurun_out/bench.log
-( timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -3 ) > gpurun_out/bench_ref.log
-( timeout 300 python scripts/run_breakdown.py 2>&1 | tail -12 ) > gpurun_out/breakdown.log
-for m in gauss_corr10 gauss1d twod lotka_volterra; do timeout 120 python scripts/bench_sweep.py $m 1000000 2>&1 | tail -1; done > gpurun_out/sweep_micro.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:smc_sweep_kernel -s 20 -c 3 -o gpurun_out/prof_sweep -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out
+( timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 ) > gpurun_out/bench.log
+for m in gauss_corr10 gauss1d twod; do timeout 120 python scripts/bench_sweep.py $m 1000000 2>&1 | tail -1; done > gpurun_out/sweep_micro.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:smc_sweep_kernel -s 20 -c 3 -o gpurun_out/prof_sweep -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.log gpurun_out/sweep_micro.log
