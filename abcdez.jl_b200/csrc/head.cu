@@ -290,10 +290,15 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constan
                 if (ok && isnan(v[k])) nan_seen = 1;
                 unsigned digit;
                 if (win) {
+                    // (window digits are spread over ~10^3 bins: plain shared-memory atomics; the generic leading digit
+                    // is the same for almost every key: warp-aggregated)
                     const unsigned long long d = key >> 42;
                     digit = d <= wbase ? 0u : (d - wbase >= 2047ull ? 2047u : (unsigned)(d - wbase));
-                } else digit = (unsigned)(key >> 53);
-                hist_add(s.hist, ok, digit);
+                    if (ok) atomicAdd(&s.hist[digit], 1u);
+                } else {
+                    digit = (unsigned)(key >> 53);
+                    hist_add(s.hist, ok, digit);
+                }
             }
         }
         if (tid == 0) { s.mn = ~0ull; s.mx = 0ull; }
