@@ -26,6 +26,10 @@ namespace cg = cooperative_groups;
 namespace abcdez {
 
 constexpr int HEAD_THREADS = BK_THREADS;
+#ifndef ABCDEZ_HEAD_MIN_BLOCKS
+#define ABCDEZ_HEAD_MIN_BLOCKS 2
+#endif
+constexpr int HEAD_MIN_BLOCKS = ABCDEZ_HEAD_MIN_BLOCKS;   // resident CTAs per SM the register budget is cut for
 constexpr int CAND_SMEM = 4096;                   // candidates staged in shared memory for the per-CTA tail; longer
                                                   // lists are first refined grid-cooperatively, one digit per round
 
@@ -243,7 +247,7 @@ __device__ __noinline__ void head_xchg_rec(const PopDev& P, Ctrl* c, int nw, Hea
     xchg_ll_block(P.x, c, s->xh, nw, nullptr, 0, s->xall, &s->xflag);
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const __grid_constant__ PopDev P)
+__global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(const __grid_constant__ PopDev P)
 {
     Ctrl* c = P.ctrl;
     if (c->stop) return;                                    // uniform: nobody reaches a grid barrier

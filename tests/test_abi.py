@@ -81,3 +81,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liborc" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_post_run_helpers_host_side(A):
+    """model probabilities (examples/minimal_example.jl:58-65) and the evidence-ladder lookup
+    (docs/src/index.md:282-284) are plain host arithmetic: no GPU needed."""
+    import math
+    import numpy as np
+    p = A.host.model_probabilities([math.log(0.047940112540007955), math.log(0.022780)])
+    assert abs(p[0] - 0.678) < 1e-3 and abs(p.sum() - 1.0) < 1e-15
+    p = A.host.model_probabilities([-3.0, -3.0, -3.0], prior_probs=[0.5, 0.25, 0.25])
+    assert np.allclose(p, [0.5, 0.25, 0.25])
+    mk = lambda eps, lz, eh, lzs: A.host.SMCResult(P=np.zeros(1), Wns=np.ones(1), C=np.zeros(1), eps=eps, logZ=lz, blobs=np.zeros((1, 0)),
+                                                   eps_hist=np.array(eh), logZs=np.array(lzs))
+    r1 = mk(0.3, -3.0, [np.inf, 1.0, 0.6, 0.45, 0.3], [0.0, -1.0, -2.0, -2.5, -3.0])
+    r2 = mk(0.5, -2.8, [np.inf, 2.0, 0.9, 0.5], [0.0, -0.5, -1.7, -2.8])
+    assert A.host.evidence_at(r1, 0.5) == -2.0 and A.host.evidence_at(r1, 0.3) == -3.0 and A.host.evidence_at(r1, 5.0) == 0.0
+    p = A.host.model_probabilities([r1, r2])            # compared at eps = 0.5: -2.0 against -2.8
+    assert abs(p[0] - 1.0 / (1.0 + math.exp(-0.8))) < 1e-12
+    with pytest.raises(A.ABCdeZError):
+        A.host.weightinds([0.5, 0.2])                   # weights must sum to 1 (test/runtests.jl:14)
