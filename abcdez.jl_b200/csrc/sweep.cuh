@@ -238,7 +238,12 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // DISC: the prior has discrete marginals (push_p rounds a copy of the proposal); the common
 // all-continuous case passes the proposal registers straight to the simulator.
 // ---------------------------------------------------------------------------------------
-template <class M, bool DISC, int PK>
+// INJ: the launch may carry injected partners / jitter / accept uniforms / a flags buffer (stage-level parity calls);
+// production launches (abcdez_smc_run) use INJ = false, which removes those tests -- and with them the basic-block
+// boundaries that keep the partner draw, the jitter's Box-Muller pair and the loads from being scheduled together
+// (101.8 -> 95.1 us per sweep).  Straightening further -- simulator and accept draw unconditional for all-Normal
+// priors, the stale-row repair moved behind the accept test -- costs registers and was slower (113.6 us).
+template <class M, bool DISC, int PK, bool INJ = true>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                  const __grid_constant__ SweepInj inj)
@@ -270,13 +275,13 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                 copy_scalars<NB>(P, cur, nxt, i, P.logpi[cur][i], P.delta[cur][i]);
                 P.moved[i] = 0;
             }
-            if (inj.flags) inj.flags[i] = 0;
+            if (INJ && inj.flags) inj.flags[i] = 0;
         } else {
             uint8_t flag = 0;
             const uint32_t pid = P.id0 + i;
             // (1) partners: integer work only (plus list lookups while some particles are dead)
             uint32_t a, b;
-            if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
+            if (INJ && inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
             else {
                 // attempt k of either loop reads block k of the partner stream (u1 -> a, u2 -> b), so the first attempts
                 // of both share ONE Philox block; the rejection loops continue from block 1
@@ -301,7 +306,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
             // (2) the gamma jitter (:128)
             Stream ms(seed, pid, epoch, TAG_MOVE);
             double z, z2;
-            if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
+            if (INJ && inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
             const double g = gamma0 * (1.0 + z * gsig);                    // :128
             // (3) own state; repair the stale row in g+1
             double thp[D];
@@ -327,7 +332,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                     bool acc = (0.0 <= w);
                     if (!acc) {                                            // :145, uniform only when w < 0
                         double u, u2;
-                        if (inj.u) { u = inj.u[i]; acc = (plog(u) < w); }
+                        if (INJ && inj.u) { u = inj.u[i]; acc = (plog(u) < w); }
                         else { ms.u2(1u, u, u2); acc = ((u == 0.0 ? -INFINITY : plog_unit(u)) < w); }   // u in [0, 1)
                     }
                     if (acc) {                                             // :146-150
@@ -341,7 +346,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                 }
             }
             if ((uint8_t)nacc != mv) P.moved[i] = (uint8_t)nacc;
-            if (inj.flags) inj.flags[i] = flag;
+            if (INJ && inj.flags) inj.flags[i] = flag;
         }
     }
     const bool last = sweep_finish<false>(c, &s_red, nsim, nacc, 0ull, 0ull, err);
@@ -512,10 +517,15 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     bool all_normal = true, all_uniform = true;
     for (int k = 0; k < M::D; ++k) { all_normal = all_normal && pr.family[k] == ABCDEZ_NORMAL; all_uniform = all_uniform && pr.family[k] == ABCDEZ_UNIFORM; }
+    const bool injected = inj.a || inj.b || inj.s || inj.z || inj.u || inj.flags;
     if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
-    else if (all_normal) smc_sweep_kernel<M, false, PK_NORMAL><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
-    else if (all_uniform) smc_sweep_kernel<M, false, PK_UNIFORM><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
-    else smc_sweep_kernel<M, false, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    else if (all_normal) {
+        if (injected) smc_sweep_kernel<M, false, PK_NORMAL, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else smc_sweep_kernel<M, false, PK_NORMAL, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    } else if (all_uniform) {
+        if (injected) smc_sweep_kernel<M, false, PK_UNIFORM, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else smc_sweep_kernel<M, false, PK_UNIFORM, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+    } else smc_sweep_kernel<M, false, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
 }
 template <class M>
 static void l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
