@@ -242,7 +242,8 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // production launches (abcdez_smc_run) use INJ = false, which removes those tests -- and with them the basic-block
 // boundaries that keep the partner draw, the jitter's Box-Muller pair and the loads from being scheduled together
 // (101.8 -> 95.1 us per sweep).  Straightening further -- simulator and accept draw unconditional for all-Normal
-// priors, the stale-row repair moved behind the accept test -- costs registers and was slower (113.6 us).
+// priors, the stale-row repair moved behind the accept test -- costs registers and was slower (113.6 us; the repair
+// move alone 99.3 us, the unconditional accept draw alone neutral).
 template <class M, bool DISC, int PK, bool INJ = true>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
@@ -289,17 +290,19 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                 double u1, u2, ua, ub; uint32_t att = 1;
                 ps.u2(0u, ua, ub);
                 a = wsample_alive(P.alive_list, n_alive, N, ua);
-                while (a == i) {                                           // :119-122
-                    if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
-                    ps.u2(att++, u1, u2);
-                    a = wsample_alive(P.alive_list, n_alive, N, u1);
-                }
-                att = 1;
                 b = wsample_alive(P.alive_list, n_alive, N, ub);
-                while (b == a || b == i) {                                 // :123-126
-                    if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
-                    ps.u2(att++, u1, u2);
-                    b = wsample_alive(P.alive_list, n_alive, N, u2);
+                if (a == i || b == a || b == i) {                          // ~3 / n_alive: one rare branch around both loops
+                    while (a == i) {                                       // :119-122
+                        if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                        ps.u2(att++, u1, u2);
+                        a = wsample_alive(P.alive_list, n_alive, N, u1);
+                    }
+                    att = 1;
+                    while (b == a || b == i) {                             // :123-126
+                        if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                        ps.u2(att++, u1, u2);
+                        b = wsample_alive(P.alive_list, n_alive, N, u2);
+                    }
                 }
             }
             SimRng r(seed, pid, epoch, TAG_MODEL);
