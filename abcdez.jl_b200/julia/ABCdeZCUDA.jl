@@ -233,11 +233,11 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
         else
             need = ccall((:abcdez_smc_state_bytes, LIB), Int64, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32), ph, mh, N, r.hist_cap)
             sout = return_state ? Vector{UInt8}(undef, need) : UInt8[]
-            sin = state === nothing ? UInt8[] : state
+            s_in = state === nothing ? UInt8[] : state
             nout = Ref{Int64}(0)
-            GC.@preserve sin sout check(ccall((:abcdez_smc_run_state, LIB), Cint,
+            GC.@preserve s_in sout check(ccall((:abcdez_smc_run_state, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{SmcOpts}, Ref{SmcResult}, Ptr{UInt8}, Int64, Ptr{UInt8}, Int64, Ref{Int64}),
-                ctx.h, ph, mh, ϵ_target, o, r, state === nothing ? C_NULL : pointer(sin), length(sin),
+                ctx.h, ph, mh, ϵ_target, o, r, state === nothing ? C_NULL : pointer(s_in), length(s_in),
                 return_state ? pointer(sout) : C_NULL, length(sout), nout))
             return_state && resize!(sout, nout[])
             state_out = return_state ? sout : nothing
