@@ -763,6 +763,7 @@ extern "C" int abcdez_pop_head(abcdez_pop* pop, double alpha, double eps_target,
     rc = push_ctrl(pop); if (rc) return rc;
     TIME_BEGIN(pop);
     int nl = launch_head(pop->ctx->stream, pop->dev, pop->ctx->sm_count);
+    if (nl < 0) return fail(ABCDEZ_ERR_CUDA, std::string("abcdez_pop_head: cooperative launch of the head kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
     CU(cudaGetLastError());
     TIME_END(pop, nl);
     rc = pull_ctrl(pop); if (rc) return rc;
@@ -1046,8 +1047,15 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
         host_iters++;
-        if (o->fused_head || shard) launches += launch_head(st, pop->dev, ctx->sm_count);   // :301-324 in one cooperative kernel
-        else {
+        if (o->fused_head || shard) {                                        // :301-324 in one cooperative kernel
+            const int nl = launch_head(st, pop->dev, ctx->sm_count);
+            if (nl < 0) {    // nothing else may run on stale eps / alive state: abort the run at once
+                rc = fail(ABCDEZ_ERR_CUDA, std::string("abcdez_smc_run: cooperative launch of the head kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
+                cudaStreamSynchronize(st);
+                goto done;
+            }
+            launches += nl;
+        } else {
             launches += launch_eps_quantile(st, pop->dev);                   // :301
             launches += launch_reweight(st, pop->dev);                       // :305-324
             launches += launch_compact(st, pop->dev);

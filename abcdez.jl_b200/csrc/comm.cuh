@@ -201,12 +201,13 @@ __device__ __forceinline__ void ll_poll_batch(const unsigned long long* p, int s
 // All 32 lanes of ONE warp call this with the same rec[].  Lane q < world posts the record to rank q and
 // then collects rank q's record from the local mailbox: on return lane q holds out[] = record of rank q
 // (lanes >= world: zeros, valid = false).  The caller reduces across lanes with shuffles.
+// The same all-gather with the exchange's sequence number supplied by the caller, who also publishes X.seq[1]
+// when its kernel has counted several exchanges (head.cu).
 template <int NW>
-__device__ __forceinline__ bool xchg_ll_warp(const XchgDev& X, Ctrl* c, const unsigned long long (&rec)[NW],
-                                             unsigned long long (&out)[NW])
+__device__ __forceinline__ bool xchg_ll_warp_seq(const XchgDev& X, Ctrl* c, unsigned long long seq, const unsigned long long (&rec)[NW],
+                                                 unsigned long long (&out)[NW])
 {
     const int lane = threadIdx.x & 31;
-    const unsigned long long seq = __ldcg(X.seq + 1) + 1ull;
     const unsigned slot = (unsigned)(seq & (XCHG_RING - 1)), flag = (unsigned)seq;
     bool ok = true;
 #pragma unroll
@@ -224,12 +225,20 @@ __device__ __forceinline__ bool xchg_ll_warp(const XchgDev& X, Ctrl* c, const un
         for (int k = 0; k < NW; ++k) out[k] = ((unsigned long long)half[2 * k + 1] << 32) | half[2 * k];
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) {
-        __stcg(X.seq + 1, seq);
-        if (!ok) xchg_fail(c);
-    }
+    if (lane == 0 && !ok) xchg_fail(c);
     __syncwarp();
     return lane < X.world;
+}
+
+template <int NW>
+__device__ __forceinline__ bool xchg_ll_warp(const XchgDev& X, Ctrl* c, const unsigned long long (&rec)[NW],
+                                             unsigned long long (&out)[NW])
+{
+    const unsigned long long seq = __ldcg(X.seq + 1) + 1ull;
+    const bool valid = xchg_ll_warp_seq<NW>(X, c, seq, rec, out);
+    if ((threadIdx.x & 31) == 0) __stcg(X.seq + 1, seq);
+    __syncwarp();
+    return valid;
 }
 
 // ---- CTA-wide LL exchange: nh <= 16 header values (all-gathered) + an nb-bin histogram (all-reduced) ----

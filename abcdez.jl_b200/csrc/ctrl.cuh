@@ -16,6 +16,10 @@ __device__ inline void push_hist(const PopDev& P, Ctrl* c, double eps, double es
         h[0] = eps; h[1] = c->dmin; h[2] = c->dmax; h[3] = c->logZ; h[4] = ess; h[5] = facc;
         h[6] = c->gamma0; h[7] = (double)K;
         c->hist_len += 1;
+        c->hist_iter = 1;                      // the most recent record is in the buffer (patch_extrema may complete it)
+    } else {
+        c->hist_iter = 0;                      // dropped: the buffer is full (reported as hist_overflow) or absent
+        if (P.hist) c->hist_overflow += 1;
     }
 }
 
@@ -95,7 +99,7 @@ static __device__ __noinline__ void patch_extrema(const PopDev& P, Ctrl* c)
 {
     c->dmin = key_f64(__ldcg(&c->acc.dmin_key)); c->dmax = key_f64(__ldcg(&c->acc.dmax_key));
     c->acc.dmin_key = ~0ull; c->acc.dmax_key = 0ull;
-    if (P.hist && c->hist_len > 0 && c->hist_len <= c->hist_cap) {
+    if (P.hist && c->hist_iter && c->hist_len > 0 && c->hist_len <= c->hist_cap) {   // only the record this generation pushed
         double* h = P.hist + (size_t)(c->hist_len - 1) * 8;
         h[1] = c->dmin; h[2] = c->dmax;
     }

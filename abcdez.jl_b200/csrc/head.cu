@@ -4,17 +4,32 @@
 //   reweighting    abcdesmc_update_ws!, wprod, wnorm, Wns, alive         :59-83, :305-311
 //   logZ / ESS     logZ += log(wnorm); ess = 1/sum(Wns^2); resample flag :315, :323-324
 //   alive list     compaction (the O(1) replacement of the wsample scans :121,125)
-// The unfused path (bookkeeping.cu) needs 10 launches of ~10-20 us each for 8 MB of state at 10^6 particles:
-// they are launch/latency bound, not bandwidth bound.  Here every CTA owns a contiguous range of
-// 1024-particle tiles, the phases are separated by grid barriers (~2 us) and every grid-wide decision is
-// recomputed redundantly by every CTA from the same integers / the same fixed-order partial sums, so no
-// phase waits on a single "last block".  Reductions keep the per-tile partials and the summation order of
-// the unfused kernels: both paths give bit-identical eps, W, wnorm, logZ and ESS.
 //
-// Radix select: two 11-bit digit passes over the alive distances (order-preserving 64-bit keys), then the
-// few keys that share the 22-bit prefix of v[j] are compacted into a candidate list and the remaining 42
-// bits, the tie test and v[j+1] are resolved on that list (per CTA in shared memory when it is small,
-// grid-cooperatively while it is large).
+// Round-2 structure.  At 10^6 particles the whole working set (delta, W, alive: 17 MB) lives in L2, so the
+// round-1 kernel (five passes, each a chain of load -> reduce -> barrier per 1024-particle tile, four grid
+// barriers) was bound by latency, not bandwidth: 50-60 us against ~6 us of L2 traffic.  Now
+//   * a CTA keeps its share of the population in REGISTERS: up to KT = 4 tiles (16 distances, 16 weights and
+//     the alive bytes per thread) are loaded once with all loads in flight together and reused by every phase
+//     (larger shares are processed in rounds of KT tiles and re-read per phase -- bandwidth bound then);
+//   * the per-tile reductions of a round are batched (one pair of CTA barriers for KT tiles);
+//   * THREE grid barriers in the common case: after the window histogram, after the candidate compaction,
+//     after the per-tile weight sums.  The alive mask is decided together with wprod (wprod / wnorm > 0 <=>
+//     wprod > 0 for a finite positive wnorm without underflow -- checked, ABCDEZ_ERR_BAD_ARG otherwise), so
+//     the alive counts travel with the weight sums and normalisation, ESS partials and the alive-list
+//     compaction need no barrier of their own; the last CTA to finish adds up the ESS partials.
+//   * the eps select uses ONE adaptive window: 2047 bins of 2^s key units below key(eps_prev), with s taken
+//     from the distance between the previous two thresholds in key space, so that the new quantile falls
+//     near the middle of the window and its bin holds ~10^-4 of the population (30-80 candidate keys at 10^6
+//     particles; the fixed 22-bit-prefix window of round 1 left 2000-5000).  The map key -> bin is monotone,
+//     so the select stays exact; when the rank falls outside the window (first iteration, eps_prev = Inf, a
+//     collapsing population) two generic 11-bit digit passes run instead.
+//   * sharded runs: no "CTA 0 exchanges, then a second grid barrier".  After the local grid
+//     barrier CTA q posts this rank's record to rank q (R CTAs post in parallel), reducer CTAs sum 256 bins
+//     each into a local flag-in-word array, and EVERY CTA of every rank polls what it needs out of local
+//     memory: the reduced histogram, the candidate keys of all ranks, the weight sums.  Every decision is
+//     recomputed redundantly from the same integers / rank-ordered FP64 sums, so all ranks agree bit for bit.
+// Reductions keep the per-tile partials and the summation order of the unfused stage kernels
+// (bookkeeping.cu): both paths give bit-identical eps, W, wnorm, logZ and ESS.
 #include "internal.h"
 #include "seqsum.cuh"
 #include "ctrl.cuh"
@@ -26,24 +41,24 @@ namespace cg = cooperative_groups;
 namespace abcdez {
 
 constexpr int HEAD_THREADS = BK_THREADS;
-#ifndef ABCDEZ_HEAD_MIN_BLOCKS
-#define ABCDEZ_HEAD_MIN_BLOCKS 2
-#endif
-constexpr int HEAD_MIN_BLOCKS = ABCDEZ_HEAD_MIN_BLOCKS;   // resident CTAs per SM the register budget is cut for
+constexpr int HEAD_MIN_BLOCKS = 2;                // resident CTAs per SM the register budget is cut for
+constexpr int KT = 4;                             // tiles per round: 16 particles per thread stay in registers
+constexpr int KE = KT * 4;
 constexpr int CAND_SMEM = 4096;                   // candidates staged in shared memory for the per-CTA tail; longer
                                                   // lists are first refined grid-cooperatively, one digit per round
+constexpr int CAND_DIRECT = 256;                  // ... and at most this many are ranked directly (one per thread)
+constexpr int NW = HEAD_THREADS / 32;
 
 struct HeadSmem {
     unsigned hist[SEL_BINS];
     unsigned long long cand[CAND_SMEM];
     unsigned part[HEAD_THREADS];
-    double red[32];
-    unsigned wcnt[32];
+    double red[KT][NW];
+    double red1[32];
+    unsigned wcnt[KT][NW];
     unsigned long long wmin[32];
     unsigned long long mn, mx, mab;
-    unsigned found_bin, found_before, found_cnt, flag;
-    unsigned long long xh[8];                     // sharded runs: this rank's header record of an exchange
-    unsigned long long xall[XCHG_MAXR * 8];       // ... and every rank's, after it
+    unsigned found_bin, found_before, found_cnt, flag, flag2;
     int xflag;
 };
 
@@ -51,19 +66,16 @@ __device__ __forceinline__ int pass_shift(int p) { const int s[6] = { 53, 42, 31
 __device__ __forceinline__ int pass_bins(int p) { return p == 5 ? 512 : 2048; }
 __device__ __forceinline__ unsigned long long pass_himask_after(int p) { return p == 5 ? ~0ull : (~0ull << pass_shift(p)); }
 
-// pick the bin holding rank `rank` in a SEL_BINS histogram (global: read through L2; else shared); every
-// thread of the CTA participates and gets the same answer.  bin == 0xffffffff: rank beyond the total.
-__device__ __noinline__ void pick_bin(const unsigned* h, bool global, int nbins, unsigned long long rank, HeadSmem* s,
-                         unsigned& bin, unsigned long long& before)
+// pick the bin holding rank `rank` in a SEL_BINS histogram of which this thread holds bins tid*8 .. tid*8+7
+// in loc[]; every thread of the CTA participates and gets the same answer.  bin == 0xffffffff: rank beyond
+// the total.  s->found_cnt: keys in the picked bin (stable until the next call).
+__device__ __noinline__ void pick_bin(const unsigned (&loc)[SEL_BINS / HEAD_THREADS], unsigned long long rank, HeadSmem* s,
+                                      unsigned& bin, unsigned long long& before)
 {
-    const int per = SEL_BINS / HEAD_THREADS;
-    unsigned loc[per], tot = 0;
+    constexpr int per = SEL_BINS / HEAD_THREADS;
+    unsigned tot = 0;
 #pragma unroll
-    for (int k = 0; k < per; ++k) {
-        int b = threadIdx.x * per + k;
-        loc[k] = (b < nbins) ? (global ? __ldcg(&h[b]) : h[b]) : 0u;
-        tot += loc[k];
-    }
+    for (int k = 0; k < per; ++k) tot += loc[k];
     // exclusive prefix of the per-thread totals: shuffle scan inside the warps, then the warp totals
     const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     unsigned incl = tot;
@@ -83,6 +95,17 @@ __device__ __noinline__ void pick_bin(const unsigned* h, bool global, int nbins,
     }
     __syncthreads();
     bin = s->found_bin; before = s->found_before;
+}
+
+__device__ __forceinline__ void load_bins_global(const unsigned* h, int nbins, unsigned (&loc)[SEL_BINS / HEAD_THREADS])
+{
+#pragma unroll
+    for (int k = 0; k < SEL_BINS / HEAD_THREADS; ++k) { int b = threadIdx.x * (SEL_BINS / HEAD_THREADS) + k; loc[k] = b < nbins ? __ldcg(&h[b]) : 0u; }
+}
+__device__ __forceinline__ void load_bins_shared(const unsigned* h, int nbins, unsigned (&loc)[SEL_BINS / HEAD_THREADS])
+{
+#pragma unroll
+    for (int k = 0; k < SEL_BINS / HEAD_THREADS; ++k) { int b = threadIdx.x * (SEL_BINS / HEAD_THREADS) + k; loc[k] = b < nbins ? h[b] : 0u; }
 }
 
 // warp-aggregated shared-memory histogram increment (leading digits of distances are highly concentrated)
@@ -111,56 +134,95 @@ __device__ __forceinline__ void hist_flush(HeadSmem* s, unsigned* gh, int nbins)
 // broadcast a block_sum result (valid in warp 0) to every thread
 __device__ __forceinline__ double block_sum_all(double v, HeadSmem* s)
 {
-    double t = block_sum(v, s->red);
+    double t = block_sum(v, s->red1);
     __syncthreads();
-    if (threadIdx.x == 0) s->red[0] = t;
+    if (threadIdx.x == 0) s->red1[0] = t;
     __syncthreads();
-    t = s->red[0];
+    t = s->red1[0];
     __syncthreads();
     return t;
 }
 
-// resolve v[j] (rank `rank` among the M listed keys, all of which match prefix/himask), the tie test and
-// v[j+1] with the digits from pass p0 on, entirely inside the CTA.  L: shared or global (L2) list.
-__device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M, int p0, unsigned long long prefix,
-                            unsigned long long himask, unsigned long long rank, unsigned long long min_above,
-                            HeadSmem* s, unsigned long long& akey, unsigned long long& bkey)
+// KT block sums at once, each with exactly the operations of block_sum (xor butterfly inside the warps, then
+// warp 0 adds the warp totals with the same butterfly): bit-identical to the stage kernels' per-tile sums.
+// Result t in out[t], valid in thread 0.
+__device__ __forceinline__ void block_sum_kt(const double (&acc)[KT], HeadSmem* s, double (&out)[KT])
 {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double v[KT];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) v[t] = warp_sum(acc[t]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < KT; ++t) s->red[t][w] = v[t];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int t = 0; t < KT; ++t) out[t] = warp_sum(lane < NW ? s->red[t][lane] : 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tail: the rank-th smallest (0-based) of the M listed RELATIVE keys (all below 2^42), whether the next
+// order statistic ties with it, and else the smallest listed key above it.  Entirely inside the CTA; every
+// thread gets the same answer.  L: shared memory.
+// ---------------------------------------------------------------------------------------------------
+__device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M, unsigned long long rank, HeadSmem* s,
+                                         unsigned long long& a_rel, bool& tie, bool& has_b, unsigned long long& b_rel)
+{
+    const unsigned tid = threadIdx.x;
     const unsigned long long rank0 = rank;
-    for (int p = p0; p < 6; ++p) {
+    unsigned long long prefix = 0ull, himask = ~0ull << 42;
+    bool found = false;
+    if (M <= (unsigned)CAND_DIRECT) {
+        // few keys (the usual case with the adaptive window): rank them directly, one key per thread
+        __syncthreads();
+        const unsigned long long my = tid < M ? L[tid] : ~0ull;
+        unsigned r = 0;
+        for (unsigned k = 0; k < M; ++k) { const unsigned long long o = L[k]; r += (o < my || (o == my && k < tid)) ? 1u : 0u; }
+        if (tid < M && (unsigned long long)r == rank) s->mn = my;
+        __syncthreads();
+        prefix = s->mn;
+        __syncthreads();
+        found = true;
+    }
+    for (int p = 2; p < 6 && !found; ++p) {
         const int shift = pass_shift(p), nbins = pass_bins(p);
         hist_clear(s);
-        for (unsigned i = threadIdx.x; i < M; i += HEAD_THREADS) {
+        for (unsigned i = tid; i < M; i += HEAD_THREADS) {
             unsigned long long key = L[i];
             if ((key & himask) == prefix) atomicAdd(&s->hist[(unsigned)((key >> shift) & (unsigned long long)(nbins - 1))], 1u);
         }
         __syncthreads();
         unsigned bin; unsigned long long before;
-        pick_bin(s->hist, false, nbins, rank, s, bin, before);
-        const unsigned in_bin = s->found_cnt;       // keys in the picked bin (read like found_bin: stable until the next pick_bin)
+        unsigned loc[SEL_BINS / HEAD_THREADS];
+        load_bins_shared(s->hist, nbins, loc);
+        pick_bin(loc, rank, s, bin, before);
+        const unsigned in_bin = s->found_cnt;
         prefix |= (unsigned long long)bin << shift;
         himask = pass_himask_after(p);
         rank -= before;
         if (in_bin <= 32u && p < 5) {
-            // few keys left (the usual case after one digit): gather them and rank them directly instead of
-            // running the remaining digit passes; same key, the exact select does not depend on how it is found
+            // few keys left: gather them and rank them directly instead of running the remaining digit passes
             __syncthreads();
-            if (threadIdx.x == 0) s->flag = 0u;
+            if (tid == 0) s->flag = 0u;
             __syncthreads();
-            for (unsigned i = threadIdx.x; i < M; i += HEAD_THREADS) {
+            for (unsigned i = tid; i < M; i += HEAD_THREADS) {
                 unsigned long long key = L[i];
                 if ((key & himask) == prefix) s->wmin[atomicAdd(&s->flag, 1u)] = key;
             }
             __syncthreads();
-            if (threadIdx.x < 32) {
+            if (tid < 32) {
                 const unsigned n = s->flag;
-                const unsigned long long my = threadIdx.x < n ? s->wmin[threadIdx.x] : ~0ull;
+                const unsigned long long my = tid < n ? s->wmin[tid] : ~0ull;
                 unsigned r = 0;
                 for (unsigned k = 0; k < n; ++k) {
                     const unsigned long long o = s->wmin[k];
-                    r += (o < my || (o == my && k < threadIdx.x)) ? 1u : 0u;
+                    r += (o < my || (o == my && k < tid)) ? 1u : 0u;
                 }
-                if (threadIdx.x < n && (unsigned long long)r == rank) s->mn = my;
+                if (tid < n && (unsigned long long)r == rank) s->mn = my;
             }
             __syncthreads();
             prefix = s->mn;
@@ -168,235 +230,306 @@ __device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M
             break;
         }
     }
-    akey = prefix;
+    a_rel = prefix;
     // #{keys <= v[j]} and min{key > v[j]} on the list
     unsigned cnt = 0; unsigned long long mn = ~0ull;
-    for (unsigned i = threadIdx.x; i < M; i += HEAD_THREADS) {
+    for (unsigned i = tid; i < M; i += HEAD_THREADS) {
         unsigned long long key = L[i];
-        if (key <= akey) cnt++; else mn = key < mn ? key : mn;
+        if (key <= a_rel) cnt++; else mn = key < mn ? key : mn;
     }
     cnt = warp_sum_u(cnt); mn = warp_min_u64(mn);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { s->wcnt[threadIdx.x >> 5] = cnt; s->wmin[threadIdx.x >> 5] = mn; }
+    if ((tid & 31) == 0) { s->part[tid >> 5] = cnt; s->wmin[tid >> 5] = mn; }
     __syncthreads();
     cnt = 0; mn = ~0ull;
-    for (int w = 0; w < HEAD_THREADS / 32; ++w) { cnt += s->wcnt[w]; mn = s->wmin[w] < mn ? s->wmin[w] : mn; }
+    for (int w = 0; w < NW; ++w) { cnt += s->part[w]; mn = s->wmin[w] < mn ? s->wmin[w] : mn; }
     __syncthreads();
-    if ((unsigned long long)cnt >= rank0 + 2) bkey = akey;          // v[j+1] ties with v[j]
-    else bkey = (mn != ~0ull) ? mn : min_above;
+    tie = (unsigned long long)cnt >= rank0 + 2;          // v[j+1] ties with v[j]
+    has_b = mn != ~0ull;
+    b_rel = mn;
 }
 
-// ---------------------------------------------------------------------------------------
-// sharded runs (exchange 1 and 2): CTA 0 turns this rank's partial results into the
-// whole population's, in place, over NVLink peer memory (comm.cuh); the caller wraps each of these in
-// grid barriers.  Integer sums and rank-ordered FP64 sums: bit-identical on every rank.
-// ---------------------------------------------------------------------------------------
-// H[0..nbins) += every other rank's histogram; optionally global extrema(delta) and the sticky error
-__device__ __noinline__ void head_xchg_hist(const PopDev& P, Ctrl* c, unsigned* H, int nbins, bool first, HeadSmem* s)
+// ---------------------------------------------------------------------------------------------------
+// sharded runs: flag-in-word exchanges in which every CTA takes part (comm.cuh has the word format).
+// `seq` is the exchange's sequence number; every CTA of every rank counts the same sequence of exchanges
+// from the value X.seq[1] held at kernel start, so nobody has to publish it inside the kernel.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long* hg_base(const XchgDev& X)
 {
-    const unsigned tid = threadIdx.x;
-    if (tid == 0 && first) {
-        int e0 = c->err, e1 = __ldcg(&c->acc.err);
-        s->xh[0] = __ldcg(&c->acc.dmin_key); s->xh[1] = __ldcg(&c->acc.dmax_key);
-        s->xh[2] = (unsigned long long)(e0 > e1 ? e0 : e1);
-    }
-    __syncthreads();
-    xchg_ll_block(P.x, c, s->xh, first ? 3 : 0, H, nbins, s->xall, &s->xflag);
-    if (tid == 0 && first) {
-        unsigned long long mn = ~0ull, mx = 0ull, e = 0ull;
-        for (int r = 0; r < P.x.world; ++r) {
-            unsigned long long a = s->xall[3 * r], b = s->xall[3 * r + 1], er = s->xall[3 * r + 2];
-            mn = a < mn ? a : mn; mx = b > mx ? b : mx; e = er > e ? er : e;
-        }
-        __stcg(&c->acc.dmin_key, mn); __stcg(&c->acc.dmax_key, mx);
-        if (e) { c->acc.err = (int)e; if (!c->err) c->err = (int)e; }
-    }
+    return reinterpret_cast<unsigned long long*>(X.mbox[X.rank] + XCHG_HG_OFF);
 }
-
-// candidate-list bookkeeping of generation g: global count / extrema / min-above into c->acc.g_*; when the
-// global list fits the per-CTA tail (and is not all-equal) this rank's candidates are posted into every
-// rank's mailbox (XCHG_GCAND_OFF), where every CTA of every rank collects the same multiset for the tail
-__device__ __noinline__ void head_xchg_cands(const PopDev& P, Ctrl* c, int g, HeadSmem* s)
+__device__ __forceinline__ unsigned long long* gcand_region(char* mbox, int src)
 {
-    const unsigned tid = threadIdx.x;
-    if (tid == 0) {
-        s->xh[0] = __ldcg(&c->acc.cand_count[g]); s->xh[1] = __ldcg(&c->acc.cand_min[g]);
-        s->xh[2] = __ldcg(&c->acc.cand_max[g]); s->xh[3] = __ldcg(&c->acc.min_above);
-    }
-    __syncthreads();
-    xchg_ll_block(P.x, c, s->xh, 4, nullptr, 0, s->xall, &s->xflag);
-    unsigned long long M = 0ull, off = 0ull, mn = ~0ull, mx = 0ull, mab = ~0ull;
-    for (int r = 0; r < P.x.world; ++r) {
-        unsigned long long m = s->xall[4 * r], a = s->xall[4 * r + 1], b = s->xall[4 * r + 2], ab = s->xall[4 * r + 3];
-        if (r < P.x.rank) off += m;
-        M += m; mn = a < mn ? a : mn; mx = b > mx ? b : mx; mab = ab < mab ? ab : mab;
-    }
-    if (tid == 0) {
-        c->acc.g_cand_count = M; c->acc.g_cand_min = mn; c->acc.g_cand_max = mx; c->acc.g_min_above = mab;
-        c->acc.g_cand_off = off;
-    }
-    if (M <= (unsigned long long)XCHG_GCAND && mn != mx)                   // uniform over ranks
-        ll_post_keys(P.x, P.cand[g & 1], (unsigned)s->xh[0], (unsigned)off);
-    __syncthreads();
+    return reinterpret_cast<unsigned long long*>(mbox + XCHG_GCAND_OFF) + 2 * (size_t)src * XCHG_GCAND_PER;
 }
 
-// all-gather of the nw-word record the caller put into s->xh (thread 0): rank r's words at s->xall[nw*r ...]
-__device__ __noinline__ void head_xchg_rec(const PopDev& P, Ctrl* c, int nw, HeadSmem* s)
+// post: CTA `role` of this rank stores the record (nh 64-bit header values + an nb-bin histogram from global
+// memory, either may be 0) into the mailbox of rank `role`.  Called by all threads of the CTAs whose role
+// loop covers role < world.
+__device__ __forceinline__ void post_record(const XchgDev& X, int to, unsigned long long seq, const unsigned long long* hdr, int nh,
+                                            const unsigned* H, int nb)
 {
-    __syncthreads();
-    xchg_ll_block(P.x, c, s->xh, nw, nullptr, 0, s->xall, &s->xflag);
+    const unsigned slot = (unsigned)(seq & (XCHG_RING - 1)), flag = (unsigned)seq;
+    unsigned long long* e = ll_entry(X.mbox[to], slot, X.rank);
+    const int tid = threadIdx.x;
+    if (tid < 2 * nh) st_relaxed_sys(e + tid, ll_pack((unsigned)(hdr[tid >> 1] >> (32 * (tid & 1))), flag));
+    for (int k = tid; k < nb; k += HEAD_THREADS) st_relaxed_sys(e + LL_HDR + k, ll_pack(__ldcg(&H[k]), flag));
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(const __grid_constant__ PopDev P)
+// collect: every thread polls the nh header values of every rank out of the local mailbox: out[r * nh + k]
+// (each thread its own copy in registers would cost too many; thread t < world * nh polls value t into shared
+// memory).  Ends with a CTA barrier.
+__device__ __forceinline__ void collect_headers(const XchgDev& X, Ctrl* c, unsigned long long seq, int nh, unsigned long long* out, bool& ok)
+{
+    const unsigned slot = (unsigned)(seq & (XCHG_RING - 1)), flag = (unsigned)seq;
+    const int tid = threadIdx.x;
+    if (tid < X.world * nh) {
+        const int r = tid / nh, k = tid - r * nh;
+        const unsigned long long* e = ll_entry(X.mbox[X.rank], slot, r) + 2 * k;
+        const unsigned lo = ll_poll(e, flag, ok), hi = ll_poll(e + 1, flag, ok);
+        out[tid] = ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(const __grid_constant__ PopDev P, const unsigned per)
 {
     Ctrl* c = P.ctrl;
     if (c->stop) return;                                    // uniform: nobody reaches a grid barrier
     cg::grid_group grid = cg::this_grid();
     __shared__ HeadSmem s;
+    __shared__ unsigned long long s_x[XCHG_MAXR * 8];       // exchanged header records: every rank's
+    __shared__ unsigned long long s_h[4];                   // ... and this rank's, before it is posted
     const unsigned G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const uint32_t N = P.N, ntiles = P.ntiles;
-    const unsigned t0 = (unsigned)((unsigned long long)blockIdx.x * ntiles / G);
-    const unsigned t1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * ntiles / G);
+    const unsigned t0 = blockIdx.x * per < ntiles ? blockIdx.x * per : ntiles;
+    const unsigned t1 = t0 + per < ntiles ? t0 + per : ntiles;
+    const unsigned rounds = (per + KT - 1) / KT;
+    const bool single = rounds == 1;                        // the CTA's whole share stays in registers
     // schedule scalars of the previous iteration (CTA 0 overwrites them after the third barrier)
     const int cur = c->cur, kind = c->kind;
     const double eps_prev = c->eps, eps_old = c->eps_k, eps_target = c->eps_target, q_gamma = c->q_gamma;
     const unsigned n_alive_prev = c->n_alive_g;
+    const int win_shift_in = c->win_shift;
     const bool sharded = P.x.world > 1;
+    const int R = P.x.world;
+    unsigned long long seq = sharded ? __ldcg(P.x.seq + 1) : 0ull;
+    bool xok = true;
     const double* __restrict__ dl = P.delta[cur];
     unsigned* H1 = P.sel_hist; unsigned* H2 = P.sel_hist + SEL_BINS; unsigned* HW = P.sel_hist + 6 * SEL_BINS;
     unsigned long long rank = c->sel_rank;
     const unsigned long long rank_all = rank;
 
-    // ---- first pass over every alive key (+ extrema(delta) over all particles, NaN check) --------------
-    // Windowed digit: every alive distance lies in the support of the previous kernel, i.e. at or below eps_prev,
-    // and the alpha-quantile sits in the top two binades below it in all but degenerate populations.  So the
-    // first digit is the 22-bit key prefix (sign, exponent, 10 mantissa bits) RELATIVE to eps_prev's: bins
-    // 1..2046 are the 2046 prefixes up to and including eps_prev's own, bin 0 collects everything below the
-    // window and bin 2047 everything above it.  The map is monotone, so the select stays exact: when the rank
-    // falls into one of the single-prefix bins, 22 bits of v[j] are known after ONE pass (the generic scheme
-    // needs two: its leading 11-bit digit is the same for almost all distances); when it falls into a
-    // collecting bin (or eps_prev is not finite: first iteration) the generic two passes run instead.
+    // ---- this CTA's share -------------------------------------------------------------------------------
+    double v[KE]; uint32_t al[KT];
+    auto fetch = [&](unsigned r) {
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            const unsigned tile = t0 + r * KT + t;
+            if (tile < t1) {
+                const size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
+                load4_f64(dl, i0, N, &v[4 * t]);
+                al[t] = load4_u8(P.alive, i0, N);
+            } else {
+                al[t] = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[4 * t + k] = 0.0;
+            }
+        }
+    };
+    auto in_range = [&](unsigned r, int t, int k) -> bool {
+        const unsigned tile = t0 + r * KT + t;
+        return tile < t1 && (size_t)tile * TILE + (size_t)tid * 4 + k < N;
+    };
+    if (single) fetch(0);
+
+    // ---- first pass: window histogram (+ extrema(delta) over all particles, NaN check) ---------------------
+    // bin 2047 - ((kp - key) >> sh) for the 2047 * 2^sh keys at and below kp = key(eps_prev); bin 0 collects
+    // everything further below, keys above kp are counted apart.  The map is monotone: an exact select.
     const bool windowed = isfinite(eps_prev) && eps_prev > 0.0;
-    const unsigned long long wbase = (f64_key(windowed ? eps_prev : 1.0) >> 42) - 2046ull;
-    auto first_pass = [&](bool win, unsigned* H) {
+    const unsigned long long kp = f64_key(windowed ? eps_prev : 1.0);
+    const int sh = (win_shift_in > 0 && win_shift_in <= 43) ? win_shift_in - 1 : 42;
+    unsigned bin; unsigned long long before;
+    unsigned long long lo_key = 0ull, hi_key = 0ull;        // the candidates' key range (inclusive)
+    bool have_range = false;
+    {
         hist_clear(&s);
         unsigned long long kmn = ~0ull, kmx = 0ull; int nan_seen = 0;
-        for (unsigned tile = t0; tile < t1; ++tile) {
-            size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-            double v[4];
-            load4_f64(dl, i0, N, v);
-            uint32_t al = load4_u8(P.alive, i0, N);
+        unsigned n_low = 0;
+        for (unsigned r = 0; r < rounds; ++r) {
+            if (!single) fetch(r);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                bool ok = (al >> (8 * k)) & 0xff;
-                unsigned long long key = f64_key(v[k]);
-                if (i0 + k < N) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
-                if (ok && isnan(v[k])) nan_seen = 1;
-                unsigned digit;
-                if (win) {
-                    // (window digits are spread over ~10^3 bins: plain shared-memory atomics; the generic leading digit
-                    // is the same for almost every key: warp-aggregated)
-                    const unsigned long long d = key >> 42;
-                    digit = d <= wbase ? 0u : (d - wbase >= 2047ull ? 2047u : (unsigned)(d - wbase));
-                    if (ok) atomicAdd(&s.hist[digit], 1u);
-                } else {
-                    digit = (unsigned)(key >> 53);
-                    hist_add(s.hist, ok, digit);
+            for (int t = 0; t < KT; ++t) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ok = (al[t] >> (8 * k)) & 0xff;
+                    const double x = v[4 * t + k];
+                    const unsigned long long key = f64_key(x);
+                    if (in_range(r, t, k)) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
+                    if (ok && isnan(x)) nan_seen = 1;
+                    if (windowed) {
+                        if (ok && key <= kp) {                                 // (keys above kp stay outside the window's total)
+                            const unsigned long long dd = (kp - key) >> sh;
+                            if (dd >= 2047ull) n_low++;                      // most keys: counted in a register
+                            else atomicAdd(&s.hist[2047u - (unsigned)dd], 1u);
+                        }
+                    } else {
+                        hist_add(s.hist, ok, (unsigned)(key >> 53));           // generic pass 1: digit 53..63
+                    }
                 }
             }
         }
         if (tid == 0) { s.mn = ~0ull; s.mx = 0ull; }
         __syncthreads();
         kmn = warp_min_u64(kmn); kmx = warp_max_u64(kmx);
-        if (lane == 0) { atomicMin(&s.mn, kmn); atomicMax(&s.mx, kmx); }
-        if (nan_seen) atomicMax(&c->acc.err, (int)ABCDEZ_ERR_NAN_DISTANCE);
-        hist_flush(&s, H, 2048);
-        if (tid == 0) { atomicMin(&c->acc.dmin_key, s.mn); atomicMax(&c->acc.dmax_key, s.mx); }
-    };
-    unsigned bin; unsigned long long before;
-    unsigned long long prefix = 0ull, himask = 0ull;
-    bool have22 = false;
-    if (windowed) {
-        first_pass(true, HW);
-        grid.sync();
-        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, HW, 2048, true, &s); grid.sync(); }
-        pick_bin(HW, true, 2048, rank, &s, bin, before);
-        if (blockIdx.x == 0 && tid == 0) patch_extrema(P, c);   // ranges_eps of the previous record, :363
-        if (bin == 0xffffffffu) {                           // empty alive set (uniform decision)
-            grid.sync();                                    // every CTA has read HW
-            if (blockIdx.x == 0 && tid == 0 && !c->err) c->err = ABCDEZ_ERR_NO_ALIVE;
-            if (blockIdx.x == 0) for (int b = tid; b < SEL_BINS; b += HEAD_THREADS) HW[b] = 0u;
-            return;
+        n_low = warp_sum_u(n_low);
+        if (lane == 0) {
+            atomicMin(&s.mn, kmn); atomicMax(&s.mx, kmx);
+            if (n_low) atomicAdd(&s.hist[0], n_low);
         }
-        if (bin >= 1u && bin <= 2046u) {
-            prefix = (wbase + (unsigned long long)bin) << 42; himask = ~0ull << 42;
+        if (nan_seen) atomicMax(&c->acc.err, (int)ABCDEZ_ERR_NAN_DISTANCE);
+        hist_flush(&s, windowed ? HW : H1, 2048);
+        if (tid == 0) { atomicMin(&c->acc.dmin_key, s.mn); atomicMax(&c->acc.dmax_key, s.mx); }
+    }
+    grid.sync();                                                                                   // ---- barrier 1
+    // the whole population's histogram: bins tid*8 .. tid*8+7 into registers
+    unsigned loc[SEL_BINS / HEAD_THREADS];
+    auto all_reduce_hist = [&](unsigned* H, int nbins, bool first) {
+        // sharded: header (extrema, error, n_above) + histogram -> every rank; reducer CTAs sum 256 bins each into the
+        // local flag-in-word array, every CTA reads the sums from there (no second grid barrier)
+        ++seq;
+        const unsigned slot = (unsigned)(seq & (XCHG_RING - 1)), flag = (unsigned)seq;
+        if (tid == 0) {
+            int e0 = c->err, e1 = __ldcg(&c->acc.err);
+            s_h[0] = __ldcg(&c->acc.dmin_key); s_h[1] = __ldcg(&c->acc.dmax_key);
+            s_h[2] = (unsigned long long)(e0 > e1 ? e0 : e1); s_h[3] = 0ull;
+        }
+        __syncthreads();
+        for (int role = blockIdx.x; role < R; role += G) post_record(P.x, role, seq, s_h, first ? 4 : 0, H, nbins);
+        unsigned long long* hg = hg_base(P.x);
+        for (int role = blockIdx.x; role < SEL_BINS / HEAD_THREADS; role += G) {       // 8 reducer roles x 256 bins
+            const int b = role * HEAD_THREADS + tid;
+            if (b < nbins) {
+                unsigned tot = 0;
+                for (int r = 0; r < R; ++r) tot += ll_poll(ll_entry(P.x.mbox[P.x.rank], slot, r) + LL_HDR + b, flag, xok);
+                st_relaxed_sys(hg + b, ll_pack(tot, flag));
+            }
+        }
+        if (first) collect_headers(P.x, c, seq, 4, s_x, xok);
+#pragma unroll
+        for (int k = 0; k < SEL_BINS / HEAD_THREADS; ++k) {
+            const int b = tid * (SEL_BINS / HEAD_THREADS) + k;
+            loc[k] = b < nbins ? ll_poll(hg + b, flag, xok) : 0u;
+        }
+    };
+    auto first_exchange = [&](unsigned* H) {
+        if (sharded) {
+            all_reduce_hist(H, 2048, true);
+            unsigned long long mn = ~0ull, mx = 0ull, e = 0ull;
+            for (int r = 0; r < R; ++r) {
+                mn = s_x[4 * r] < mn ? s_x[4 * r] : mn; mx = s_x[4 * r + 1] > mx ? s_x[4 * r + 1] : mx;
+                e = s_x[4 * r + 2] > e ? s_x[4 * r + 2] : e;
+            }
+            if (blockIdx.x == 0 && tid == 0) {
+                __stcg(&c->acc.dmin_key, mn); __stcg(&c->acc.dmax_key, mx);
+                if (e) { c->acc.err = (int)e; if (!c->err) c->err = (int)e; }
+            }
+        } else {
+            load_bins_global(H, 2048, loc);
+        }
+        if (blockIdx.x == 0 && tid == 0) patch_extrema(P, c);                  // ranges_eps of the previous record, :363
+    };
+    unsigned long long prefix = 0ull, himask = 0ull;
+    if (windowed) {
+        first_exchange(HW);
+        pick_bin(loc, rank, &s, bin, before);
+        if (bin >= 1u && bin != 0xffffffffu) {              // inside the window
+            const unsigned long long dd = 2047ull - bin;
+            hi_key = kp - (dd << sh);
+            const unsigned long long span = (dd + 1ull) << sh;
+            lo_key = kp >= span ? kp - span + 1ull : 0ull;
             rank -= before;
-            have22 = true;
+            have_range = true;
         }
     }
-    if (!have22) {
-        // ---- generic pass 1: digit 53..63 --------------------------------------------------------------
+    if (!have_range) {
+        // ---- generic path: two 11-bit digit passes (first iteration, or the rank fell outside the window) -----
         rank = rank_all;
-        first_pass(false, H1);
-        grid.sync();
-        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H1, 2048, !windowed, &s); grid.sync(); }
-        pick_bin(H1, true, 2048, rank, &s, bin, before);
-        if (!windowed && blockIdx.x == 0 && tid == 0) patch_extrema(P, c);   // ranges_eps of the previous record, :363
+        if (windowed) {
+            // the window pass has the extrema already; this pass only builds the leading-digit histogram
+            hist_clear(&s);
+            for (unsigned r = 0; r < rounds; ++r) {
+                if (!single) fetch(r);
+#pragma unroll
+                for (int t = 0; t < KT; ++t)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        hist_add(s.hist, (al[t] >> (8 * k)) & 0xff, (unsigned)(f64_key(v[4 * t + k]) >> 53));
+            }
+            hist_flush(&s, H1, 2048);
+            grid.sync();
+            if (sharded) all_reduce_hist(H1, 2048, false); else load_bins_global(H1, 2048, loc);
+        } else {
+            first_exchange(H1);
+        }
+        pick_bin(loc, rank, &s, bin, before);
         if (bin == 0xffffffffu) {                           // empty alive set (uniform decision)
-            grid.sync();                                    // every CTA has read H1
-            if (blockIdx.x == 0 && tid == 0 && !c->err) c->err = ABCDEZ_ERR_NO_ALIVE;
-            if (blockIdx.x == 0) for (int b = tid; b < SEL_BINS; b += HEAD_THREADS) { P.sel_hist[b] = 0u; HW[b] = 0u; }
+            grid.sync();                                    // every CTA has read the histograms
+            if (blockIdx.x == 0 && tid == 0) {
+                if (!c->err) c->err = ABCDEZ_ERR_NO_ALIVE;
+                if (sharded) __stcg(P.x.seq + 1, seq);
+            }
+            if (blockIdx.x == 0) for (int b = tid; b < 7 * SEL_BINS; b += HEAD_THREADS) P.sel_hist[b] = 0u;
             return;
         }
         prefix = (unsigned long long)bin << 53; himask = ~0ull << 53;
         rank -= before;
-
-        // ---- generic pass 2: digit 42..52 among the keys of that bin -----------------------------------
+        // generic pass 2: digit 42..52 among the keys of that bin
         hist_clear(&s);
-        for (unsigned tile = t0; tile < t1; ++tile) {
-            size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-            double v[4];
-            load4_f64(dl, i0, N, v);
-            uint32_t al = load4_u8(P.alive, i0, N);
+        for (unsigned r = 0; r < rounds; ++r) {
+            if (!single) fetch(r);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                unsigned long long key = f64_key(v[k]);
-                bool ok = ((al >> (8 * k)) & 0xff) && ((key & himask) == prefix);
-                hist_add(s.hist, ok, (unsigned)((key >> 42) & 2047ull));
-            }
+            for (int t = 0; t < KT; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned long long key = f64_key(v[4 * t + k]);
+                    const bool ok = ((al[t] >> (8 * k)) & 0xff) && ((key & himask) == prefix);
+                    hist_add(s.hist, ok, (unsigned)((key >> 42) & 2047ull));
+                }
         }
         hist_flush(&s, H2, 2048);
         grid.sync();
-        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H2, 2048, false, &s); grid.sync(); }
-        pick_bin(H2, true, 2048, rank, &s, bin, before);
-        prefix |= (unsigned long long)bin << 42; himask = ~0ull << 42;
+        if (sharded) all_reduce_hist(H2, 2048, false); else load_bins_global(H2, 2048, loc);
+        pick_bin(loc, rank, &s, bin, before);
+        prefix |= (unsigned long long)bin << 42;
         rank -= before;
+        lo_key = prefix; hi_key = prefix | ((1ull << 42) - 1ull);
     }
 
-    // ---- pass 3: compact the keys sharing the 22-bit prefix; min key above the prefix ----------------
-    unsigned long long* cand = P.cand[0];
+    // ---- compact the candidates (keys in [lo_key, hi_key], stored relative to lo_key: < 2^42); min key above ----
     {
+        unsigned long long* cand = P.cand[0];
         unsigned long long mab = ~0ull, cmn = ~0ull, cmx = 0ull;
-        for (unsigned tile = t0; tile < t1; ++tile) {
-            size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-            double v[4];
-            load4_f64(dl, i0, N, v);
-            uint32_t al = load4_u8(P.alive, i0, N);
+        for (unsigned r = 0; r < rounds; ++r) {
+            if (!single) fetch(r);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                unsigned long long key = f64_key(v[k]);
-                bool ok = (al >> (8 * k)) & 0xff;
-                unsigned long long hi = key & himask;
-                bool is_c = ok && hi == prefix;
-                if (ok && hi > prefix) mab = key < mab ? key : mab;
-                unsigned m = __ballot_sync(0xffffffffu, is_c);
-                if (m) {
-                    unsigned base = 0;
-                    if (lane == 0) base = (unsigned)atomicAdd(&c->acc.cand_count[0], (unsigned long long)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (is_c) {
-                        cand[base + __popc(m & ((1u << lane) - 1u))] = key;
-                        cmn = key < cmn ? key : cmn; cmx = key > cmx ? key : cmx;
+            for (int t = 0; t < KT; ++t) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned long long key = f64_key(v[4 * t + k]);
+                    const bool ok = (al[t] >> (8 * k)) & 0xff;
+                    const bool is_c = ok && key >= lo_key && key <= hi_key;
+                    if (ok && key > hi_key) mab = key < mab ? key : mab;
+                    const unsigned m = __ballot_sync(0xffffffffu, is_c);
+                    if (m) {
+                        unsigned base = 0;
+                        if (lane == 0) base = (unsigned)atomicAdd(&c->acc.cand_count[0], (unsigned long long)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (is_c) {
+                            const unsigned long long rk = key - lo_key;
+                            cand[base + __popc(m & ((1u << lane) - 1u))] = rk;
+                            cmn = rk < cmn ? rk : cmn; cmx = rk > cmx ? rk : cmx;
+                        }
                     }
                 }
             }
@@ -411,19 +544,54 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             if (s.mn != ~0ull) { atomicMin(&c->acc.cand_min[0], s.mn); atomicMax(&c->acc.cand_max[0], s.mx); }
         }
     }
-    grid.sync();
-    if (sharded) { if (blockIdx.x == 0) head_xchg_cands(P, c, 0, &s); grid.sync(); }
-    // candidate-list generation g: list P.cand[g & 1], accumulators cand_count/min/max[g] (reset after the run).
-    // M: this rank's candidates; Mg, cmin, cmax, min_above: the whole population's
-    int p_next = 2, g = 0;
-    unsigned M = (unsigned)__ldcg(&c->acc.cand_count[0]);
-    unsigned long long Mg = sharded ? __ldcg(&c->acc.g_cand_count) : (unsigned long long)M;
-    unsigned long long cmin = sharded ? __ldcg(&c->acc.g_cand_min) : __ldcg(&c->acc.cand_min[0]);
-    unsigned long long cmax = sharded ? __ldcg(&c->acc.g_cand_max) : __ldcg(&c->acc.cand_max[0]);
-    unsigned long long min_above = sharded ? __ldcg(&c->acc.g_min_above) : __ldcg(&c->acc.min_above);
+    grid.sync();                                                                                   // ---- barrier 2
+    // candidate-list generation g: list P.cand[g & 1] (relative keys), accumulators cand_count/min/max[g].
+    // M: this rank's candidates; Mg, cmin, cmax, min_above: the whole population's.  Sharded: CTA q posts this
+    // rank's counts (and its keys while they fit its region of the gather area) to rank q; every CTA collects.
+    int g = 0, p_next = 2;
+    unsigned M = 0; unsigned long long Mg = 0, cmin = ~0ull, cmax = 0ull, min_above = ~0ull;
+    bool need_refine = false;                               // the candidates do not fit the per-CTA tail yet
+    auto exchange_cands = [&]() {
+        M = (unsigned)__ldcg(&c->acc.cand_count[g]);
+        if (!sharded) {
+            Mg = M; cmin = __ldcg(&c->acc.cand_min[g]); cmax = __ldcg(&c->acc.cand_max[g]); min_above = __ldcg(&c->acc.min_above);
+            need_refine = Mg > (unsigned long long)CAND_SMEM;
+            return;
+        }
+        ++seq;
+        const unsigned flag = (unsigned)seq;
+        if (tid == 0) {
+            s_h[0] = M; s_h[1] = __ldcg(&c->acc.cand_min[g]); s_h[2] = __ldcg(&c->acc.cand_max[g]); s_h[3] = __ldcg(&c->acc.min_above);
+        }
+        __syncthreads();
+        for (int role = blockIdx.x; role < R; role += G) {
+            post_record(P.x, role, seq, s_h, 4, nullptr, 0);
+            if (M <= (unsigned)XCHG_GCAND_PER) {
+                unsigned long long* gr = gcand_region(P.x.mbox[role], P.x.rank);
+                const unsigned long long* src = P.cand[g & 1];
+                for (unsigned i = tid; i < M; i += HEAD_THREADS) {
+                    const unsigned long long key = __ldcg(&src[i]);
+                    st_relaxed_sys(gr + 2 * i, ll_pack((unsigned)key, flag));
+                    st_relaxed_sys(gr + 2 * i + 1, ll_pack((unsigned)(key >> 32), flag));
+                }
+            }
+        }
+        collect_headers(P.x, c, seq, 4, s_x, xok);
+        Mg = 0; cmin = ~0ull; cmax = 0ull; min_above = ~0ull;
+        bool fits = true;
+        for (int r = 0; r < R; ++r) {
+            const unsigned long long m = s_x[4 * r];
+            Mg += m; fits = fits && m <= (unsigned long long)XCHG_GCAND_PER;
+            cmin = s_x[4 * r + 1] < cmin ? s_x[4 * r + 1] : cmin; cmax = s_x[4 * r + 2] > cmax ? s_x[4 * r + 2] : cmax;
+            min_above = s_x[4 * r + 3] < min_above ? s_x[4 * r + 3] : min_above;
+        }
+        need_refine = !(fits && Mg <= (unsigned long long)CAND_SMEM);          // (uniform over ranks)
+    };
+    exchange_cands();
 
-    // ---- large candidate lists: refine grid-cooperatively, one digit per round -----------------------
-    while (Mg > (unsigned long long)CAND_SMEM && cmin != cmax && p_next < 6) {
+    // ---- large candidate lists: refine grid-cooperatively, one digit per round (rare with the adaptive window) ----
+    prefix = 0ull; himask = ~0ull << 42;                    // over relative keys from here on
+    while (need_refine && cmin != cmax && p_next < 6) {
         const int shift = pass_shift(p_next), nbins = pass_bins(p_next);
         unsigned* H = P.sel_hist + (size_t)p_next * SEL_BINS;
         const unsigned long long* src = P.cand[g & 1]; unsigned long long* dst = P.cand[(g + 1) & 1];
@@ -432,20 +600,20 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             atomicAdd(&s.hist[(unsigned)((__ldcg(&src[i]) >> shift) & (unsigned long long)(nbins - 1))], 1u);
         hist_flush(&s, H, nbins);
         grid.sync();
-        if (sharded) { if (blockIdx.x == 0) head_xchg_hist(P, c, H, nbins, false, &s); grid.sync(); }
-        pick_bin(H, true, nbins, rank, &s, bin, before);
+        if (sharded) all_reduce_hist(H, nbins, false); else load_bins_global(H, nbins, loc);
+        pick_bin(loc, rank, &s, bin, before);
         prefix |= (unsigned long long)bin << shift; himask = pass_himask_after(p_next);
         rank -= before;
         {
             unsigned long long mab = ~0ull, cmn = ~0ull, cmx = 0ull;
-            size_t rounds = ((size_t)M + (size_t)G * HEAD_THREADS - 1) / ((size_t)G * HEAD_THREADS);
-            for (size_t r = 0; r < rounds; ++r) {
-                size_t i = r * (size_t)G * HEAD_THREADS + (size_t)blockIdx.x * HEAD_THREADS + tid;
-                unsigned long long key = i < M ? __ldcg(&src[i]) : 0ull;
-                unsigned long long hi = key & himask;
-                bool is_c = i < M && hi == prefix;
+            const size_t rnds = ((size_t)M + (size_t)G * HEAD_THREADS - 1) / ((size_t)G * HEAD_THREADS);
+            for (size_t r = 0; r < rnds; ++r) {
+                const size_t i = r * (size_t)G * HEAD_THREADS + (size_t)blockIdx.x * HEAD_THREADS + tid;
+                const unsigned long long key = i < M ? __ldcg(&src[i]) : 0ull;
+                const unsigned long long hi = key & himask;
+                const bool is_c = i < M && hi == prefix;
                 if (i < M && hi > prefix) mab = key < mab ? key : mab;
-                unsigned m = __ballot_sync(0xffffffffu, is_c);
+                const unsigned m = __ballot_sync(0xffffffffu, is_c);
                 if (m) {
                     unsigned base = 0;
                     if (lane == 0) base = (unsigned)atomicAdd(&c->acc.cand_count[g + 1], (unsigned long long)__popc(m));
@@ -458,30 +626,41 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             }
             mab = warp_min_u64(mab); cmn = warp_min_u64(cmn); cmx = warp_max_u64(cmx);
             if (lane == 0) {
-                if (mab != ~0ull) atomicMin(&c->acc.min_above, mab);
+                if (mab != ~0ull) atomicMin(&c->acc.min_above, lo_key + mab);     // (absolute, like the first generation's)
                 if (cmn != ~0ull) { atomicMin(&c->acc.cand_min[g + 1], cmn); atomicMax(&c->acc.cand_max[g + 1], cmx); }
             }
         }
         grid.sync();
         g++; p_next++;
-        if (sharded) { if (blockIdx.x == 0) head_xchg_cands(P, c, g, &s); grid.sync(); }
-        M = (unsigned)__ldcg(&c->acc.cand_count[g]);
-        Mg = sharded ? __ldcg(&c->acc.g_cand_count) : (unsigned long long)M;
-        cmin = sharded ? __ldcg(&c->acc.g_cand_min) : __ldcg(&c->acc.cand_min[g]);
-        cmax = sharded ? __ldcg(&c->acc.g_cand_max) : __ldcg(&c->acc.cand_max[g]);
-        min_above = sharded ? __ldcg(&c->acc.g_min_above) : __ldcg(&c->acc.min_above);
+        exchange_cands();
     }
 
     // ---- tail: v[j], tie test, v[j+1], type-7 interpolation, clamp (every CTA, same integers) ---------
     unsigned long long akey, bkey;
     if (cmin == cmax) {                                     // all candidates equal (discrete distances, ties)
-        akey = cmin;
+        akey = lo_key + cmin;
         bkey = (rank + 1 < Mg) ? akey : min_above;
     } else {                                                // Mg <= CAND_SMEM (after p_next == 6 all keys are equal)
-        if (sharded) ll_collect_keys(P.x, c, (unsigned)Mg, s.cand);        // every rank's candidates, from the local mailbox
-        else { for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&P.cand[g & 1][i]); }
+        if (sharded) {
+            // every rank's candidates, from the local gather area: rank r's keys at its region, its count in s_x
+            const unsigned flag = (unsigned)seq;
+            unsigned off = 0;
+            for (int r = 0; r < R; ++r) {
+                const unsigned m = (unsigned)s_x[4 * r];
+                const unsigned long long* gr = gcand_region(P.x.mbox[P.x.rank], r);
+                for (unsigned i = tid; i < m; i += HEAD_THREADS) {
+                    const unsigned lo = ll_poll(gr + 2 * i, flag, xok), hi = ll_poll(gr + 2 * i + 1, flag, xok);
+                    s.cand[off + i] = ((unsigned long long)hi << 32) | lo;
+                }
+                off += m;
+            }
+        } else { for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&P.cand[g & 1][i]); }
         __syncthreads();
-        tail_select(s.cand, (unsigned)Mg, p_next, prefix, himask, rank, min_above, &s, akey, bkey);
+        unsigned long long a_rel, b_rel; bool tie, has_b;
+        // after refine rounds the list holds the keys that match (prefix, himask); the rank is relative to them
+        tail_select(s.cand, (unsigned)Mg, rank, &s, a_rel, tie, has_b, b_rel);
+        akey = lo_key + a_rel;
+        bkey = tie ? akey : (has_b ? lo_key + b_rel : min_above);
     }
     double eps;
     {
@@ -489,48 +668,107 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         double b = (n_alive_prev <= 1 || bkey == ~0ull) ? a : key_f64(bkey);
         double q = (isfinite(a) && isfinite(b)) ? a + q_gamma * (b - a) : (1.0 - q_gamma) * a + q_gamma * b;
         eps = fmax(fmin(q, eps_prev), eps_target);          // :301
-        if (blockIdx.x == 0 && tid == 0) { c->q_a = a; c->q_b = b; c->q = q; c->eps = eps; c->sel_prefix = akey; }
-    }
-
-    // ---- reweight pass A: ws, wprod (unnormalised, kept in W), per-tile sums -------------------------
-    for (unsigned tile = t0; tile < t1; ++tile) {
-        size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-        double v[4], w[4];
-        load4_f64(dl, i0, N, v);
-        load4_f64(P.W, i0, N, w);
-        uint32_t al = load4_u8(P.alive, i0, N);
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            bool ok = ((al >> (8 * k)) & 0xff) && (i0 + k < N);
-            double ws = 0.0;
-            if (ok) ws = abck_ws(kind, eps, eps_old, v[k]);                                              // :75
-            w[k] = ok ? w[k] * ws : 0.0;                                                          // :308
-            acc += w[k];
-        }
-        store4_f64(P.W, i0, N, w);
-        double t = block_sum(acc, s.red);
-        if (tid == 0) P.partial[tile] = t;
-    }
-    grid.sync();
-    double wnorm;
-    {
-        double a = 0.0;
-        for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) a += __ldcg(&P.partial[b]);
-        wnorm = block_sum_all(a, &s);                                                             // :309
-    }
-    if (sharded) {                                          // wnorm = sum over ranks, rank order (exchange 2)
-        if (blockIdx.x == 0) {
-            if (tid == 0) s.xh[0] = (unsigned long long)__double_as_longlong(wnorm);
-            head_xchg_rec(P, c, 1, &s);
-            if (tid == 0) {
-                double tot = 0.0;
-                for (int r = 0; r < P.x.world; ++r) tot += __longlong_as_double((long long)s.xall[r]);
-                c->acc.g_wnorm = tot;
+        if (blockIdx.x == 0 && tid == 0) {
+            c->q_a = a; c->q_b = b; c->q = q; c->eps = eps; c->sel_prefix = akey;
+            // the next select's window: ~512-1023 bins between this threshold and the next quantile, if the
+            // population keeps contracting at this rate in key space
+            if (windowed && eps > 0.0 && eps < eps_prev) {
+                const unsigned long long gap = kp - f64_key(eps);
+                int sn = 63 - __clzll((long long)gap) - 9;
+                sn = sn < 0 ? 0 : (sn > 42 ? 42 : sn);
+                c->win_shift = sn + 1;
             }
         }
-        grid.sync();
-        wnorm = __ldcg(&c->acc.g_wnorm);
+    }
+
+    // ---- reweight pass A: ws, wprod, per-tile sums and alive counts ------------------------------------
+    double w[KE];
+    auto fetch_w = [&](unsigned r) {
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            const unsigned tile = t0 + r * KT + t;
+            if (tile < t1) load4_f64(P.W, (size_t)tile * TILE + (size_t)tid * 4, N, &w[4 * t]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[4 * t + k] = 0.0;
+            }
+        }
+    };
+    for (unsigned r = 0; r < rounds; ++r) {
+        if (!single) fetch(r);
+        fetch_w(r);
+        double acc[KT]; unsigned cnt[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            acc[t] = 0.0; cnt[t] = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = ((al[t] >> (8 * k)) & 0xff) && in_range(r, t, k);
+                double ws = 0.0;
+                if (ok) ws = abck_ws(kind, eps, eps_old, v[4 * t + k]);                           // :75
+                const double wp_ = ok ? w[4 * t + k] * ws : 0.0;                                   // :308
+                w[4 * t + k] = wp_;
+                acc[t] += wp_;
+                cnt[t] += (wp_ > 0.0) ? 1u : 0u;
+            }
+            cnt[t] = warp_sum_u(cnt[t]);
+        }
+        if (!single) {
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                const unsigned tile = t0 + r * KT + t;
+                if (tile < t1) store4_f64(P.W, (size_t)tile * TILE + (size_t)tid * 4, N, &w[4 * t]);
+            }
+        }
+        double tsum[KT];
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < KT; ++t) s.wcnt[t][wp] = cnt[t];
+        }
+        block_sum_kt(acc, &s, tsum);                        // (its barriers also publish wcnt)
+        if (tid == 0) {
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                const unsigned tile = t0 + r * KT + t;
+                if (tile < t1) {
+                    unsigned tc = 0;
+                    for (int q = 0; q < NW; ++q) tc += s.wcnt[t][q];
+                    P.partial[tile] = tsum[t];
+                    P.tile_cnt[tile] = tc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    grid.sync();                                                                                   // ---- barrier 3
+    double wnorm;
+    unsigned n_alive, my_off;
+    {
+        double a = 0.0; unsigned tot = 0, pre = 0;
+        for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) {
+            a += __ldcg(&P.partial[b]);
+            const unsigned tc = __ldcg(&P.tile_cnt[b]);
+            tot += tc; if (b < t0) pre += tc;
+        }
+        wnorm = block_sum_all(a, &s);                                                             // :309
+        tot = warp_sum_u(tot); pre = warp_sum_u(pre);
+        if (lane == 0) { s.wcnt[0][wp] = tot; s.part[wp] = pre; }
+        __syncthreads();
+        n_alive = 0; my_off = 0;
+        for (int q = 0; q < NW; ++q) { n_alive += s.wcnt[0][q]; my_off += s.part[q]; }
+        __syncthreads();
+    }
+    unsigned n_alive_g = n_alive;
+    if (sharded) {                                          // wnorm = sum over ranks in rank order; alive counts of every rank
+        ++seq;
+        if (tid == 0) { s_h[0] = (unsigned long long)__double_as_longlong(wnorm); s_h[1] = (unsigned long long)n_alive; }
+        __syncthreads();
+        for (int role = blockIdx.x; role < R; role += G) post_record(P.x, role, seq, s_h, 2, nullptr, 0);
+        collect_headers(P.x, c, seq, 2, s_x, xok);
+        double tot = 0.0; unsigned ng = 0;
+        for (int r = 0; r < R; ++r) { tot += __longlong_as_double((long long)s_x[2 * r]); ng += (unsigned)s_x[2 * r + 1]; }
+        wnorm = tot; n_alive_g = ng;
+        if (blockIdx.x == 0 && tid < (unsigned)R) c->rank_alive[tid] = (unsigned)s_x[2 * tid + 1];
     }
     if (blockIdx.x == 0) {
         if (tid == 0) {
@@ -541,123 +779,139 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         for (int b = tid; b < 7 * SEL_BINS; b += HEAD_THREADS) P.sel_hist[b] = 0u;              // every reader is past them
     }
 
-    // ---- reweight pass B: Wns, alive, sum(Wns^2), alive counts per tile ------------------------------
+    // ---- pass B: Wns, alive, sum(Wns^2) per tile, alive-first particle list -- no further grid barrier ----
     double* partial2 = P.partial + ntiles;
-    for (unsigned tile = t0; tile < t1; ++tile) {
-        size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-        double w[4];
-        load4_f64(P.W, i0, N, w);
-        double acc = 0.0; unsigned cnt = 0; uint32_t al = 0; double wal = 0.0;
+    const bool need_list = n_alive != N;
+    unsigned off = my_off;
+    int mismatch = 0;
+    for (unsigned r = 0; r < rounds; ++r) {
+        if (!single) fetch_w(r);
+        double acc[KT]; uint32_t nal[KT]; double wal = 0.0; unsigned any = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < N) {
-                w[k] = w[k] / wnorm;                                                              // :310
-                bool a = (w[k] > 0.0);                                                            // :311
-                if (a) { al |= 1u << (8 * k); cnt++; wal = w[k]; }
-                acc += w[k] * w[k];
-            }
-        }
-        store4_f64(P.W, i0, N, w);
-        if (i0 + 3 < N) *reinterpret_cast<uint32_t*>(P.alive + i0) = al;
-        else { for (int k = 0; k < 4; ++k) if (i0 + k < N) P.alive[i0 + k] = (al >> (8 * k)) & 0xff; }
-        if (cnt) c->acc.w_alive = wal;          // indicator kernels: every alive weight is this same double
-        double t = block_sum(acc, s.red);
-        cnt = warp_sum_u(cnt);
-        if (lane == 0) s.wcnt[wp] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned tc = 0;
-            for (int q = 0; q < HEAD_THREADS / 32; ++q) tc += s.wcnt[q];
-            partial2[tile] = t;
-            P.tile_cnt[tile] = tc;
-        }
-        __syncthreads();
-    }
-    grid.sync();
-    double sumsq;
-    unsigned n_alive, my_off;
-    {
-        double a = 0.0; unsigned tot = 0, pre = 0;
-        for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) {
-            a += __ldcg(&partial2[b]);
-            unsigned tc = __ldcg(&P.tile_cnt[b]);
-            tot += tc; if (b < t0) pre += tc;
-        }
-        sumsq = block_sum_all(a, &s);
-        tot = warp_sum_u(tot); pre = warp_sum_u(pre);
-        if (lane == 0) { s.wcnt[wp] = tot; s.part[wp] = pre; }
-        __syncthreads();
-        n_alive = 0; my_off = 0;
-        for (int q = 0; q < HEAD_THREADS / 32; ++q) { n_alive += s.wcnt[q]; my_off += s.part[q]; }
-        __syncthreads();
-    }
-    if (sharded) {                                          // sum(Wns^2), alive counts, common alive weight (exchange 2)
-        if (blockIdx.x == 0) {
-            if (tid == 0) {
-                s.xh[0] = (unsigned long long)__double_as_longlong(sumsq); s.xh[1] = (unsigned long long)n_alive;
-                s.xh[2] = (unsigned long long)__double_as_longlong(__ldcg(&c->acc.w_alive));
-            }
-            head_xchg_rec(P, c, 3, &s);
-            if (tid == 0) {
-                double tot = 0.0; unsigned ng = 0;
-                for (int r = 0; r < P.x.world; ++r) {
-                    tot += __longlong_as_double((long long)s.xall[3 * r]);
-                    unsigned na = (unsigned)s.xall[3 * r + 1];
-                    c->rank_alive[r] = na; ng += na;
-                    if (na) __stcg(&c->acc.w_alive, __longlong_as_double((long long)s.xall[3 * r + 2]));   // same double on every rank
-                }
-                ctrl_after_reweight(P, c, tot, n_alive, ng);                                      // :318-324
-            }
-        }
-    } else if (blockIdx.x == 0 && tid == 0) ctrl_after_reweight(P, c, sumsq, n_alive, n_alive);   // :318-324
-
-    // ---- compaction: alive particles first (index order), the dead ones behind them ------------------
-    if (n_alive != N) {
-        unsigned off = my_off;
-        for (unsigned tile = t0; tile < t1; ++tile) {
-            size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-            uint32_t al = load4_u8(P.alive, i0, N);
-            unsigned cnt = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cnt += ((al >> (8 * k)) & 0xff) ? 1u : 0u;
-            unsigned incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            __syncthreads();
-            if (lane == 31) s.wcnt[wp] = incl;
-            __syncthreads();
-            unsigned woff = 0, ttot = 0;
-            for (int q = 0; q < HEAD_THREADS / 32; ++q) { if (q < (int)wp) woff += s.wcnt[q]; ttot += s.wcnt[q]; }
-            unsigned pos = off + woff + incl - cnt;                       // alive before element i0
-            unsigned dpos = n_alive + ((unsigned)i0 - pos);               // dead before element i0
+        for (int t = 0; t < KT; ++t) {
+            acc[t] = 0.0; nal[t] = 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (i0 + k < N) {
-                    if ((al >> (8 * k)) & 0xff) P.alive_list[pos++] = (uint32_t)(i0 + k);
-                    else P.alive_list[dpos++] = (uint32_t)(i0 + k);
+                if (in_range(r, t, k)) {
+                    const double wp_ = w[4 * t + k];
+                    const double q = wp_ / wnorm;                                                 // :310
+                    const bool a = (q > 0.0);                                                     // :311
+                    if (a != (wp_ > 0.0)) mismatch = 1;
+                    if (a) { nal[t] |= 1u << (8 * k); wal = q; any = 1; }
+                    acc[t] += q * q;
+                    w[4 * t + k] = q;
                 }
             }
-            off += ttot;
+            const unsigned tile = t0 + r * KT + t;
+            if (tile < t1) {
+                const size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
+                store4_f64(P.W, i0, N, &w[4 * t]);
+                if (i0 + 3 < N) *reinterpret_cast<uint32_t*>(P.alive + i0) = nal[t];
+                else { for (int k = 0; k < 4; ++k) if (i0 + k < N) P.alive[i0 + k] = (nal[t] >> (8 * k)) & 0xff; }
+            }
+        }
+        if (any) c->acc.w_alive = wal;          // indicator kernels: every alive weight is this same double
+        double tsum[KT];
+        block_sum_kt(acc, &s, tsum);
+        if (tid == 0) {
+#pragma unroll
+            for (int t = 0; t < KT; ++t) { const unsigned tile = t0 + r * KT + t; if (tile < t1) partial2[tile] = tsum[t]; }
+        }
+        if (need_list) {
+            // alive particles first (index order), the dead ones behind them
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                const unsigned tile = t0 + r * KT + t;
+                if (tile >= t1) break;
+                const size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
+                unsigned cnt = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cnt += ((nal[t] >> (8 * k)) & 0xff) ? 1u : 0u;
+                unsigned incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += u; }
+                __syncthreads();
+                if (lane == 31) s.part[wp] = incl;
+                __syncthreads();
+                unsigned woff = 0, ttot = 0;
+                for (int q = 0; q < NW; ++q) { if (q < (int)wp) woff += s.part[q]; ttot += s.part[q]; }
+                unsigned pos = off + woff + incl - cnt;                       // alive before element i0
+                unsigned dpos = n_alive + ((unsigned)i0 - pos);               // dead before element i0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (i0 + k < N) {
+                        if ((nal[t] >> (8 * k)) & 0xff) P.alive_list[pos++] = (uint32_t)(i0 + k);
+                        else P.alive_list[dpos++] = (uint32_t)(i0 + k);
+                    }
+                }
+                off += ttot;
+            }
+        }
+        __syncthreads();
+    }
+    if (mismatch) atomicMax(&c->acc.alive_mismatch, 1);
+    if (!xok) xchg_fail(c);
+
+    // ---- the last CTA to finish: ESS, the decisions of :318-324 -------------------------------------------
+    if (last_block(&c->acc.ticket[5], G)) {
+        double a = 0.0;
+        for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) a += __ldcg(&partial2[b]);
+        double sumsq = block_sum_all(a, &s);
+        if (sharded) {                                      // sum(Wns^2) in rank order, the common alive weight
+            ++seq;
+            if (tid < 32) {
+                unsigned long long rec[2] = { (unsigned long long)__double_as_longlong(sumsq),
+                                              (unsigned long long)__double_as_longlong(__ldcg(&c->acc.w_alive)) }, got[2];
+                const bool valid = xchg_ll_warp_seq<2>(P.x, c, seq, rec, got);
+                // lane r holds rank r's record: rank-ordered sum by lane 0
+                double tot = 0.0; double wal = 0.0; bool have = false;
+                for (int r = 0; r < R; ++r) {
+                    const unsigned long long s0 = __shfl_sync(0xffffffffu, got[0], r), s1 = __shfl_sync(0xffffffffu, got[1], r);
+                    tot += __longlong_as_double((long long)s0);
+                    if (!have && __ldcg(&c->rank_alive[r])) { wal = __longlong_as_double((long long)s1); have = true; }
+                }
+                (void)valid;
+                if (tid == 0) {
+                    if (have) __stcg(&c->acc.w_alive, wal);                  // same double on every rank
+                    sumsq = tot;
+                }
+            }
+            if (tid == 0) __stcg(P.x.seq + 1, seq);
+        }
+        if (tid == 0) {
+            // (wprod > 0) != (wprod / wnorm > 0) somewhere: weights far from normalised (never in a run); a NaN distance
+            // (reported as such) also lands here, and the larger code wins
+            if (__ldcg(&c->acc.alive_mismatch)) { c->acc.alive_mismatch = 0; atomicMax(&c->acc.err, (int)ABCDEZ_ERR_BAD_ARG); }
+            ctrl_after_reweight(P, c, sumsq, n_alive, n_alive_g);                                 // :318-324
         }
     }
 }
 
-static int g_head_blocks_per_sm = -1;
+// resident CTAs per SM of head_kernel, per device (cooperative launches need the whole grid resident)
+static int head_blocks_per_sm(int device)
+{
+    static int cache[64] = { 0 };
+    if (device >= 0 && device < 64 && cache[device] > 0) return cache[device];
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, head_kernel, HEAD_THREADS, 0) != cudaSuccess || nb < 1) nb = 1;
+    nb = nb > HEAD_MIN_BLOCKS ? HEAD_MIN_BLOCKS : nb;
+    if (device >= 0 && device < 64) cache[device] = nb;
+    return nb;
+}
 
+// returns the number of launches (1), or -1 when the cooperative launch failed (cudaGetLastError has the reason)
 int launch_head(cudaStream_t st, const PopDev& P, int sm_count)
 {
-    if (g_head_blocks_per_sm < 0) {
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, head_kernel, HEAD_THREADS, 0) != cudaSuccess || nb < 1) nb = 1;
-        g_head_blocks_per_sm = nb > 4 ? 4 : nb;
-    }
-    unsigned Gmax = (unsigned)(g_head_blocks_per_sm * sm_count);
-    unsigned per = (P.ntiles + Gmax - 1) / Gmax;            // tiles per CTA, balanced
+    int device = 0;
+    cudaGetDevice(&device);
+    const unsigned Gmax = (unsigned)(head_blocks_per_sm(device) * sm_count);
+    unsigned per = (P.ntiles + Gmax - 1) / Gmax;            // tiles per CTA
+    if (per < 1) per = 1;
     unsigned G = (P.ntiles + per - 1) / per;
     if (G < 1) G = 1;
     PopDev Pc = P;
-    void* args[] = { (void*)&Pc };
-    cudaLaunchCooperativeKernel((const void*)head_kernel, dim3(G), dim3(HEAD_THREADS), args, 0, st);
+    void* args[] = { (void*)&Pc, (void*)&per };
+    if (cudaLaunchCooperativeKernel((const void*)head_kernel, dim3(G), dim3(HEAD_THREADS), args, 0, st) != cudaSuccess) return -1;
     return 1;
 }
 

@@ -42,15 +42,17 @@ constexpr int XCHG_RING = 4;                      // mailbox slots (power of two
 constexpr int XCHG_HDR = 32;                      // 64-bit header words per entry: [0] flag, [1..31] small record
 constexpr int XCHG_BODY = SEL_BINS * 4;           // body bytes per entry (one radix histogram)
 constexpr int XCHG_STRIDE = XCHG_HDR * 8 + XCHG_BODY;
-constexpr int XCHG_GCAND = 4096;                  // gathered candidate keys of the distributed radix select (= CAND_SMEM)
+constexpr int XCHG_GCAND = 4096;                  // most candidate keys the distributed eps select gathers on every rank (= CAND_SMEM)
+constexpr int XCHG_GCAND_PER = 1024;              // ... and the most one rank may contribute (its fixed region of the gather area)
 // low-latency region: every 8-byte word carries 32 data bits and the 32-bit sequence number of the exchange
 // that wrote it, so a word is valid as soon as it is seen -- no fence, one NVLink crossing (comm.cuh)
 constexpr int LL_HDR = 32;                        // LL words of an entry's header record (16 64-bit values)
 constexpr int LL_BODY = SEL_BINS;                 // LL words of an entry's body (one radix histogram)
 constexpr size_t LL_STRIDE = (size_t)(LL_HDR + LL_BODY) * 8;
 constexpr size_t XCHG_LL_OFF = (size_t)XCHG_RING * XCHG_MAXR * XCHG_STRIDE;
-constexpr size_t XCHG_GCAND_OFF = XCHG_LL_OFF + (size_t)XCHG_RING * XCHG_MAXR * LL_STRIDE;   // 2 LL words per gathered key
-constexpr size_t XCHG_MBOX_BYTES = XCHG_GCAND_OFF + (size_t)XCHG_GCAND * 16;
+constexpr size_t XCHG_GCAND_OFF = XCHG_LL_OFF + (size_t)XCHG_RING * XCHG_MAXR * LL_STRIDE;   // 2 LL words per gathered key, one region per rank
+constexpr size_t XCHG_HG_OFF = XCHG_GCAND_OFF + (size_t)XCHG_MAXR * XCHG_GCAND_PER * 16;     // the reduced histogram of an exchange (LL words, local readers)
+constexpr size_t XCHG_MBOX_BYTES = XCHG_HG_OFF + (size_t)SEL_BINS * 8;
 constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct XchgDev {

@@ -410,6 +410,41 @@ def test_fused_head_equals_stage_calls_and_oracle(A, oracle, gpu_ctx, kind, N, d
     assert math.isclose(f[3], wess, rel_tol=1e-12) or (math.isnan(f[3]) and math.isnan(wess)) or (wnorm == 0.0)
 
 
+@pytest.mark.parametrize("kind", ["indicator_strict", "epa"])
+@pytest.mark.parametrize("N,alpha", [(50000, 0.95), (1 << 20, 0.95), (1300001, 0.9), (20000, 0.3)])
+def test_fused_head_sequence_adapts_its_window(A, oracle, gpu_ctx, kind, N, alpha):
+    """Successive heads on one population (each starts from the previous eps and the window the previous head
+    derived from the eps gap): every call equals the stage kernels bit for bit and the oracle's quantile."""
+    rng = np.random.default_rng(N + 7)
+    dl = np.abs(rng.normal(size=N)) ** 1.5 + 0.01
+    alive = np.ones(N, dtype=np.uint8)
+    Wv = np.where(alive > 0, rng.random(N) if kind == "epa" else 1.0, 0.0); Wv /= Wv.sum()
+    spec, data = MODEL_CASES["gauss1d"]
+    pops = {}
+    for mode in ("fused", "stage"):
+        pop = A.Population(to_prior(A, spec), A.Model("gauss1d", data), N)
+        pop.upload(delta=dl, W=Wv, alive=alive)
+        pop.set(eps=math.inf, eps_prev=math.inf, kernel=kind)
+        pops[mode] = pop
+    eps_prev = math.inf
+    for it in range(6):
+        q, eps, wn, ess, na = pops["fused"].head(alpha, 0.0)
+        sq = pops["stage"].eps_quantile(alpha)[0]
+        seps = max(min(sq, eps_prev), 0.0)
+        pops["stage"].set(eps=eps_prev, eps_prev=eps_prev, kernel=kind)
+        swn, sess, sna = pops["stage"].reweight(seps)
+        f, s_ = pops["fused"].download(), pops["stage"].download()
+        wq = oracle.quantile_alive(dl, alive if it == 0 else prev_alive, alpha)[0]
+        assert q == sq == wq, (it, q, sq, wq)
+        assert (eps, wn, ess, na) == (seps, swn, sess, sna), it
+        assert np.array_equal(f["W"], s_["W"]) and np.array_equal(f["alive"], s_["alive"])
+        prev_alive = s_["alive"].copy()
+        eps_prev = eps
+        assert 0 < na < N
+    for pop in pops.values():
+        pop.close()
+
+
 def test_fused_head_alive_list_drives_partner_draws(A, oracle, gpu_ctx):
     """After the fused head, a Philox sweep (partners through the compacted alive list) equals the oracle's."""
     name = "gauss_corr10"
