@@ -248,6 +248,32 @@ static void model_prepare_data(int id, double* v)
     }
 }
 
+// the per-model layout of the bound data (DESIGN.md "Models"): counts embedded in the data index further entries of
+// the 64-double block or bound loops inside the kernels, so they are checked here, once
+static const char* model_check_data(int id, const double* v, size_t n)
+{
+    auto whole = [](double x, double lo, double hi) { return x == floor(x) && x >= lo && x <= hi; };
+    switch (id) {
+    case M_GAUSS1D: case M_GAUSS1D_BLOB: if (n < 2) return "gauss1d: data = (observation, sigma)"; break;
+    case M_GAUSS_CORR10: if (n < 11 || !(fabs(v[10]) < 1.0)) return "gauss_corr10: data = y_obs[10], rho with |rho| < 1"; break;
+    case M_DIRAC: case M_NORMDU: case M_MIXTURE: if (n < 1) return "this model needs data = (observation)"; break;
+    case M_WIENER: if (n < 31) return "wiener: data = 31 summary values"; break;
+    case M_SOCKS: if (n < 2) return "socks: data = (pairs, odds)"; break;
+    case M_LOTKA_VOLTERRA: case M_LOTKA_VOLTERRA_LIN:
+        if (n < 6 || !whole(v[4], 1, 29) || n < 6 + 2 * (size_t)v[4]) return "lotka_volterra: data = x0, y0, dt, substeps, nobs (1..29), sigma, obs[2 nobs]";
+        if (!whole(v[3], 1, 100000) || !(v[2] > 0.0)) return "lotka_volterra: dt must be positive and substeps in 1..100000";
+        break;
+    case M_BIRTH_DEATH:
+        if (n < 4 || !whole(v[1], 1, 60) || n < 4 + (size_t)v[1]) return "birth_death: data = n0, nobs (1..60), dt, max_events, obs[nobs]";
+        if (!(v[3] >= 0.0 && v[3] <= 1e9) || !(v[2] > 0.0) || !(v[0] >= 0.0)) return "birth_death: need n0 >= 0, dt > 0 and 0 <= max_events <= 1e9";
+        break;
+    case M_GK: case M_GK_F32:
+        if (n < 8 || !whole(v[0], 8, 16384)) return "gk: data = n (8..16384 draws), 7 observed octiles";
+        break;
+    }
+    return nullptr;
+}
+
 extern "C" int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, size_t ndata, abcdez_model** out)
 {
     CHECK_ARG(ctx && out, "abcdez_model_bind: NULL argument");
@@ -256,6 +282,7 @@ extern "C" int abcdez_model_bind(abcdez_ctx* ctx, int id, const double* data, si
     if (!o->smc_sweep) return fail(ABCDEZ_ERR_UNSUPPORTED, std::string("model '") + o->name + "' has no device functor in this build");
     CHECK_ARG(ndata <= ABCDEZ_MAXDATA, "abcdez_model_bind: more than ABCDEZ_MAXDATA doubles of data");
     CHECK_ARG(ndata == 0 || data != nullptr, "abcdez_model_bind: data is NULL");
+    if (const char* why = model_check_data(id, data, ndata)) return fail(ABCDEZ_ERR_BAD_ARG, std::string("abcdez_model_bind: ") + why);
     abcdez_model* m = new (std::nothrow) abcdez_model();
     if (!m) return fail(ABCDEZ_ERR_CUDA, "out of host memory");
     m->id = id; m->ops = o;
@@ -562,8 +589,11 @@ static int check_dev_err(abcdez_pop* pop, const char* where)
                      : e == ABCDEZ_ERR_NO_ALIVE ? "No alive particles"
                      : e == ABCDEZ_ERR_INIT_RETRY ? "abcde_init!: redraw limit reached without a finite distance/log-prior"
                      : e == ABCDEZ_ERR_PARTNER_RETRY ? "partner draw did not terminate (fewer than 3 alive particles?)"
+                     : e == ABCDEZ_ERR_BAD_ARG ? "weights are not normalised (wprod > 0 but wprod / wnorm == 0)"
+                     : e == ABCDEZ_ERR_NCCL ? "in-kernel exchange with a peer GPU timed out"
                      : "device-side error";
-    return fail(e, std::string(where) + ": " + what);
+    char num[64]; snprintf(num, sizeof num, " [ctrl.err=%d acc.err=%d]", pop->h_ctrl->err, pop->h_ctrl->acc.err);
+    return fail(e, std::string(where) + ": " + what + num);
 }
 
 #define TIME_BEGIN(pop) CU(cudaEventRecord((pop)->ev0, (pop)->ctx->stream))
@@ -666,9 +696,8 @@ extern "C" int abcdez_pop_mc_sweep(abcdez_pop* pop, double eps_pop, double eps_t
     cudaStream_t st = pop->ctx->stream;
     TIME_BEGIN(pop);
     int nl = 1;
-    if (!inj_s) nl += launch_mc_prepare(st, pop->dev.N, pop->dev.delta[pop->h_ctrl->cur], pop->sorted_delta, pop->order,
-                                        pop->sort_tmp, pop->sort_tmp_bytes);
-    McArgs mc{ eps_pop, eps_target, pop->sorted_delta, pop->order };
+    if (!inj_s) nl += launch_mc_prepare(st, pop->dev, pop->sorted_delta, pop->order, pop->sort_tmp, pop->sort_tmp_bytes, 1);
+    McArgs mc{ eps_pop, eps_target, 0, pop->sorted_delta, pop->order };
     pop->ops->mc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, inj, mc);
     CU(cudaGetLastError());
     TIME_END(pop, nl);
@@ -876,10 +905,21 @@ extern "C" void abcdez_smc_opts_default(abcdez_smc_opts* o)
 // bytes, and a restored run continues decision by decision like the uninterrupted one (the random streams are
 // counter based: particle id, sweep epoch and iteration number are part of the state).
 namespace {
-struct SmcStateHdr {
+struct SmcStateHdr {         // 96 bytes
     uint64_t magic; uint32_t version, d, ds, nb; int64_t N; int32_t hist_cap, model_id; uint64_t ctrl_bytes, total_bytes;
+    uint64_t prior_hash;     // FNV-1a of the prior's families / parameters and the bound data
     char model[32];
 };
+static_assert(sizeof(SmcStateHdr) == 96, "snapshot header layout (DESIGN.md section 4b)");
+uint64_t prior_hash(const PriorDev& pr, const ModelData& md)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    mix(&pr.d, sizeof pr.d);
+    for (int k = 0; k < pr.d; ++k) { mix(&pr.family[k], sizeof(int32_t)); mix(pr.p[k], 2 * sizeof(double)); }
+    mix(md.v, sizeof md.v);
+    return h;
+}
 constexpr uint64_t SMC_STATE_MAGIC = 0x3174535a65644342ull;   // "BCdeZSt1"
 size_t smc_state_size(int64_t N, int ds, int nb, int hist_cap)
 {
@@ -969,7 +1009,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         if (state_out && state_out_cap < need) return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: state_out is smaller than abcdez_smc_state_bytes()");
         if (state_in) {
             const SmcStateHdr* h = (const SmcStateHdr*)state_in;
-            const bool ok = state_in_bytes >= sizeof(SmcStateHdr) && h->magic == SMC_STATE_MAGIC && h->version == 1 &&
+            const bool ok = state_in_bytes >= sizeof(SmcStateHdr) && h->magic == SMC_STATE_MAGIC && h->version == 2 &&
                             h->ctrl_bytes == sizeof(Ctrl) && h->N == N && (int)h->d == prior->dev.d &&
                             (int)h->nb == model->ops->blob / 8 && strncmp(h->model, model->ops->name, sizeof(h->model) - 1) == 0 &&
                             h->total_bytes == need && state_in_bytes >= need;
@@ -999,6 +1039,13 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
                           s0.Kmcmc_min == o->Kmcmc_min && s0.kind == o->kernel && s0.facc_min == o->facc_min &&
                           s0.facc_tune == o->facc_tune && h->hist_cap == dev_hist && s0.hist_cap == hist_cap;
         if (!same) { abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: options differ from the snapshot's (only eps_target, nsims_max, facc_stop and max_iters may change)"); }
+        // the control block is trusted state: indices into buffers, tickets the kernels count on being zero, the prior it was drawn under
+        bool sane = (s0.cur == 0 || s0.cur == 1) && s0.hist_len >= 0 && s0.hist_len <= dev_hist && s0.N == (unsigned)N && s0.Ng == (unsigned)Ng &&
+                    s0.n_alive <= s0.N && s0.n_alive_g <= s0.Ng && s0.iters >= 0 && s0.sweep_idx >= 0 && s0.acc.sweep_nsims == 0 && s0.acc.sweep_naccs == 0 &&
+                    h->prior_hash == prior_hash(prior->dev, model->data);
+        for (int q = 0; q < 8; ++q) sane = sane && s0.acc.ticket[q] == 0u;
+        for (int q = 0; q < 6; ++q) sane = sane && s0.acc.cand_count[q] == 0ull;
+        if (!sane) { abcdez_pop_destroy(pop); return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: the snapshot's control block is inconsistent (corrupt, or taken under another prior / observed data)"); }
         *c = s0;
         c->eps_target = eps_target; c->nsims_max = o->nsims_max; c->facc_stop = o->facc_stop;
         c->max_iters = o->max_iters > 0 ? c->iters + o->max_iters : 0;
@@ -1093,7 +1140,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         RUN_CU(cudaStreamSynchronize(st));
         const size_t n = (size_t)N; const int cur = c->cur;
         SmcStateHdr h; memset(&h, 0, sizeof h);
-        h.magic = SMC_STATE_MAGIC; h.version = 1; h.d = (uint32_t)pop->D; h.ds = (uint32_t)pop->DS; h.nb = (uint32_t)pop->NB;
+        h.magic = SMC_STATE_MAGIC; h.version = 2; h.prior_hash = prior_hash(pop->prior, pop->data); h.d = (uint32_t)pop->D; h.ds = (uint32_t)pop->DS; h.nb = (uint32_t)pop->NB;
         h.N = N; h.hist_cap = dev_hist; h.model_id = model->id; h.ctrl_bytes = sizeof(Ctrl);
         h.total_bytes = smc_state_size(N, pop->DS, pop->NB, dev_hist);
         strncpy(h.model, model->ops->name, sizeof(h.model) - 1);
@@ -1131,6 +1178,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     res->eps = c->eps; res->logZ = c->logZ; res->iters = c->iters; res->nsims = c->nsims_total;
     res->status = c->status; res->n_resamples = c->n_resamples; res->n_sweeps = c->n_sweeps; res->n_launches = launches;
     res->hist_len = hist_cap > 0 ? c->hist_len : 0;
+    res->hist_dropped = hist_cap > 0 ? c->hist_overflow : 0;
     // results, :382-393
     if (res->P) {
         rc = ensure_scratch(pop, (size_t)N * pop->D * 8); if (rc) goto done;
@@ -1187,6 +1235,7 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
     CHECK_ARG(5 <= o->nparticles, "nparticles must be at least 5");          // :109
     CHECK_ARG(1 <= o->generations, "generations must be at least 1");        // :110
     if (!model->ops->mc_sweep) return fail(ABCDEZ_ERR_UNSUPPORTED, std::string("abcdemc!: model '") + model->ops->name + "' has no abcdemc! sweep in this build");
+    CHECK_ARG(o->generations <= 1000000, "generations must be at most 10^6");
     CU(cudaSetDevice(ctx->device));
     // sharded run: nparticles is the whole population; base particle and partners are drawn inside the rank's
     // block, extrema(delta) (:146) and the simulation count are global (in-kernel exchange after every sweep)
@@ -1219,25 +1268,22 @@ extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const a
     RUN_CU(cudaEventCreate(&e0)); RUN_CU(cudaEventCreate(&e1));
     pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :117-125
     launches++;
-    RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-    RUN_CU(cudaStreamSynchronize(st));
-    rc = check_dev_err(pop, "abcdez_mc_run"); if (rc) goto done;
     RUN_CU(cudaEventRecord(e0, st));
-    for (int it = 0; it < o->generations; ++it) {                            // :134
-        // extrema(delta) of the live generation come from the previous kernel's epilogue (:146)
-        double eps_pop = fmax(eps_target, c->dmin + 0.0 * (c->dmax - c->dmin));   // :147, alpha = 0 (:107)
-        if (c->dmax > eps_target)         // only particles above eps need the sorted order (:20-24)
-            launches += launch_mc_prepare(st, pop->dev.N, pop->dev.delta[c->cur], pop->sorted_delta, pop->order,
-                                          pop->sort_tmp, pop->sort_tmp_bytes);
-        McArgs mc{ eps_pop, eps_target, pop->sorted_delta, pop->order };
-        pop->ops->mc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj, mc);   // :149
-        launches++;
-        RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-        RUN_CU(cudaStreamSynchronize(st));
-        if (c->err || c->acc.err) break;
+    {
+        // The generation loop (:134-161) is a fixed launch list: extrema(delta) of the live generation come from the
+        // previous kernel's epilogue and stay in the device control block, eps_pop (:146-147) is derived from them
+        // inside the sweep, the sort kernels return at once when no particle is above eps_target (:19-24), and every
+        // kernel behind an error returns at once -- no host round trip per generation.
+        McArgs mc{ 0.0, eps_target, 1, pop->sorted_delta, pop->order };
+        for (int it = 0; it < o->generations; ++it) {                        // :134
+            launches += launch_mc_prepare(st, pop->dev, pop->sorted_delta, pop->order, pop->sort_tmp, pop->sort_tmp_bytes, 0);
+            pop->ops->mc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj, mc);   // :149
+            launches++;
+        }
     }
     RUN_CU(cudaEventRecord(e1, st));
     RUN_CU(cudaGetLastError());
+    RUN_CU(cudaMemcpyAsync(c, pop->dev.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     RUN_CU(cudaStreamSynchronize(st));
     rc = check_dev_err(pop, "abcdez_mc_run"); if (rc) goto done;
     { float ms = 0.f; RUN_CU(cudaEventElapsedTime(&ms, e0, e1)); res->total_ms = ms; res->sweep_ms = ms; }

@@ -12,7 +12,6 @@
 #include "seqsum.cuh"
 #include "ctrl.cuh"
 #include "comm.cuh"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace abcdez {
 
@@ -913,37 +912,6 @@ int launch_push_rows(cudaStream_t st, const PopDev& P, const PriorDev& pr, int D
     int64_t n = (int64_t)P.N * D;
     push_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, pr, D, row_stride(D), out_dense);
     return 1;
-}
-
-// ---------------------------------------------------------------------------------------
-// abcdemc!: (delta, index)-sorted order for the "better-or-equal particle" draw
-// (src/abcdez_mc.jl:23).  Library radix sort (CUB) -- plumbing, not a hot kernel: one sort per
-// generation and only while some particle is still above eps_target.
-// ---------------------------------------------------------------------------------------
-__global__ void iota_kernel(uint32_t* p, uint32_t N)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) p[i] = i;
-}
-
-size_t mc_sort_tmp_bytes(int64_t N)
-{
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const double*)nullptr, (double*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
-    return bytes + (size_t)N * sizeof(uint32_t);    // + iota input
-}
-
-int launch_mc_prepare(cudaStream_t st, uint32_t N, const double* delta_live, double* sorted_delta, uint32_t* order,
-                      void* tmp, size_t tmp_bytes)
-{
-    uint32_t* iota = reinterpret_cast<uint32_t*>(tmp);
-    void* cub_tmp = reinterpret_cast<char*>(tmp) + (size_t)N * sizeof(uint32_t);
-    size_t cub_bytes = tmp_bytes - (size_t)N * sizeof(uint32_t);
-    iota_kernel<<<(N + 255) / 256, 256, 0, st>>>(iota, N);
-    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, delta_live, sorted_delta,
-                                    (const uint32_t*)iota, order, (int)N, 0, 64, st);
-    return 3;
 }
 
 }  // namespace abcdez

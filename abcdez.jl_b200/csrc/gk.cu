@@ -1,16 +1,25 @@
 // gk.cu -- config 3 of BASELINE.json: the g-and-k distribution, 4 parameters, quantile summaries of n
-// (<= 16384, default 10^4) simulated draws.  One dist! evaluation is ~10^6 FP32 operations, so a particle is
-// simulated by a whole CTA instead of one thread:
-//   draws      thread t generates the Philox blocks t, t+256, ... (4 normals each, Box-Muller in FP32) and
-//              pushes them through x = A + B (1 + 0.8 tanh(g z / 2)) (1 + z^2)^k z into shared memory;
-//   summaries  the 7 octiles are order statistics x_(ceil(n j / 8)); instead of sorting, a radix multi-select
-//              on order-preserving 32-bit keys (11 + 8 + 8 + 5 bits) resolves all 7 ranks in 4 passes over
-//              shared memory;
+// (<= 16384, default 10^4) simulated draws.  One dist! evaluation is ~2 * 10^6 arithmetic operations, so a
+// particle is simulated by a whole CTA instead of one thread:
+//   draws      thread t generates the Philox blocks t, t + 256, ... (one Box-Muller pair each in FP64, two in
+//              FP32) and pushes them through
+//                  x = A + B (1 + 0.8 (1 - e^{-g z}) / (1 + e^{-g z})) (1 + z^2)^k z
+//              into shared memory, tracking the extrema of the order-preserving keys on the way;
+//   summaries  the 7 octiles are order statistics x_(ceil(n j / 8)); instead of sorting, a multi-select in KEY
+//              space: one 2048-bin histogram between the extrema resolves all 7 ranks to a bucket each,
+//              buckets that are still large are refined 256 ways, and the <= 64 keys left per octile are
+//              ranked directly by one warp -- 3 passes over shared memory in the usual case;
 //   distance   sqrt(mean squared octile difference) in FP64.
-// The proposal / accept logic around it is abcdesmc_swarm! (src/abcdez_smc.jl:106-153) exactly as in sweep.cuh,
-// evaluated redundantly by every thread of the CTA (same Philox streams -> same decisions); thread 0 stores.
-// Bound: FP32 / SFU pipes.  Normative definition: DESIGN.md "Models"; the oracle restates
-// it with glibc's libm, hence the 1e-4 relative parity tolerance of this model (tests say so).
+// Two registered models, same definition, different arithmetic:
+//   "gk"      FP64 with the library's portable log / exp / sin / cos (common.cuh), i.e. the arithmetic a Julia
+//             dist! would use (Float64).  The oracle restates it operation by operation: distances, accept
+//             decisions and whole runs are bit-identical.
+//   "gk_f32"  relaxed-precision mode: the draws in FP32 with portable FP32 log / exp /
+//             sin / cos defined below (again restated in the oracle -> bit-identical to *its* oracle), twice the
+//             lanes and shorter polynomials; its posterior agrees with "gk" within Monte-Carlo error.
+// The proposal / accept logic around the simulation is abcdesmc_swarm! (src/abcdez_smc.jl:106-153) and
+// abcdemc_swarm! (src/abcdez_mc.jl:5-61) exactly as in sweep.cuh, evaluated redundantly by every thread of the
+// CTA (same Philox streams -> same decisions); thread 0 stores.  Bound: FP64 (FP32) pipe, DESIGN.md section 5.
 #include "sweep.cuh"
 
 namespace abcdez {
@@ -18,112 +27,288 @@ namespace abcdez {
 constexpr int GK_THREADS = 256;
 constexpr int GK_MAXN = 16384;
 constexpr int GK_NQ = 7;
+constexpr int GK_LIST = 64;               // keys per octile ranked directly
 
 struct GkSmem {
-    unsigned hist[SEL_BINS];              // pass 1: 11-bit digit
-    unsigned sub[GK_NQ][256];             // passes 2-4: one 8-bit histogram per target
+    unsigned hist[SEL_BINS];              // round 1: 2048 bins between the extrema
+    unsigned sub[GK_NQ][256];             // refinement rounds: one 256-bin histogram per octile
+    unsigned long long list[GK_NQ][GK_LIST];
+    unsigned long long lo[GK_NQ], hi[GK_NQ], q[GK_NQ];
+    unsigned rank[GK_NQ], cnt[GK_NQ], nlist[GK_NQ];
     unsigned part[GK_THREADS];
-    unsigned prefix[GK_NQ];               // resolved high bits of each target's key
-    unsigned rank[GK_NQ];                 // rank of the target inside its current bucket
+    unsigned long long kmin, kmax;
     double dist;
 };
 
-__device__ __forceinline__ unsigned f32_key(float x)
+// ---- portable FP32 math of the relaxed-precision mode (restated in oracle/abcdez_oracle.c) ------------------
+// IEEE single operations only (the library is built -fmad=false; sqrtf and / are correctly rounded), explicit
+// fmaf in the Horner steps.
+__device__ __forceinline__ float gk_logf_pos(float x)          // x positive and normal
 {
-    unsigned b = __float_as_uint(x);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    const unsigned b = __float_as_uint(x);
+    int e = (int)((b >> 23) & 0xffu) - 127;
+    float m = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+    if (m > 0x1.6a09e6p+0f) { m = m * 0.5f; e += 1; }                   // sqrt(2)
+    const float f = m - 1.0f;
+    const float s = f / (2.0f + f);
+    const float z = s * s;
+    float p = 2.0f / 9.0f;
+    p = fmaf(p, z, 2.0f / 7.0f);
+    p = fmaf(p, z, 2.0f / 5.0f);
+    p = fmaf(p, z, 2.0f / 3.0f);
+    const float r = (s * z) * p;
+    const float lm = 2.0f * s + r;
+    return ((float)e * 0x1.62e4p-1f + lm) + (float)e * 0x1.7f7d1cp-20f;  // ln 2 = hi + lo
 }
-__device__ __forceinline__ float key_f32(unsigned k)
+__device__ __forceinline__ float gk_expf(float x)
 {
-    unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(b);
+    if (x > 88.0f) return INFINITY;
+    if (x < -87.0f) return 0.0f;
+    const float k = floorf(x * 0x1.715476p+0f + 0.5f);                  // 1 / ln 2
+    const float r = (x - k * 0x1.62e4p-1f) - k * 0x1.7f7d1cp-20f;
+    float p = 1.0f / 5040.0f;
+    p = fmaf(p, r, 1.0f / 720.0f);
+    p = fmaf(p, r, 1.0f / 120.0f);
+    p = fmaf(p, r, 1.0f / 24.0f);
+    p = fmaf(p, r, 1.0f / 6.0f);
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    return p * __uint_as_float((unsigned)((int)k + 127) << 23);         // 2^k, k in [-126, 127]
+}
+__device__ __forceinline__ void gk_sincos2pif(float u, float* sn, float* cs)
+{
+    const float q = floorf(4.0f * u + 0.5f);
+    const float r = u - 0.25f * q;
+    const float x = r * 0x1.921fb6p+2f;                                 // 2 pi
+    const float x2 = x * x;
+    float ps = -1.0f / 39916800.0f;
+    ps = fmaf(ps, x2, 1.0f / 362880.0f);
+    ps = fmaf(ps, x2, -1.0f / 5040.0f);
+    ps = fmaf(ps, x2, 1.0f / 120.0f);
+    ps = fmaf(ps, x2, -1.0f / 6.0f);
+    float pc = -1.0f / 3628800.0f;
+    pc = fmaf(pc, x2, 1.0f / 40320.0f);
+    pc = fmaf(pc, x2, -1.0f / 720.0f);
+    pc = fmaf(pc, x2, 1.0f / 24.0f);
+    pc = fmaf(pc, x2, -0.5f);
+    const float s = x + x * (x2 * ps);
+    const float c = 1.0f + x2 * pc;
+    const int k = (int)q & 3;
+    const bool swap = (k & 1) != 0;
+    const float a = swap ? c : s, b = swap ? s : c;
+    *sn = (k & 2) ? -a : a;
+    *cs = ((k + 1) & 2) ? -b : b;
 }
 
-// every thread of the CTA calls; returns the distance in every thread.  xs: n floats of shared memory.
-__device__ double gk_simulate_cta(const double* th, const double* data, const Stream& rs, float* xs, GkSmem* s)
+// ---- the simulator's arithmetic, per precision -------------------------------------------------------------
+template <class T> struct GkMath;
+
+template <> struct GkMath<double> {
+    static constexpr int PER_BLOCK = 2;           // draws per Philox block
+    static constexpr const char* name = "gk";
+    __device__ static __forceinline__ void normals(const Stream& rs, uint32_t b, double* z) { rs.n2(b, z[0], z[1]); }
+    __device__ static __forceinline__ double transform(double A, double B, double g, double k, double z)
+    {
+        const double gz = g * z;
+        const double e = pexp(-fabs(gz));                       // in (0, 1]
+        double t = pm_div_inrange(1.0 - e, 1.0 + e);            // == (1 - e) / (1 + e); tanh(|g z| / 2)
+        t = gz < 0.0 ? -t : t;
+        const double c = 1.0 + 0.8 * t;
+        const double l = plog_unit(1.0 + z * z);                // == plog: the argument is >= 1
+        const double p = pexp(k * l);                           // (1 + z^2)^k
+        return A + ((B * c) * p) * z;
+    }
+    __device__ static __forceinline__ unsigned long long key(double x) { return f64_key(x); }
+    __device__ static __forceinline__ double value(unsigned long long k) { return key_f64(k); }
+};
+
+template <> struct GkMath<float> {
+    static constexpr int PER_BLOCK = 4;
+    static constexpr const char* name = "gk_f32";
+    __device__ static __forceinline__ void normals(const Stream& rs, uint32_t b, float* z)
+    {
+        float u[4];
+        rs.f4(b, u);
+        const float r1 = sqrtf(-2.0f * gk_logf_pos(1.0f - u[0])), r2 = sqrtf(-2.0f * gk_logf_pos(1.0f - u[2]));   // 1 - u in [2^-24, 1]
+        float s1, c1, s2, c2;
+        gk_sincos2pif(u[1], &s1, &c1);
+        gk_sincos2pif(u[3], &s2, &c2);
+        z[0] = r1 * c1; z[1] = r1 * s1; z[2] = r2 * c2; z[3] = r2 * s2;
+    }
+    __device__ static __forceinline__ float transform(float A, float B, float g, float k, float z)
+    {
+        const float gz = g * z;
+        const float e = gk_expf(-fabsf(gz));
+        float t = (1.0f - e) / (1.0f + e);
+        t = gz < 0.0f ? -t : t;
+        const float c = 1.0f + 0.8f * t;
+        const float l = gk_logf_pos(1.0f + z * z);
+        const float p = gk_expf(k * l);
+        return A + ((B * c) * p) * z;
+    }
+    __device__ static __forceinline__ unsigned long long key(float x)
+    {
+        unsigned b = __float_as_uint(x);
+        return (unsigned long long)((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+    }
+    __device__ static __forceinline__ double value(unsigned long long k)
+    {
+        unsigned kk = (unsigned)k;
+        unsigned b = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
+        return (double)__uint_as_float(b);
+    }
+};
+
+// every thread of the CTA calls; returns the distance in every thread.  xs: n values of shared memory.
+template <class T>
+__device__ double gk_simulate_cta(const double* th, const double* data, const Stream& rs, T* xs, GkSmem* s)
 {
-    const int tid = threadIdx.x;
+    using MT = GkMath<T>;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     int n = (int)data[0];
     n = n < 8 ? 8 : (n > GK_MAXN ? GK_MAXN : n);
-    const float A = (float)th[0], B = (float)th[1], g = (float)th[2], k = (float)th[3];
+    const T A = (T)th[0], B = (T)th[1], g = (T)th[2], k = (T)th[3];
     __syncthreads();                                   // the previous particle's readers are done with xs / s
-    for (int b = tid; b * 4 < n; b += GK_THREADS) {
-        float u[4];
-        rs.f4((uint32_t)b, u);
-        float r1 = sqrtf(-2.0f * logf(1.0f - u[0])), r2 = sqrtf(-2.0f * logf(1.0f - u[2]));
-        float s1, c1, s2, c2;
-        sincosf(6.2831853f * u[1], &s1, &c1);
-        sincosf(6.2831853f * u[3], &s2, &c2);
-        float z[4] = { r1 * c1, r1 * s1, r2 * c2, r2 * s2 };
+    // ---- draws ---------------------------------------------------------------------------------------
+    unsigned long long kmn = ~0ull, kmx = 0ull;
+    for (int b = tid; b * MT::PER_BLOCK < n; b += GK_THREADS) {
+        T z[MT::PER_BLOCK];
+        MT::normals(rs, (uint32_t)b, z);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float zz = z[j];
-            float x = A + B * (1.0f + 0.8f * tanhf(0.5f * g * zz)) * powf(1.0f + zz * zz, k) * zz;
-            if (b * 4 + j < n) xs[b * 4 + j] = x;
+        for (int j = 0; j < MT::PER_BLOCK; ++j) {
+            const T x = MT::transform(A, B, g, k, z[j]);
+            const int i = b * MT::PER_BLOCK + j;
+            if (i < n) {
+                xs[i] = x;
+                const unsigned long long key = MT::key(x);
+                kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx;
+            }
         }
     }
     for (int q = tid; q < SEL_BINS; q += GK_THREADS) s->hist[q] = 0u;
     for (int q = tid; q < GK_NQ * 256; q += GK_THREADS) (&s->sub[0][0])[q] = 0u;
+    if (tid == 0) { s->kmin = ~0ull; s->kmax = 0ull; }
+    if (tid < GK_NQ) s->nlist[tid] = 0u;
     __syncthreads();
-    // ---- pass 1: top 11 bits of every key ------------------------------------------------------------
-    for (int i = tid; i < n; i += GK_THREADS) atomicAdd(&s->hist[f32_key(xs[i]) >> 21], 1u);
+    kmn = warp_min_u64(kmn); kmx = warp_max_u64(kmx);
+    if (lane == 0) { atomicMin(&s->kmin, kmn); atomicMax(&s->kmax, kmx); }
     __syncthreads();
-    {   // exclusive prefix over the 2048 bins: 8 bins per thread + a scan of the 256 partials
+    const unsigned long long kmin = s->kmin, kmax = s->kmax, width = kmax - kmin;
+    // ---- round 1: 2048 bins of 2^sh keys between the extrema ----------------------------------------------
+    const int sh = width ? max(0, 64 - __clzll((long long)width) - 11) : 0;       // (width >> sh) <= 2047
+    for (int i = tid; i < n; i += GK_THREADS) atomicAdd(&s->hist[(unsigned)((MT::key(xs[i]) - kmin) >> sh)], 1u);
+    __syncthreads();
+    {   // exclusive prefix over the 2048 bins (8 per thread, shuffle scan of the thread totals), then every octile's bin
         unsigned loc[8], tot = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) { loc[q] = s->hist[tid * 8 + q]; tot += loc[q]; }
-        s->part[tid] = tot;
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s->part[wp] = incl;
         __syncthreads();
-        unsigned before = 0;
-        for (int t = 0; t < tid; ++t) before += s->part[t];
-        unsigned cum = before;
+        unsigned cum = incl - tot;
+        for (int w = 0; w < wp; ++w) cum += s->part[w];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (loc[q]) {
 #pragma unroll
                 for (int j = 0; j < GK_NQ; ++j) {
-                    unsigned r = (unsigned)((n * (j + 1) + 7) / 8) - 1u;        // 0-based rank of octile j+1
-                    if (r >= cum && r < cum + loc[q]) { s->prefix[j] = (unsigned)(tid * 8 + q) << 21; s->rank[j] = r - cum; }
+                    const unsigned r = (unsigned)((n * (j + 1) + 7) / 8) - 1u;        // 0-based rank of octile j+1
+                    if (r >= cum && r < cum + loc[q]) {
+                        const unsigned long long lo = kmin + ((unsigned long long)(tid * 8 + q) << sh);
+                        const unsigned long long top = lo + ((1ull << sh) - 1ull);
+                        s->lo[j] = lo; s->hi[j] = top < kmax ? top : kmax;
+                        s->rank[j] = r - cum; s->cnt[j] = loc[q];
+                    }
                 }
             }
             cum += loc[q];
         }
     }
     __syncthreads();
-    // ---- passes 2-4: 8, 8 and 5 further bits, one small histogram per target ---------------------------
-    const int shifts[3] = { 13, 5, 0 }, widths[3] = { 8, 8, 5 };
-    unsigned himask = 0xffe00000u;
-    for (int p = 0; p < 3; ++p) {
-        const int shift = shifts[p];
-        const unsigned dmask = (1u << widths[p]) - 1u;
-        unsigned pf[GK_NQ];
+    // ---- refinement: octiles whose bucket still holds more than GK_LIST keys, 256 ways per round -------------
+    for (int it = 0; it < 10; ++it) {
+        unsigned long long lo[GK_NQ], hi[GK_NQ];
+        unsigned mask = 0;
 #pragma unroll
-        for (int j = 0; j < GK_NQ; ++j) pf[j] = s->prefix[j];
+        for (int j = 0; j < GK_NQ; ++j) {
+            lo[j] = s->lo[j]; hi[j] = s->hi[j];
+            if (s->cnt[j] > (unsigned)GK_LIST && lo[j] < hi[j]) mask |= 1u << j;
+        }
+        if (!mask) break;                                   // (uniform: read from shared memory)
         for (int i = tid; i < n; i += GK_THREADS) {
-            unsigned key = f32_key(xs[i]), hi = key & himask;
+            const unsigned long long key = MT::key(xs[i]);
 #pragma unroll
-            for (int j = 0; j < GK_NQ; ++j)
-                if (hi == pf[j]) atomicAdd(&s->sub[j][(key >> shift) & dmask], 1u);
+            for (int j = 0; j < GK_NQ; ++j) {
+                if (((mask >> j) & 1u) && key >= lo[j] && key <= hi[j]) {
+                    const int shj = max(0, 64 - __clzll((long long)(hi[j] - lo[j])) - 8);
+                    atomicAdd(&s->sub[j][(unsigned)((key - lo[j]) >> shj)], 1u);
+                }
+            }
         }
         __syncthreads();
-        if (tid < GK_NQ) {                              // 7 threads walk their 256-bin histograms
-            unsigned r = s->rank[tid], cum = 0, nb = dmask + 1u;
-            for (unsigned q = 0; q < nb; ++q) {
-                unsigned cnt = s->sub[tid][q];
-                if (r < cum + cnt) { s->prefix[tid] |= q << shift; s->rank[tid] = r - cum; break; }
+        if (tid < GK_NQ && ((mask >> tid) & 1u)) {           // 7 threads walk their 256-bin histograms
+            const int shj = max(0, 64 - __clzll((long long)(hi[tid] - lo[tid])) - 8);
+            unsigned r = s->rank[tid], cum = 0;
+            for (unsigned q = 0; q < 256u; ++q) {
+                const unsigned cnt = s->sub[tid][q];
+                if (r < cum + cnt) {
+                    const unsigned long long nlo = lo[tid] + ((unsigned long long)q << shj);
+                    const unsigned long long top = nlo + ((1ull << shj) - 1ull);
+                    s->lo[tid] = nlo; s->hi[tid] = top < hi[tid] ? top : hi[tid];
+                    s->rank[tid] = r - cum; s->cnt[tid] = cnt;
+                    break;
+                }
                 cum += cnt;
             }
         }
         __syncthreads();
         for (int q = tid; q < GK_NQ * 256; q += GK_THREADS) (&s->sub[0][0])[q] = 0u;
-        himask |= dmask << shift;
         __syncthreads();
     }
+    // ---- gather the <= GK_LIST keys of every octile's bucket and rank them directly ----------------------------
+    {
+        unsigned long long lo[GK_NQ], hi[GK_NQ];
+        unsigned small = 0;
+#pragma unroll
+        for (int j = 0; j < GK_NQ; ++j) { lo[j] = s->lo[j]; hi[j] = s->hi[j]; if (s->cnt[j] <= (unsigned)GK_LIST) small |= 1u << j; }
+        for (int i = tid; i < n; i += GK_THREADS) {
+            const unsigned long long key = MT::key(xs[i]);
+#pragma unroll
+            for (int j = 0; j < GK_NQ; ++j) {
+                if (((small >> j) & 1u) && key >= lo[j] && key <= hi[j]) {
+                    const unsigned idx = atomicAdd(&s->nlist[j], 1u);
+                    if (idx < (unsigned)GK_LIST) s->list[j][idx] = key;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (wp < GK_NQ) {                                       // warp j ranks octile j's keys: two per lane
+        const int j = wp;
+        if (s->cnt[j] > (unsigned)GK_LIST) { if (lane == 0) s->q[j] = s->lo[j]; }     // one key value fills the bucket
+        else {
+            const unsigned m = s->nlist[j] < (unsigned)GK_LIST ? s->nlist[j] : (unsigned)GK_LIST, r = s->rank[j];
+#pragma unroll
+            for (int h = 0; h < GK_LIST / 32; ++h) {
+                const unsigned me = lane + 32 * h;
+                if (me < m) {
+                    const unsigned long long my = s->list[j][me];
+                    unsigned below = 0;
+                    for (unsigned o = 0; o < m; ++o) { const unsigned long long ot = s->list[j][o]; below += (ot < my || (ot == my && o < me)) ? 1u : 0u; }
+                    if (below == r) s->q[j] = my;
+                }
+            }
+        }
+    }
+    __syncthreads();
     if (tid == 0) {
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < GK_NQ; ++j) {
-            double dq = (double)key_f32(s->prefix[j]) - data[1 + j];
+            const double dq = MT::value(s->q[j]) - data[1 + j];
             acc += dq * dq;
         }
         s->dist = sqrt(acc / 7.0);
@@ -132,24 +317,25 @@ __device__ double gk_simulate_cta(const double* th, const double* data, const St
     return s->dist;
 }
 
-struct GK {
-    static constexpr int D = 4, BLOB = 0;
-    static constexpr const char* name = "gk";
-};
-
-static inline size_t gk_smem_bytes() { return sizeof(GkSmem) + (size_t)GK_MAXN * sizeof(float); }
+template <class T> static inline size_t gk_smem_bytes(const ModelData& md)
+{
+    int n = (int)md.v[0];
+    n = n < 8 ? 8 : (n > GK_MAXN ? GK_MAXN : n);
+    return sizeof(GkSmem) + (((size_t)n * sizeof(T) + 15) & ~(size_t)15);
+}
 
 #define GK_SMEM_DECL                                                                     \
     extern __shared__ __align__(16) unsigned char gk_raw[];                              \
     GkSmem* gs = reinterpret_cast<GkSmem*>(gk_raw);                                      \
-    float* xs = reinterpret_cast<float*>(gk_raw + sizeof(GkSmem));
+    T* xs = reinterpret_cast<T*>(gk_raw + sizeof(GkSmem));
 
 // ---- abcde_init! (src/abcdez_init.jl:2-22), one CTA per particle ----------------------------------------
+template <class T>
 __global__ void __launch_bounds__(GK_THREADS)
 gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                const __grid_constant__ PhiloxKeys seed, int draw_prior)
 {
-    constexpr int D = GK::D;
+    constexpr int D = 4;
     GK_SMEM_DECL
     Ctrl* c = P.ctrl;
     const int cur = c->cur;
@@ -166,7 +352,7 @@ gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDe
         if (isfinite(lp)) {
             Stream r(seed, pid, 0u, TAG_INIT_MODEL);
             push_p<D>(pr, th, x);
-            dl = gk_simulate_cta(x, md.v, r, xs, gs);
+            dl = gk_simulate_cta<T>(x, md.v, r, xs, gs);
         }
         uint32_t attempt = 0;
         while (!isfinite(dl) || !isfinite(lp)) {           // init.jl:14-20 (uniform over the CTA)
@@ -175,7 +361,7 @@ gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDe
             push_p<D>(pr, th, x);
             lp = prior_logpdf<D>(pr, x);
             Stream r(seed, pid, attempt, TAG_INIT_MODEL);
-            dl = gk_simulate_cta(x, md.v, r, xs, gs);
+            dl = gk_simulate_cta<T>(x, md.v, r, xs, gs);
             if (threadIdx.x == 0) redraws++;
         }
         if (threadIdx.x == 0) {
@@ -195,11 +381,12 @@ gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDe
 }
 
 // ---- abcdesmc_swarm! (src/abcdez_smc.jl:106-153), one CTA per listed particle ------------------------------
+template <class T>
 __global__ void __launch_bounds__(GK_THREADS)
 gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                     const __grid_constant__ SweepInj inj)
 {
-    constexpr int D = GK::D;
+    constexpr int D = 4;
     GK_SMEM_DECL
     Ctrl* c = P.ctrl;
     if (c->stop | c->sweeps_done) return;
@@ -264,7 +451,7 @@ gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pr
             double lp = prior_logpdf<D>(pr, xsd);                              // :134
             if (!(lp < 0.0 && isinf(lp))) {                                    // :135 (uniform over the CTA)
                 Stream r(seed, pid, epoch, TAG_MODEL);
-                double dp = gk_simulate_cta(xsd, md.v, r, xs, gs);             // :137
+                double dp = gk_simulate_cta<T>(xsd, md.v, r, xs, gs);          // :137
                 flag |= ABCDEZ_FLAG_SIM;                                       // :138
                 const double eps = c->eps; const int kind = c->kind;
                 double w = lp - lpi;                                           // :140-141
@@ -293,7 +480,112 @@ gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pr
     if (last) ctrl_after_smc_sweep(P, c);
 }
 
+// ---- abcdemc_swarm! (src/abcdez_mc.jl:5-61), one CTA per particle -------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(GK_THREADS)
+gk_mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+                   const __grid_constant__ SweepInj inj, const __grid_constant__ McArgs mc)
+{
+    constexpr int D = 4;
+    GK_SMEM_DECL
+    Ctrl* c = P.ctrl;
+    if (mc.from_ctrl && (c->stop | c->err)) return;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const uint32_t N = P.N;
+    const double* __restrict__ th = P.theta[cur];
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
+    const bool lead = threadIdx.x == 0;
+    const double eps_target = mc.from_ctrl ? c->eps_target : mc.eps_target;
+    const double eps_pop = mc.from_ctrl ? fmax(eps_target, c->dmin + 0.0 * (c->dmax - c->dmin)) : mc.eps_pop;   // mc.jl:146-147
+    unsigned nsim = 0, nacc = 0; int err = 0;
+    unsigned long long kmn = ~0ull, kmx = 0ull;
+    for (uint32_t i = blockIdx.x; i < N; i += gridDim.x) {
+        double thp[D];
+        load_row<D>(th, i, thp);
+        const double lpi = P.logpi[cur][i];
+        double dli = P.delta[cur][i];
+        const uint8_t mv = P.moved[i];
+        if (mv && lead) { store_row<D>(P.theta[nxt], i, thp); copy_scalars<0>(P, cur, nxt, i, lpi, dli); }
+        uint8_t flag = 0; unsigned acc_now = 0;
+        const uint32_t pid = P.id0 + i;
+        const PhiloxKeys& seed = P.keys;
+        const uint32_t epoch = c->sweep_epoch;
+        uint32_t s = i;                                                        // :18
+        const double eps = (dli <= eps_target) ? eps_target : eps_pop;         // :19
+        if (dli > eps) {                                                       // :20-24
+            if (inj.s) s = (uint32_t)inj.s[i];
+            else {
+                uint32_t lo = 0, hi = N;
+                while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (mc.sorted_delta[m] <= dli) lo = m + 1; else hi = m; }
+                Stream cs(seed, pid, epoch, TAG_MC);
+                double u1, u2; cs.u2(0u, u1, u2);
+                long long k = (long long)floor(u1 * (double)lo);
+                if (k >= (long long)lo) k = (long long)lo - 1;
+                s = mc.order[k];
+            }
+        }
+        uint32_t a, b; int perr = 0;
+        if (inj.a) { a = (uint32_t)inj.a[i]; b = (uint32_t)inj.b[i]; }
+        else {
+            Stream ps(seed, pid, epoch, TAG_PARTNER);
+            double u1, u2, ua, ub; uint32_t att = 1;
+            auto pick = [N](double u) { long long k = (long long)floor(u * (double)N); if (k >= (long long)N) k = (long long)N - 1; return (uint32_t)k; };
+            ps.u2(0u, ua, ub);
+            a = pick(ua);
+            while (a == s) {                                                   // :25-28
+                if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { perr = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                ps.u2(att++, u1, u2);
+                a = pick(u1);
+            }
+            att = 1;
+            b = pick(ub);
+            while (b == a || b == s) {                                         // :29-32
+                if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { perr = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                ps.u2(att++, u1, u2);
+                b = pick(u2);
+            }
+        }
+        if (perr) { if (lead) err = perr; }
+        else {
+            Stream ms(seed, pid, epoch, TAG_MOVE);
+            if (s != i) load_row<D>(th, s, thp);                               // base particle theta_s
+            double z, z2;
+            if (inj.z) z = inj.z[i]; else ms.n2(0u, z, z2);
+            const double g = c->gamma0 * (1.0 + z * c->gsig);                  // :34
+            de_proposal<D>(th, a, b, g, thp);
+            double xsd[D];
+            push_p<D>(pr, thp, xsd);
+            const double lp = prior_logpdf<D>(pr, xsd);                        // :41
+            const double w_prior = lp - lpi;                                   // :42 (logpi[i], not [s])
+            double u, u2;
+            if (inj.u) u = inj.u[i]; else ms.u2(1u, u, u2);                    // :43, always drawn
+            if (!(plog(u) > fmin(0.0, w_prior))) {                             // (uniform over the CTA)
+                flag |= ABCDEZ_FLAG_SIM;                                       // :44
+                Stream r(seed, pid, epoch, TAG_MODEL);
+                const double dp = gk_simulate_cta<T>(xsd, md.v, r, xs, gs);    // :45
+                if (dp <= fmax(eps, dli)) {                                    // :54-59
+                    if (lead) { store_row<D>(P.theta[nxt], i, thp); P.logpi[nxt][i] = lp; P.delta[nxt][i] = dp; }
+                    dli = dp;
+                    acc_now = 1; flag |= ABCDEZ_FLAG_ACC;
+                }
+                if (lead) { nsim += 1; nacc += acc_now; }
+            }
+        }
+        if (lead) {
+            if ((uint8_t)acc_now != mv) P.moved[i] = (uint8_t)acc_now;
+            if (inj.flags) inj.flags[i] = flag;
+            const unsigned long long kdl = f64_key(dli);                       // extrema(delta), src/abcdez_mc.jl:146
+            kmn = kdl < kmn ? kdl : kmn; kmx = kdl > kmx ? kdl : kmx;
+        }
+    }
+    const bool last = sweep_finish<true>(c, &s_red, nsim, nacc, kmn, kmx, err);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, true);
+    if (last) ctrl_after_mc_sweep(P, c);
+}
+
 // ---- one dist! evaluation per row (stage-level model parity) ------------------------------------------------
+template <class T>
 __global__ void __launch_bounds__(GK_THREADS)
 gk_simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, const __grid_constant__ PhiloxKeys seed,
                    uint32_t epoch, uint32_t tag, uint32_t id0, double* __restrict__ dist)
@@ -303,45 +595,65 @@ gk_simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double
         double x[4];
         for (int k = 0; k < 4; ++k) x[k] = theta_pushed[i * 4 + k];
         Stream r(seed, id0 + (uint32_t)i, epoch, tag);
-        double d = gk_simulate_cta(x, md.v, r, xs, gs);
+        double d = gk_simulate_cta<T>(x, md.v, r, xs, gs);
         if (threadIdx.x == 0) dist[i] = d;
     }
 }
 
-static int g_gk_grid = 0;
-static unsigned gk_grid(int64_t N)
+// persistent grid: a multiple of the SM count (SMs x resident CTAs for this n)
+template <class T>
+static unsigned gk_grid(int64_t N, size_t smem)
 {
-    if (!g_gk_grid) {
-        size_t sm = gk_smem_bytes();
-        cudaFuncSetAttribute(gk_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cudaFuncSetAttribute(gk_smc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cudaFuncSetAttribute(gk_simulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    static size_t cached_smem = 0; static int cached_grid = 0;
+    if (cached_smem != smem || !cached_grid) {
+        cudaFuncSetAttribute(gk_init_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
+        cudaFuncSetAttribute(gk_smc_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
+        cudaFuncSetAttribute(gk_mc_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
+        cudaFuncSetAttribute(gk_simulate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
         int dev = 0, sms = 148, per = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gk_smc_sweep_kernel, GK_THREADS, sm) != cudaSuccess || per < 1) per = 1;
-        g_gk_grid = sms * per;              // persistent CTAs: a multiple of the SM count
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gk_smc_sweep_kernel<T>, GK_THREADS, smem) != cudaSuccess || per < 1) per = 1;
+        cached_grid = sms * per; cached_smem = smem;
     }
-    return (unsigned)(N < g_gk_grid ? N : g_gk_grid);
+    return (unsigned)(N < cached_grid ? N : cached_grid);
 }
 
+template <class T>
 static void gk_l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
-    gk_init_kernel<<<gk_grid(P.N), GK_THREADS, gk_smem_bytes(), st>>>(P, pr, md, philox_keys(seed), dp);
+    const size_t sm = gk_smem_bytes<T>(md);
+    gk_init_kernel<T><<<gk_grid<T>(P.N, sm), GK_THREADS, sm, st>>>(P, pr, md, philox_keys(seed), dp);
 }
+template <class T>
 static void gk_l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
 {
-    gk_smc_sweep_kernel<<<gk_grid(P.N), GK_THREADS, gk_smem_bytes(), st>>>(P, pr, md, inj);
+    const size_t sm = gk_smem_bytes<T>(md);
+    gk_smc_sweep_kernel<T><<<gk_grid<T>(P.N, sm), GK_THREADS, sm, st>>>(P, pr, md, inj);
 }
+template <class T>
+static void gk_l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
+                    const McArgs& mc)
+{
+    const size_t sm = gk_smem_bytes<T>(md);
+    gk_mc_sweep_kernel<T><<<gk_grid<T>(P.N, sm), GK_THREADS, sm, st>>>(P, pr, md, inj, mc);
+}
+template <class T>
 static void gk_l_sim(const ModelOps&, cudaStream_t st, const PriorDev*, const ModelData& md, int64_t N, const double* th, uint64_t seed,
                      uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double*)
 {
-    gk_simulate_kernel<<<gk_grid(N), GK_THREADS, gk_smem_bytes(), st>>>(md, N, th, philox_keys(seed), epoch, tag, id0, dist);
+    const size_t sm = gk_smem_bytes<T>(md);
+    gk_simulate_kernel<T><<<gk_grid<T>(N, sm), GK_THREADS, sm, st>>>(md, N, th, philox_keys(seed), epoch, tag, id0, dist);
 }
 
 const ModelOps* ops_gk()
 {
-    static const ModelOps o = { GK::name, GK::D, GK::BLOB, &gk_l_init, &gk_l_smc, nullptr /* abcdemc!: not for this model */, &gk_l_sim, nullptr };
+    static const ModelOps o = { GkMath<double>::name, 4, 0, &gk_l_init<double>, &gk_l_smc<double>, &gk_l_mc<double>, &gk_l_sim<double>, nullptr };
+    return &o;
+}
+const ModelOps* ops_gk_f32()
+{
+    static const ModelOps o = { GkMath<float>::name, 4, 0, &gk_l_init<float>, &gk_l_smc<float>, &gk_l_mc<float>, &gk_l_sim<float>, nullptr };
     return &o;
 }
 

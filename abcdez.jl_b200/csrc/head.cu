@@ -8,9 +8,12 @@
 // Round-2 structure.  At 10^6 particles the whole working set (delta, W, alive: 17 MB) lives in L2, so the
 // round-1 kernel (five passes, each a chain of load -> reduce -> barrier per 1024-particle tile, four grid
 // barriers) was bound by latency, not bandwidth: 50-60 us against ~6 us of L2 traffic.  Now
-//   * a CTA keeps its share of the population in REGISTERS: up to KT = 4 tiles (16 distances, 16 weights and
-//     the alive bytes per thread) are loaded once with all loads in flight together and reused by every phase
-//     (larger shares are processed in rounds of KT tiles and re-read per phase -- bandwidth bound then);
+//   * a CTA keeps its share of the population ON CHIP: up to KT = 4 tiles (16 distance keys and 16 weights per
+//     thread) are loaded once and reused by every phase (larger shares are processed in rounds of KT tiles and
+//     re-read per phase -- bandwidth bound then).  The share lives in shared memory as thread-private slots
+//     ([tile][k][thread], conflict-free, no barriers needed), not in registers: a first version with register
+//     arrays had to unroll every phase 16 times and came out at 26 000 SASS instructions, 37 % of whose stall
+//     samples were instruction-fetch misses (profiles/README.md); loops over tiles keep the code ~5x smaller;
 //   * the per-tile reductions of a round are batched (one pair of CTA barriers for KT tiles);
 //   * THREE grid barriers in the common case: after the window histogram, after the candidate compaction,
 //     after the per-tile weight sums.  The alive mask is decided together with wprod (wprod / wnorm > 0 <=>
@@ -44,7 +47,7 @@ constexpr int HEAD_THREADS = BK_THREADS;
 constexpr int HEAD_MIN_BLOCKS = 2;                // resident CTAs per SM the register budget is cut for
 constexpr int KT = 4;                             // tiles per round: 16 particles per thread stay in registers
 constexpr int KE = KT * 4;
-constexpr int CAND_SMEM = 4096;                   // candidates staged in shared memory for the per-CTA tail; longer
+constexpr int CAND_SMEM = 2048;                   // candidates staged in shared memory for the per-CTA tail; longer
                                                   // lists are first refined grid-cooperatively, one digit per round
 constexpr int CAND_DIRECT = 256;                  // ... and at most this many are ranked directly (one per thread)
 constexpr int NW = HEAD_THREADS / 32;
@@ -143,27 +146,6 @@ __device__ __forceinline__ double block_sum_all(double v, HeadSmem* s)
     return t;
 }
 
-// KT block sums at once, each with exactly the operations of block_sum (xor butterfly inside the warps, then
-// warp 0 adds the warp totals with the same butterfly): bit-identical to the stage kernels' per-tile sums.
-// Result t in out[t], valid in thread 0.
-__device__ __forceinline__ void block_sum_kt(const double (&acc)[KT], HeadSmem* s, double (&out)[KT])
-{
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double v[KT];
-#pragma unroll
-    for (int t = 0; t < KT; ++t) v[t] = warp_sum(acc[t]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int t = 0; t < KT; ++t) s->red[t][w] = v[t];
-    }
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int t = 0; t < KT; ++t) out[t] = warp_sum(lane < NW ? s->red[t][lane] : 0.0);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // tail: the rank-th smallest (0-based) of the M listed RELATIVE keys (all below 2^42), whether the next
 // order statistic ties with it, and else the smallest listed key above it.  Entirely inside the CTA; every
@@ -191,6 +173,7 @@ __device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M
     for (int p = 2; p < 6 && !found; ++p) {
         const int shift = pass_shift(p), nbins = pass_bins(p);
         hist_clear(s);
+#pragma unroll 1
         for (unsigned i = tid; i < M; i += HEAD_THREADS) {
             unsigned long long key = L[i];
             if ((key & himask) == prefix) atomicAdd(&s->hist[(unsigned)((key >> shift) & (unsigned long long)(nbins - 1))], 1u);
@@ -209,6 +192,7 @@ __device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M
             __syncthreads();
             if (tid == 0) s->flag = 0u;
             __syncthreads();
+#pragma unroll 1
             for (unsigned i = tid; i < M; i += HEAD_THREADS) {
                 unsigned long long key = L[i];
                 if ((key & himask) == prefix) s->wmin[atomicAdd(&s->flag, 1u)] = key;
@@ -233,6 +217,7 @@ __device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M
     a_rel = prefix;
     // #{keys <= v[j]} and min{key > v[j]} on the list
     unsigned cnt = 0; unsigned long long mn = ~0ull;
+#pragma unroll 1
     for (unsigned i = tid; i < M; i += HEAD_THREADS) {
         unsigned long long key = L[i];
         if (key <= a_rel) cnt++; else mn = key < mn ? key : mn;
@@ -292,12 +277,82 @@ __device__ __forceinline__ void collect_headers(const XchgDev& X, Ctrl* c, unsig
     __syncthreads();
 }
 
+// sharded runs: all-reduce of a histogram (+ optionally the first exchange's header: extrema, error).  Every CTA
+// of every rank calls; on return loc[] holds bins tid*8 .. tid*8+7 of the sum over all ranks and, when `first`,
+// s_x the header records of all ranks.  No grid barrier: CTA q posts this rank's record to rank q, reducer CTAs
+// sum 256 bins each into the local flag-in-word array, every CTA polls the sums from there.
+static __device__ __noinline__ void all_reduce_hist(const PopDev& P, Ctrl* c, unsigned long long seq, const unsigned* H, int nbins, bool first,
+                                                    unsigned (&loc)[SEL_BINS / HEAD_THREADS], unsigned long long* s_h, unsigned long long* s_x, bool& xok)
+{
+    const unsigned tid = threadIdx.x, G = gridDim.x;
+    const int R = P.x.world;
+    const unsigned slot = (unsigned)(seq & (XCHG_RING - 1)), flag = (unsigned)seq;
+    if (tid == 0) {
+        int e0 = c->err, e1 = __ldcg(&c->acc.err);
+        s_h[0] = __ldcg(&c->acc.dmin_key); s_h[1] = __ldcg(&c->acc.dmax_key);
+        s_h[2] = (unsigned long long)(e0 > e1 ? e0 : e1); s_h[3] = 0ull;
+    }
+    __syncthreads();
+    for (int role = blockIdx.x; role < R; role += G) post_record(P.x, role, seq, s_h, first ? 4 : 0, H, nbins);
+    unsigned long long* hg = hg_base(P.x);
+    for (int role = blockIdx.x; role < SEL_BINS / HEAD_THREADS; role += G) {       // 8 reducer roles x 256 bins
+        const int b = role * HEAD_THREADS + tid;
+        if (b < nbins) {
+            unsigned tot = 0;
+#pragma unroll 1
+            for (int r = 0; r < R; ++r) tot += ll_poll(ll_entry(P.x.mbox[P.x.rank], slot, r) + LL_HDR + b, flag, xok);
+            st_relaxed_sys(hg + b, ll_pack(tot, flag));
+        }
+    }
+    if (first) collect_headers(P.x, c, seq, 4, s_x, xok);
+#pragma unroll
+    for (int k = 0; k < SEL_BINS / HEAD_THREADS; ++k) {
+        const int b = tid * (SEL_BINS / HEAD_THREADS) + k;
+        loc[k] = b < nbins ? ll_poll(hg + b, flag, xok) : 0u;
+    }
+}
+
+// The CTA's share of one round in shared memory: thread tid owns the particles tile * 1024 + tid * 4 + k of each
+// of the round's tiles, as [tile][k][tid] so that its accesses are conflict-free.  Only the owning thread ever
+// touches an entry, so the phases need no CTA barrier for them: this is register-like storage that a loop can index.
+constexpr unsigned long long DEAD_KEY = ~0ull;            // dead or out-of-range particle (the key of one NaN pattern; NaNs are an error anyway)
+struct HeadShare {
+    unsigned long long key[KT][4][HEAD_THREADS];
+    double w[KT][4][HEAD_THREADS];
+};
+
+// distances of the round's tiles [tb, tb + nt) -> keys; with ext != nullptr also extrema(delta) over all particles
+// and the NaN check (ext[0] = min key, ext[1] = max key, ext[2] = NaN among alive)
+static __device__ __noinline__ void load_keys(const PopDev& P, const double* __restrict__ dl, unsigned tb, unsigned nt, HeadShare* sh,
+                                              unsigned long long* ext)
+{
+    const unsigned tid = threadIdx.x;
+    const uint32_t N = P.N;
+    unsigned long long kmn = ~0ull, kmx = 0ull, nan_seen = 0ull;
+#pragma unroll 1
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
+        double v[4] = { 0.0, 0.0, 0.0, 0.0 }; uint32_t al = 0u;
+        if (i0 < N) { load4_f64(dl, i0, N, v); al = load4_u8(P.alive, i0, N); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool valid = i0 + k < N, ok = valid && ((al >> (8 * k)) & 0xff);
+            const unsigned long long key = f64_key(v[k]);
+            if (ext && valid) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; if (ok && isnan(v[k])) nan_seen = 1ull; }
+            sh->key[t][k][tid] = ok ? key : DEAD_KEY;
+        }
+    }
+    if (ext) { ext[0] = kmn; ext[1] = kmx; ext[2] = nan_seen; }
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(const __grid_constant__ PopDev P, const unsigned per)
 {
     Ctrl* c = P.ctrl;
     if (c->stop) return;                                    // uniform: nobody reaches a grid barrier
     cg::grid_group grid = cg::this_grid();
-    __shared__ HeadSmem s;
+    extern __shared__ __align__(16) unsigned char head_raw[];
+    HeadSmem& s = *reinterpret_cast<HeadSmem*>(head_raw);
+    HeadShare* sh = reinterpret_cast<HeadShare*>(head_raw + sizeof(HeadSmem));
     __shared__ unsigned long long s_x[XCHG_MAXR * 8];       // exchanged header records: every rank's
     __shared__ unsigned long long s_h[4];                   // ... and this rank's, before it is posted
     const unsigned G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
@@ -305,7 +360,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     const unsigned t0 = blockIdx.x * per < ntiles ? blockIdx.x * per : ntiles;
     const unsigned t1 = t0 + per < ntiles ? t0 + per : ntiles;
     const unsigned rounds = (per + KT - 1) / KT;
-    const bool single = rounds == 1;                        // the CTA's whole share stays in registers
+    const bool single = rounds == 1;                        // the CTA's whole share stays in shared memory
+    auto round_tiles = [&](unsigned r, unsigned& tb) -> unsigned { tb = t0 + r * KT; return tb >= t1 ? 0u : (t1 - tb < (unsigned)KT ? t1 - tb : (unsigned)KT); };
     // schedule scalars of the previous iteration (CTA 0 overwrites them after the third barrier)
     const int cur = c->cur, kind = c->kind;
     const double eps_prev = c->eps, eps_old = c->eps_k, eps_target = c->eps_target, q_gamma = c->q_gamma;
@@ -320,61 +376,37 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     unsigned long long rank = c->sel_rank;
     const unsigned long long rank_all = rank;
 
-    // ---- this CTA's share -------------------------------------------------------------------------------
-    double v[KE]; uint32_t al[KT];
-    auto fetch = [&](unsigned r) {
-#pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            const unsigned tile = t0 + r * KT + t;
-            if (tile < t1) {
-                const size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-                load4_f64(dl, i0, N, &v[4 * t]);
-                al[t] = load4_u8(P.alive, i0, N);
-            } else {
-                al[t] = 0u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[4 * t + k] = 0.0;
-            }
-        }
-    };
-    auto in_range = [&](unsigned r, int t, int k) -> bool {
-        const unsigned tile = t0 + r * KT + t;
-        return tile < t1 && (size_t)tile * TILE + (size_t)tid * 4 + k < N;
-    };
-    if (single) fetch(0);
-
     // ---- first pass: window histogram (+ extrema(delta) over all particles, NaN check) ---------------------
-    // bin 2047 - ((kp - key) >> sh) for the 2047 * 2^sh keys at and below kp = key(eps_prev); bin 0 collects
-    // everything further below, keys above kp are counted apart.  The map is monotone: an exact select.
+    // bin 2047 - ((kp - key) >> sft) for the 2047 * 2^sft keys at and below kp = key(eps_prev); bin 0 collects
+    // everything further below, keys above kp stay outside.  The map is monotone: an exact select.
     const bool windowed = isfinite(eps_prev) && eps_prev > 0.0;
     const unsigned long long kp = f64_key(windowed ? eps_prev : 1.0);
-    const int sh = (win_shift_in > 0 && win_shift_in <= 43) ? win_shift_in - 1 : 42;
+    const int sft = (win_shift_in > 0 && win_shift_in <= 43) ? win_shift_in - 1 : 42;
     unsigned bin; unsigned long long before;
     unsigned long long lo_key = 0ull, hi_key = 0ull;        // the candidates' key range (inclusive)
     bool have_range = false;
     {
         hist_clear(&s);
-        unsigned long long kmn = ~0ull, kmx = 0ull; int nan_seen = 0;
+        unsigned long long kmn = ~0ull, kmx = 0ull, nan_seen = 0ull;
         unsigned n_low = 0;
         for (unsigned r = 0; r < rounds; ++r) {
-            if (!single) fetch(r);
-#pragma unroll
-            for (int t = 0; t < KT; ++t) {
+            unsigned tb; const unsigned nt = round_tiles(r, tb);
+            unsigned long long ext[3];
+            load_keys(P, dl, tb, nt, sh, ext);
+            kmn = ext[0] < kmn ? ext[0] : kmn; kmx = ext[1] > kmx ? ext[1] : kmx; nan_seen |= ext[2];
+#pragma unroll 1
+            for (unsigned t = 0; t < nt; ++t) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const bool ok = (al[t] >> (8 * k)) & 0xff;
-                    const double x = v[4 * t + k];
-                    const unsigned long long key = f64_key(x);
-                    if (in_range(r, t, k)) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
-                    if (ok && isnan(x)) nan_seen = 1;
+                    const unsigned long long key = sh->key[t][k][tid];
                     if (windowed) {
-                        if (ok && key <= kp) {                                 // (keys above kp stay outside the window's total)
-                            const unsigned long long dd = (kp - key) >> sh;
-                            if (dd >= 2047ull) n_low++;                      // most keys: counted in a register
+                        if (key <= kp) {                                       // (dead entries are above every key)
+                            const unsigned long long dd = (kp - key) >> sft;
+                            if (dd >= 2047ull) n_low++;                        // most keys: counted in a register
                             else atomicAdd(&s.hist[2047u - (unsigned)dd], 1u);
                         }
                     } else {
-                        hist_add(s.hist, ok, (unsigned)(key >> 53));           // generic pass 1: digit 53..63
+                        hist_add(s.hist, key != DEAD_KEY, (unsigned)(key >> 53));   // generic pass 1: digit 53..63
                     }
                 }
             }
@@ -394,38 +426,11 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     grid.sync();                                                                                   // ---- barrier 1
     // the whole population's histogram: bins tid*8 .. tid*8+7 into registers
     unsigned loc[SEL_BINS / HEAD_THREADS];
-    auto all_reduce_hist = [&](unsigned* H, int nbins, bool first) {
-        // sharded: header (extrema, error, n_above) + histogram -> every rank; reducer CTAs sum 256 bins each into the
-        // local flag-in-word array, every CTA reads the sums from there (no second grid barrier)
-        ++seq;
-        const unsigned slot = (unsigned)(seq & (XCHG_RING - 1)), flag = (unsigned)seq;
-        if (tid == 0) {
-            int e0 = c->err, e1 = __ldcg(&c->acc.err);
-            s_h[0] = __ldcg(&c->acc.dmin_key); s_h[1] = __ldcg(&c->acc.dmax_key);
-            s_h[2] = (unsigned long long)(e0 > e1 ? e0 : e1); s_h[3] = 0ull;
-        }
-        __syncthreads();
-        for (int role = blockIdx.x; role < R; role += G) post_record(P.x, role, seq, s_h, first ? 4 : 0, H, nbins);
-        unsigned long long* hg = hg_base(P.x);
-        for (int role = blockIdx.x; role < SEL_BINS / HEAD_THREADS; role += G) {       // 8 reducer roles x 256 bins
-            const int b = role * HEAD_THREADS + tid;
-            if (b < nbins) {
-                unsigned tot = 0;
-                for (int r = 0; r < R; ++r) tot += ll_poll(ll_entry(P.x.mbox[P.x.rank], slot, r) + LL_HDR + b, flag, xok);
-                st_relaxed_sys(hg + b, ll_pack(tot, flag));
-            }
-        }
-        if (first) collect_headers(P.x, c, seq, 4, s_x, xok);
-#pragma unroll
-        for (int k = 0; k < SEL_BINS / HEAD_THREADS; ++k) {
-            const int b = tid * (SEL_BINS / HEAD_THREADS) + k;
-            loc[k] = b < nbins ? ll_poll(hg + b, flag, xok) : 0u;
-        }
-    };
     auto first_exchange = [&](unsigned* H) {
         if (sharded) {
-            all_reduce_hist(H, 2048, true);
+            all_reduce_hist(P, c, ++seq, H, 2048, true, loc, s_h, s_x, xok);
             unsigned long long mn = ~0ull, mx = 0ull, e = 0ull;
+#pragma unroll 1
             for (int r = 0; r < R; ++r) {
                 mn = s_x[4 * r] < mn ? s_x[4 * r] : mn; mx = s_x[4 * r + 1] > mx ? s_x[4 * r + 1] : mx;
                 e = s_x[4 * r + 2] > e ? s_x[4 * r + 2] : e;
@@ -445,8 +450,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         pick_bin(loc, rank, &s, bin, before);
         if (bin >= 1u && bin != 0xffffffffu) {              // inside the window
             const unsigned long long dd = 2047ull - bin;
-            hi_key = kp - (dd << sh);
-            const unsigned long long span = (dd + 1ull) << sh;
+            hi_key = kp - (dd << sft);
+            const unsigned long long span = (dd + 1ull) << sft;
             lo_key = kp >= span ? kp - span + 1ull : 0ull;
             rank -= before;
             have_range = true;
@@ -459,16 +464,16 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             // the window pass has the extrema already; this pass only builds the leading-digit histogram
             hist_clear(&s);
             for (unsigned r = 0; r < rounds; ++r) {
-                if (!single) fetch(r);
+                unsigned tb; const unsigned nt = round_tiles(r, tb);
+                if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+#pragma unroll 1
+                for (unsigned t = 0; t < nt; ++t)
 #pragma unroll
-                for (int t = 0; t < KT; ++t)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        hist_add(s.hist, (al[t] >> (8 * k)) & 0xff, (unsigned)(f64_key(v[4 * t + k]) >> 53));
+                    for (int k = 0; k < 4; ++k) { const unsigned long long key = sh->key[t][k][tid]; hist_add(s.hist, key != DEAD_KEY, (unsigned)(key >> 53)); }
             }
             hist_flush(&s, H1, 2048);
             grid.sync();
-            if (sharded) all_reduce_hist(H1, 2048, false); else load_bins_global(H1, 2048, loc);
+            if (sharded) all_reduce_hist(P, c, ++seq, H1, 2048, false, loc, s_h, s_x, xok); else load_bins_global(H1, 2048, loc);
         } else {
             first_exchange(H1);
         }
@@ -487,19 +492,19 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         // generic pass 2: digit 42..52 among the keys of that bin
         hist_clear(&s);
         for (unsigned r = 0; r < rounds; ++r) {
-            if (!single) fetch(r);
-#pragma unroll
-            for (int t = 0; t < KT; ++t)
+            unsigned tb; const unsigned nt = round_tiles(r, tb);
+            if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+#pragma unroll 1
+            for (unsigned t = 0; t < nt; ++t)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const unsigned long long key = f64_key(v[4 * t + k]);
-                    const bool ok = ((al[t] >> (8 * k)) & 0xff) && ((key & himask) == prefix);
-                    hist_add(s.hist, ok, (unsigned)((key >> 42) & 2047ull));
+                    const unsigned long long key = sh->key[t][k][tid];
+                    hist_add(s.hist, key != DEAD_KEY && (key & himask) == prefix, (unsigned)((key >> 42) & 2047ull));
                 }
         }
         hist_flush(&s, H2, 2048);
         grid.sync();
-        if (sharded) all_reduce_hist(H2, 2048, false); else load_bins_global(H2, 2048, loc);
+        if (sharded) all_reduce_hist(P, c, ++seq, H2, 2048, false, loc, s_h, s_x, xok); else load_bins_global(H2, 2048, loc);
         pick_bin(loc, rank, &s, bin, before);
         prefix |= (unsigned long long)bin << 42;
         rank -= before;
@@ -511,17 +516,17 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         unsigned long long* cand = P.cand[0];
         unsigned long long mab = ~0ull, cmn = ~0ull, cmx = 0ull;
         for (unsigned r = 0; r < rounds; ++r) {
-            if (!single) fetch(r);
-#pragma unroll
-            for (int t = 0; t < KT; ++t) {
+            unsigned tb; const unsigned nt = round_tiles(r, tb);
+            if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+#pragma unroll 1
+            for (unsigned t = 0; t < nt; ++t) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const unsigned long long key = f64_key(v[4 * t + k]);
-                    const bool ok = (al[t] >> (8 * k)) & 0xff;
-                    const bool is_c = ok && key >= lo_key && key <= hi_key;
-                    if (ok && key > hi_key) mab = key < mab ? key : mab;
+                    const unsigned long long key = sh->key[t][k][tid];
+                    const bool is_c = key >= lo_key && key <= hi_key;
+                    if (key > hi_key && key != DEAD_KEY) mab = key < mab ? key : mab;
                     const unsigned m = __ballot_sync(0xffffffffu, is_c);
-                    if (m) {
+                    if (m) {                                                   // (rare: ~10^-4 of the keys)
                         unsigned base = 0;
                         if (lane == 0) base = (unsigned)atomicAdd(&c->acc.cand_count[0], (unsigned long long)__popc(m));
                         base = __shfl_sync(0xffffffffu, base, 0);
@@ -536,8 +541,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         }
         if (tid == 0) { s.mn = ~0ull; s.mx = 0ull; s.mab = ~0ull; }
         __syncthreads();
-        mab = warp_min_u64(mab); cmn = warp_min_u64(cmn); cmx = warp_max_u64(cmx);
-        if (lane == 0) { atomicMin(&s.mab, mab); atomicMin(&s.mn, cmn); atomicMax(&s.mx, cmx); }
+        mab = warp_min_u64(mab);
+        if (lane == 0 && mab != ~0ull) atomicMin(&s.mab, mab);
+        if (cmn != ~0ull) { atomicMin(&s.mn, cmn); atomicMax(&s.mx, cmx); }       // (only the few threads that hold a candidate)
         __syncthreads();
         if (tid == 0) {
             if (s.mab != ~0ull) atomicMin(&c->acc.min_above, s.mab);
@@ -569,6 +575,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             if (M <= (unsigned)XCHG_GCAND_PER) {
                 unsigned long long* gr = gcand_region(P.x.mbox[role], P.x.rank);
                 const unsigned long long* src = P.cand[g & 1];
+#pragma unroll 1
                 for (unsigned i = tid; i < M; i += HEAD_THREADS) {
                     const unsigned long long key = __ldcg(&src[i]);
                     st_relaxed_sys(gr + 2 * i, ll_pack((unsigned)key, flag));
@@ -579,6 +586,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         collect_headers(P.x, c, seq, 4, s_x, xok);
         Mg = 0; cmin = ~0ull; cmax = 0ull; min_above = ~0ull;
         bool fits = true;
+#pragma unroll 1
         for (int r = 0; r < R; ++r) {
             const unsigned long long m = s_x[4 * r];
             Mg += m; fits = fits && m <= (unsigned long long)XCHG_GCAND_PER;
@@ -596,17 +604,19 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         unsigned* H = P.sel_hist + (size_t)p_next * SEL_BINS;
         const unsigned long long* src = P.cand[g & 1]; unsigned long long* dst = P.cand[(g + 1) & 1];
         hist_clear(&s);
+#pragma unroll 1
         for (size_t i = (size_t)blockIdx.x * HEAD_THREADS + tid; i < M; i += (size_t)G * HEAD_THREADS)
             atomicAdd(&s.hist[(unsigned)((__ldcg(&src[i]) >> shift) & (unsigned long long)(nbins - 1))], 1u);
         hist_flush(&s, H, nbins);
         grid.sync();
-        if (sharded) all_reduce_hist(H, nbins, false); else load_bins_global(H, nbins, loc);
+        if (sharded) all_reduce_hist(P, c, ++seq, H, nbins, false, loc, s_h, s_x, xok); else load_bins_global(H, nbins, loc);
         pick_bin(loc, rank, &s, bin, before);
         prefix |= (unsigned long long)bin << shift; himask = pass_himask_after(p_next);
         rank -= before;
         {
             unsigned long long mab = ~0ull, cmn = ~0ull, cmx = 0ull;
             const size_t rnds = ((size_t)M + (size_t)G * HEAD_THREADS - 1) / ((size_t)G * HEAD_THREADS);
+#pragma unroll 1
             for (size_t r = 0; r < rnds; ++r) {
                 const size_t i = r * (size_t)G * HEAD_THREADS + (size_t)blockIdx.x * HEAD_THREADS + tid;
                 const unsigned long long key = i < M ? __ldcg(&src[i]) : 0ull;
@@ -645,16 +655,21 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             // every rank's candidates, from the local gather area: rank r's keys at its region, its count in s_x
             const unsigned flag = (unsigned)seq;
             unsigned off = 0;
+#pragma unroll 1
             for (int r = 0; r < R; ++r) {
                 const unsigned m = (unsigned)s_x[4 * r];
                 const unsigned long long* gr = gcand_region(P.x.mbox[P.x.rank], r);
+#pragma unroll 1
                 for (unsigned i = tid; i < m; i += HEAD_THREADS) {
                     const unsigned lo = ll_poll(gr + 2 * i, flag, xok), hi = ll_poll(gr + 2 * i + 1, flag, xok);
                     s.cand[off + i] = ((unsigned long long)hi << 32) | lo;
                 }
                 off += m;
             }
-        } else { for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&P.cand[g & 1][i]); }
+        } else {
+#pragma unroll 1
+            for (unsigned i = tid; i < (unsigned)Mg; i += HEAD_THREADS) s.cand[i] = __ldcg(&P.cand[g & 1][i]);
+        }
         __syncthreads();
         unsigned long long a_rel, b_rel; bool tie, has_b;
         // after refine rounds the list holds the keys that match (prefix, himask); the rank is relative to them
@@ -681,61 +696,37 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         }
     }
 
-    // ---- reweight pass A: ws, wprod, per-tile sums and alive counts ------------------------------------
-    double w[KE];
-    auto fetch_w = [&](unsigned r) {
-#pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            const unsigned tile = t0 + r * KT + t;
-            if (tile < t1) load4_f64(P.W, (size_t)tile * TILE + (size_t)tid * 4, N, &w[4 * t]);
-            else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) w[4 * t + k] = 0.0;
-            }
-        }
-    };
+    // ---- reweight pass A: ws, wprod (kept in shared memory when the share is a single round), per-tile sums and alive counts ----
     for (unsigned r = 0; r < rounds; ++r) {
-        if (!single) fetch(r);
-        fetch_w(r);
-        double acc[KT]; unsigned cnt[KT];
-#pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            acc[t] = 0.0; cnt[t] = 0u;
+        unsigned tb; const unsigned nt = round_tiles(r, tb);
+        if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+#pragma unroll 1
+        for (unsigned t = 0; t < nt; ++t) {
+            const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
+            double w[4] = { 0.0, 0.0, 0.0, 0.0 };
+            if (i0 < N) load4_f64(P.W, i0, N, w);
+            double acc = 0.0; unsigned cnt = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool ok = ((al[t] >> (8 * k)) & 0xff) && in_range(r, t, k);
-                double ws = 0.0;
-                if (ok) ws = abck_ws(kind, eps, eps_old, v[4 * t + k]);                           // :75
-                const double wp_ = ok ? w[4 * t + k] * ws : 0.0;                                   // :308
-                w[4 * t + k] = wp_;
-                acc[t] += wp_;
-                cnt[t] += (wp_ > 0.0) ? 1u : 0u;
+                const unsigned long long key = sh->key[t][k][tid];
+                double wp_ = 0.0;
+                if (key != DEAD_KEY) wp_ = w[k] * abck_ws(kind, eps, eps_old, key_f64(key));      // :75, :308
+                w[k] = wp_;
+                sh->w[t][k][tid] = wp_;
+                acc += wp_;
+                cnt += (wp_ > 0.0) ? 1u : 0u;
             }
-            cnt[t] = warp_sum_u(cnt[t]);
+            if (!single && i0 < N) store4_f64(P.W, i0, N, w);
+            acc = warp_sum(acc); cnt = warp_sum_u(cnt);
+            if (lane == 0) { s.red[t][wp] = acc; s.wcnt[t][wp] = cnt; }
         }
-        if (!single) {
-#pragma unroll
-            for (int t = 0; t < KT; ++t) {
-                const unsigned tile = t0 + r * KT + t;
-                if (tile < t1) store4_f64(P.W, (size_t)tile * TILE + (size_t)tid * 4, N, &w[4 * t]);
-            }
-        }
-        double tsum[KT];
-        if (lane == 0) {
-#pragma unroll
-            for (int t = 0; t < KT; ++t) s.wcnt[t][wp] = cnt[t];
-        }
-        block_sum_kt(acc, &s, tsum);                        // (its barriers also publish wcnt)
-        if (tid == 0) {
-#pragma unroll
-            for (int t = 0; t < KT; ++t) {
-                const unsigned tile = t0 + r * KT + t;
-                if (tile < t1) {
-                    unsigned tc = 0;
-                    for (int q = 0; q < NW; ++q) tc += s.wcnt[t][q];
-                    P.partial[tile] = tsum[t];
-                    P.tile_cnt[tile] = tc;
-                }
+        __syncthreads();
+        if (wp == 0) {                                      // warp 0 adds the warp totals of every tile (block_sum's second level)
+#pragma unroll 1
+            for (unsigned t = 0; t < nt; ++t) {
+                const double tsum = warp_sum(lane < NW ? s.red[t][lane] : 0.0);
+                const unsigned tc = warp_sum_u(lane < NW ? s.wcnt[t][lane] : 0u);
+                if (lane == 0) { P.partial[tb + t] = tsum; P.tile_cnt[tb + t] = tc; }
             }
         }
         __syncthreads();
@@ -745,6 +736,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     unsigned n_alive, my_off;
     {
         double a = 0.0; unsigned tot = 0, pre = 0;
+#pragma unroll 2
         for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) {
             a += __ldcg(&P.partial[b]);
             const unsigned tc = __ldcg(&P.tile_cnt[b]);
@@ -766,6 +758,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         for (int role = blockIdx.x; role < R; role += G) post_record(P.x, role, seq, s_h, 2, nullptr, 0);
         collect_headers(P.x, c, seq, 2, s_x, xok);
         double tot = 0.0; unsigned ng = 0;
+#pragma unroll 1
         for (int r = 0; r < R; ++r) { tot += __longlong_as_double((long long)s_x[2 * r]); ng += (unsigned)s_x[2 * r + 1]; }
         wnorm = tot; n_alive_g = ng;
         if (blockIdx.x == 0 && tid < (unsigned)R) c->rank_alive[tid] = (unsigned)s_x[2 * tid + 1];
@@ -780,68 +773,76 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     }
 
     // ---- pass B: Wns, alive, sum(Wns^2) per tile, alive-first particle list -- no further grid barrier ----
+    // w / wnorm through the reciprocal (pdiv_r, common.cuh: the same double as the division, 3 instructions; operands
+    // outside its premises take the plain division)
     double* partial2 = P.partial + ntiles;
     const bool need_list = n_alive != N;
+    const double rwn = (wnorm >= 0x1p-100 && wnorm <= 0x1p100 &&
+                        ((unsigned long long)__double_as_longlong(wnorm) & 0x000fffffffffffffull) != 0x000fffffffffffffull) ? 1.0 / wnorm : 0.0;
     unsigned off = my_off;
-    int mismatch = 0;
+    int mismatch = 0; double wal = 0.0; unsigned any = 0;
     for (unsigned r = 0; r < rounds; ++r) {
-        if (!single) fetch_w(r);
-        double acc[KT]; uint32_t nal[KT]; double wal = 0.0; unsigned any = 0;
-#pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            acc[t] = 0.0; nal[t] = 0u;
+        unsigned tb; const unsigned nt = round_tiles(r, tb);
+#pragma unroll 1
+        for (unsigned t = 0; t < nt; ++t) {
+            const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
+            double w[4] = { 0.0, 0.0, 0.0, 0.0 };
+            if (!single && i0 < N) load4_f64(P.W, i0, N, w);
+            double acc = 0.0; uint32_t nal = 0u; unsigned cnt = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (in_range(r, t, k)) {
-                    const double wp_ = w[4 * t + k];
-                    const double q = wp_ / wnorm;                                                 // :310
+                if (i0 + k < N) {
+                    const double wp_ = single ? sh->w[t][k][tid] : w[k];
+                    const double q = (wp_ == 0.0 && rwn != 0.0) ? wp_ : pdiv_r(wp_, wnorm, rwn);      // :310 (0 / wnorm without the detour)
                     const bool a = (q > 0.0);                                                     // :311
                     if (a != (wp_ > 0.0)) mismatch = 1;
-                    if (a) { nal[t] |= 1u << (8 * k); wal = q; any = 1; }
-                    acc[t] += q * q;
-                    w[4 * t + k] = q;
+                    if (a) { nal |= 1u << (8 * k); wal = q; any = 1; cnt++; }
+                    acc += q * q;
+                    w[k] = q;
                 }
             }
-            const unsigned tile = t0 + r * KT + t;
-            if (tile < t1) {
-                const size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-                store4_f64(P.W, i0, N, &w[4 * t]);
-                if (i0 + 3 < N) *reinterpret_cast<uint32_t*>(P.alive + i0) = nal[t];
-                else { for (int k = 0; k < 4; ++k) if (i0 + k < N) P.alive[i0 + k] = (nal[t] >> (8 * k)) & 0xff; }
+            if (i0 < N) {
+                store4_f64(P.W, i0, N, w);
+                if (i0 + 3 < N) *reinterpret_cast<uint32_t*>(P.alive + i0) = nal;
+                else { for (int k = 0; k < 4; ++k) if (i0 + k < N) P.alive[i0 + k] = (nal >> (8 * k)) & 0xff; }
             }
-        }
-        if (any) c->acc.w_alive = wal;          // indicator kernels: every alive weight is this same double
-        double tsum[KT];
-        block_sum_kt(acc, &s, tsum);
-        if (tid == 0) {
+            // this thread's alive flags and their count stay in shared memory for the list below (its own key slots are free now)
+            sh->key[t][0][tid] = ((unsigned long long)cnt << 32) | nal;
+            acc = warp_sum(acc);
+            unsigned incl = cnt;                                               // inclusive scan of the alive counts inside the warp
 #pragma unroll
-            for (int t = 0; t < KT; ++t) { const unsigned tile = t0 + r * KT + t; if (tile < t1) partial2[tile] = tsum[t]; }
+            for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += u; }
+            sh->key[t][1][tid] = incl;
+            if (lane == 0) s.red[t][wp] = acc;
+            if (lane == 31) s.wcnt[t][wp] = incl;
+        }
+        __syncthreads();
+        if (wp == 0) {
+#pragma unroll 1
+            for (unsigned t = 0; t < nt; ++t) {
+                const double tsum = warp_sum(lane < NW ? s.red[t][lane] : 0.0);
+                if (lane == 0) partial2[tb + t] = tsum;
+            }
         }
         if (need_list) {
             // alive particles first (index order), the dead ones behind them
-#pragma unroll
-            for (int t = 0; t < KT; ++t) {
-                const unsigned tile = t0 + r * KT + t;
-                if (tile >= t1) break;
-                const size_t i0 = (size_t)tile * TILE + (size_t)tid * 4;
-                unsigned cnt = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) cnt += ((nal[t] >> (8 * k)) & 0xff) ? 1u : 0u;
-                unsigned incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += u; }
-                __syncthreads();
-                if (lane == 31) s.part[wp] = incl;
-                __syncthreads();
+#pragma unroll 1
+            for (unsigned t = 0; t < nt; ++t) {
+                const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
+                const unsigned long long pk = sh->key[t][0][tid];
+                const uint32_t nal = (uint32_t)pk; const unsigned cnt = (unsigned)(pk >> 32), incl = (unsigned)sh->key[t][1][tid];
                 unsigned woff = 0, ttot = 0;
-                for (int q = 0; q < NW; ++q) { if (q < (int)wp) woff += s.part[q]; ttot += s.part[q]; }
+#pragma unroll
+                for (int q = 0; q < NW; ++q) { const unsigned wc = s.wcnt[t][q]; if (q < (int)wp) woff += wc; ttot += wc; }
                 unsigned pos = off + woff + incl - cnt;                       // alive before element i0
                 unsigned dpos = n_alive + ((unsigned)i0 - pos);               // dead before element i0
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (i0 + k < N) {
-                        if ((nal[t] >> (8 * k)) & 0xff) P.alive_list[pos++] = (uint32_t)(i0 + k);
-                        else P.alive_list[dpos++] = (uint32_t)(i0 + k);
+                        // (the bounds only bite when the alive counts of pass A disagree with these flags: NaN weights,
+                        // reported as an error below -- the list must still not be overrun)
+                        if ((nal >> (8 * k)) & 0xff) { if (pos < N) P.alive_list[pos] = (uint32_t)(i0 + k); pos++; }
+                        else { if (dpos < N) P.alive_list[dpos] = (uint32_t)(i0 + k); dpos++; }
                     }
                 }
                 off += ttot;
@@ -849,6 +850,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         }
         __syncthreads();
     }
+    if (any) c->acc.w_alive = wal;              // indicator kernels: every alive weight is this same double
     if (mismatch) atomicMax(&c->acc.alive_mismatch, 1);
     if (!xok) xchg_fail(c);
 
@@ -862,17 +864,17 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             if (tid < 32) {
                 unsigned long long rec[2] = { (unsigned long long)__double_as_longlong(sumsq),
                                               (unsigned long long)__double_as_longlong(__ldcg(&c->acc.w_alive)) }, got[2];
-                const bool valid = xchg_ll_warp_seq<2>(P.x, c, seq, rec, got);
+                xchg_ll_warp_seq<2>(P.x, c, seq, rec, got);
                 // lane r holds rank r's record: rank-ordered sum by lane 0
-                double tot = 0.0; double wal = 0.0; bool have = false;
+                double tot = 0.0; double wal_g = 0.0; bool have = false;
+#pragma unroll 1
                 for (int r = 0; r < R; ++r) {
                     const unsigned long long s0 = __shfl_sync(0xffffffffu, got[0], r), s1 = __shfl_sync(0xffffffffu, got[1], r);
                     tot += __longlong_as_double((long long)s0);
-                    if (!have && __ldcg(&c->rank_alive[r])) { wal = __longlong_as_double((long long)s1); have = true; }
+                    if (!have && __ldcg(&c->rank_alive[r])) { wal_g = __longlong_as_double((long long)s1); have = true; }
                 }
-                (void)valid;
                 if (tid == 0) {
-                    if (have) __stcg(&c->acc.w_alive, wal);                  // same double on every rank
+                    if (have) __stcg(&c->acc.w_alive, wal_g);                // same double on every rank
                     sumsq = tot;
                 }
             }
@@ -887,13 +889,16 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     }
 }
 
+static inline size_t head_smem_bytes() { return sizeof(HeadSmem) + sizeof(HeadShare); }
+
 // resident CTAs per SM of head_kernel, per device (cooperative launches need the whole grid resident)
 static int head_blocks_per_sm(int device)
 {
     static int cache[64] = { 0 };
     if (device >= 0 && device < 64 && cache[device] > 0) return cache[device];
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, head_kernel, HEAD_THREADS, 0) != cudaSuccess || nb < 1) nb = 1;
+    cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem_bytes());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, head_kernel, HEAD_THREADS, head_smem_bytes()) != cudaSuccess || nb < 1) nb = 1;
     nb = nb > HEAD_MIN_BLOCKS ? HEAD_MIN_BLOCKS : nb;
     if (device >= 0 && device < 64) cache[device] = nb;
     return nb;
@@ -911,7 +916,7 @@ int launch_head(cudaStream_t st, const PopDev& P, int sm_count)
     if (G < 1) G = 1;
     PopDev Pc = P;
     void* args[] = { (void*)&Pc, (void*)&per };
-    if (cudaLaunchCooperativeKernel((const void*)head_kernel, dim3(G), dim3(HEAD_THREADS), args, 0, st) != cudaSuccess) return -1;
+    if (cudaLaunchCooperativeKernel((const void*)head_kernel, dim3(G), dim3(HEAD_THREADS), args, head_smem_bytes(), st) != cudaSuccess) return -1;
     return 1;
 }
 

@@ -3,4 +3,5 @@
 
 namespace abcdez {
 ABCDEZ_DEFINE_MODEL(ops_lotka_volterra, LotkaVolterra)
+ABCDEZ_DEFINE_MODEL(ops_lotka_volterra_lin, LotkaVolterraLin)
 }  // namespace abcdez

@@ -105,8 +105,9 @@ struct SweepInj {
 };
 
 struct McArgs {
-    double eps_pop, eps_target;
-    const double* sorted_delta;   // delta sorted ascending
+    double eps_pop, eps_target;   // stage calls: given by the caller
+    int from_ctrl;                // abcdez_mc_run: eps_target and extrema(delta) (-> eps_pop, src/abcdez_mc.jl:146-147) from the control block
+    const double* sorted_delta;   // delta sorted ascending (ties in index order)
     const uint32_t* order;        // particle index per sorted position
 };
 
@@ -153,8 +154,8 @@ int launch_strat_indices(cudaStream_t, int64_t N, const double* W_dev, const dou
                          double* partial_dev, SeqTab* tabs_dev, int mode, long long* inds_dev);
 int launch_push_rows(cudaStream_t, const PopDev&, const PriorDev&, int D, double* out_dense);
 int launch_pack_rows(cudaStream_t, int D, int64_t N, const double* dense, double* rows, int to_rows);
-int launch_mc_prepare(cudaStream_t, uint32_t N, const double* delta_live, double* sorted_delta, uint32_t* order,
-                      void* tmp, size_t tmp_bytes);
+int launch_mc_prepare(cudaStream_t, const PopDev&, double* sorted_delta, uint32_t* order, void* tmp, size_t tmp_bytes,
+                      int force);          // mcsort.cu; force = 0: decided on the device (extrema(delta) vs eps_target)
 size_t mc_sort_tmp_bytes(int64_t N);
 
 // sharded runs, host side (comm.cu)

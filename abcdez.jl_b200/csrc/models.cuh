@@ -137,14 +137,17 @@ struct Wiener {
     }
 };
 
-// config 4: Lotka-Volterra, fixed-step RK4 (see DESIGN.md for the data layout)
-struct LotkaVolterra {
+// config 4: Lotka-Volterra, fixed-step RK4 (see DESIGN.md for the data layout).  Two competing models for the
+// evidence comparison: the classical one (predators grow with the encounter rate x y) and a variant whose
+// predators grow with the prey density alone (LINEAR = true, "lotka_volterra_lin").
+template <bool LINEAR>
+struct LotkaVolterraT {
     static constexpr int D = 4, BLOB = 0, NOISE = 0;
-    static constexpr const char* name = "lotka_volterra";
+    static constexpr const char* name = LINEAR ? "lotka_volterra_lin" : "lotka_volterra";
     __device__ static __forceinline__ void rhs(const double* th, double x, double y, double& dx, double& dy)
     {
         dx = th[0] * x - th[1] * x * y;
-        dy = th[2] * x * y - th[3] * y;
+        dy = LINEAR ? th[2] * x - th[3] * y : th[2] * x * y - th[3] * y;
     }
     __device__ static double run(const double* th, const double* data, SimRng& r, double*)
     {
@@ -170,6 +173,8 @@ struct LotkaVolterra {
         return sqrt(acc / (2.0 * nobs));
     }
 };
+typedef LotkaVolterraT<false> LotkaVolterra;
+typedef LotkaVolterraT<true> LotkaVolterraLin;
 
 // config 5: linear birth-death process, Gillespie SSA (divergent trajectory lengths)
 struct BirthDeath {
@@ -229,7 +234,7 @@ struct Socks {
 enum {
     M_GAUSS1D = 0, M_GAUSS1D_BLOB = 1, M_GAUSS_CORR10 = 2, M_DIRAC = 3, M_NORMDU = 4, M_TWOD = 5,
     M_TWOD_INF = 6, M_MIXTURE = 7, M_WIENER = 8, M_LOTKA_VOLTERRA = 9, M_BIRTH_DEATH = 10, M_GK = 11,
-    M_SOCKS = 12, M_COUNT = 13
+    M_SOCKS = 12, M_GK_F32 = 13, M_LOTKA_VOLTERRA_LIN = 14, M_COUNT = 15
 };
 
 }  // namespace abcdez

@@ -7,7 +7,8 @@ namespace abcdez {
 const ModelOps* ops_gauss1d(); const ModelOps* ops_gauss1d_blob(); const ModelOps* ops_gauss_corr10();
 const ModelOps* ops_dirac(); const ModelOps* ops_normdu(); const ModelOps* ops_twod(); const ModelOps* ops_twod_inf();
 const ModelOps* ops_mixture(); const ModelOps* ops_wiener(); const ModelOps* ops_lotka_volterra();
-const ModelOps* ops_birth_death(); const ModelOps* ops_socks(); const ModelOps* ops_gk();
+const ModelOps* ops_birth_death(); const ModelOps* ops_socks(); const ModelOps* ops_gk(); const ModelOps* ops_gk_f32();
+const ModelOps* ops_lotka_volterra_lin();
 
 
 const ModelOps* model_ops(int id)
@@ -26,6 +27,8 @@ const ModelOps* model_ops(int id)
     case M_BIRTH_DEATH: return ops_birth_death();
     case M_GK: return ops_gk();            // CTA-cooperative simulator (gk.cu)
     case M_SOCKS: return ops_socks();
+    case M_GK_F32: return ops_gk_f32();    // relaxed-precision mode of the same simulator
+    case M_LOTKA_VOLTERRA_LIN: return ops_lotka_volterra_lin();
     }
     return rtc_model_ops(id);          // runtime-compiled models (rtc.cu) follow the static ones
 }

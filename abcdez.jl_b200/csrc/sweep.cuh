@@ -367,11 +367,15 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
+    if (mc.from_ctrl && (c->stop | c->err)) return;                        // a generation behind an error
     const int cur = c->cur, nxt = cur ^ 1;
     const uint32_t N = P.N;
     const double* __restrict__ th = P.theta[cur];
     __shared__ SweepSmem s_red;
     sweep_smem_init(&s_red);
+    // abcdez_mc_run: the schedule scalars live on the device (no host round trip per generation)
+    const double eps_target = mc.from_ctrl ? c->eps_target : mc.eps_target;
+    const double eps_pop = mc.from_ctrl ? fmax(eps_target, c->dmin + 0.0 * (c->dmax - c->dmin)) : mc.eps_pop;   // src/abcdez_mc.jl:146-147, alpha = 0 (:107)
 
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
@@ -391,7 +395,7 @@ mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorD
         const PhiloxKeys& seed = P.keys;
         const uint32_t epoch = c->sweep_epoch;
         uint32_t s = i;                                                    // :18
-        const double eps = (dli <= mc.eps_target) ? mc.eps_target : mc.eps_pop;   // :19
+        const double eps = (dli <= eps_target) ? eps_target : eps_pop;   // :19
         if (dli > eps) {                                                   // :20-24
             if (inj.s) s = (uint32_t)inj.s[i];
             else {

@@ -54,7 +54,8 @@ class _SmcResult(C.Structure):
                 ("eps", C.c_double), ("logZ", C.c_double), ("iters", C.c_int64), ("nsims", C.c_int64),
                 ("hist_len", C.c_int32), ("status", C.c_int32),
                 ("n_resamples", C.c_int64), ("n_sweeps", C.c_int64), ("n_launches", C.c_int64),
-                ("sweep_ms", C.c_double), ("total_ms", C.c_double), ("init_ms", C.c_double)]
+                ("sweep_ms", C.c_double), ("total_ms", C.c_double), ("init_ms", C.c_double),
+                ("hist_dropped", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class _McOpts(C.Structure):
@@ -593,7 +594,9 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
         print("Warning: No alive particles")                                 # src/abcdez_smc.jl:375
     stats = dict(n_resamples=r.n_resamples, n_sweeps=r.n_sweeps, n_launches=r.n_launches, sweep_ms=r.sweep_ms,
                  total_ms=r.total_ms, init_ms=r.init_ms, seed=o.seed, rank=ctx.rank, world=ctx.world,
-                 nparticles=Nglobal)
+                 nparticles=Nglobal, hist_dropped=r.hist_dropped)
+    if r.hist_dropped and verbose:
+        print(f"Warning: {r.hist_dropped} history records did not fit hist_cap={hist_cap}; the histories are truncated")
     Pout = P[:, 0] if scalar else P
     out = SMCResult(Pout, W, Cc, r.eps, r.logZ, _blob_view(bl, B), iters=r.iters, nsims=r.nsims, status=r.status,
                     stats=stats)

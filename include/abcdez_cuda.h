@@ -187,6 +187,8 @@ typedef struct {
     double sweep_ms;         /* profile=1: summed CUDA-event time of the sweep kernel launches */
     double total_ms;         /* CUDA-event time of the whole device loop (after init) */
     double init_ms;
+    int32_t hist_dropped;    /* history records that did not fit hist_cap (the histories are truncated, not mislabelled) */
+    int32_t reserved0;
 } abcdez_smc_result;
 
 void abcdez_smc_opts_default(abcdez_smc_opts* o);

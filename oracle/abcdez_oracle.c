@@ -505,7 +505,7 @@ double orc_kernel_logpdf(int kind, double eps, double x)
 enum {
     M_GAUSS1D = 0, M_GAUSS1D_BLOB = 1, M_GAUSS_CORR10 = 2, M_DIRAC = 3, M_NORMDU = 4,
     M_TWOD = 5, M_TWOD_INF = 6, M_MIXTURE = 7, M_WIENER = 8, M_LOTKA_VOLTERRA = 9,
-    M_BIRTH_DEATH = 10, M_GK = 11, M_SOCKS = 12, M_COUNT
+    M_BIRTH_DEATH = 10, M_GK = 11, M_SOCKS = 12, M_GK_F32 = 13, M_LOTKA_VOLTERRA_LIN = 14, M_COUNT
 };
 
 typedef struct { const char* name; int d; int blob; } model_info_t;
@@ -513,7 +513,7 @@ static const model_info_t MODELS[M_COUNT] = {
     { "gauss1d", 1, 0 }, { "gauss1d_blob", 1, 8 }, { "gauss_corr10", 10, 0 }, { "dirac", 1, 0 },
     { "normdu", 2, 0 }, { "twod", 2, 0 }, { "twod_inf", 2, 0 }, { "mixture", 1, 0 },
     { "wiener", 2, 0 }, { "lotka_volterra", 4, 0 }, { "birth_death", 2, 16 }, { "gk", 4, 0 },
-    { "socks", 2, 0 }
+    { "socks", 2, 0 }, { "gk_f32", 4, 0 }, { "lotka_volterra_lin", 4, 0 }
 };
 
 int orc_model_count(void) { return M_COUNT; }
@@ -528,10 +528,14 @@ int orc_model_blob(int id) { return (id >= 0 && id < M_COUNT) ? MODELS[id].blob 
  * data[5]=obs noise sigma, data[6+2j], data[7+2j] = observed (x,y) at obs j.
  * distance = sqrt(mean squared residual) over 2*nobs values; observation
  * noise sigma*N(0,1) is added to each simulated observation. */
+/* the competing model of the evidence comparison ("lotka_volterra_lin"): predators grow with the prey density alone,
+ *   dy/dt = th2*x - th3*y */
+static int lv_linear = 0;
+#pragma omp threadprivate(lv_linear)
 static inline void lv_rhs(const double* th, double x, double y, double* dx, double* dy)
 {
     *dx = th[0] * x - th[1] * x * y;
-    *dy = th[2] * x * y - th[3] * y;
+    *dy = lv_linear ? th[2] * x - th[3] * y : th[2] * x * y - th[3] * y;
 }
 
 static double model_lv(const double* th, const double* data, simrng_t* r)
@@ -590,13 +594,56 @@ static double model_bd(const double* th, const double* data, simrng_t* r, double
 }
 
 /* --- g-and-k (config 3) ------------------------------------------- */
-/* theta = (A, B, g, k), c = 0.8.  data[0] = number of draws n (<= 16384),
- * data[1..7] = observed octiles.  Draw n standard normals, map through the
- * g-and-k quantile function in FP32, take the 7 octiles as order statistics
- * x_(ceil(n*j/8)) (1-based), distance = sqrt(mean squared diff).  The
- * simulator arithmetic is FP32 (north star: FP32 pipe for compute-bound
- * simulators); FP32 libm differs between glibc and CUDA, hence the parity
- * tolerance for this model is 1e-4 relative (tests say so). */
+/* theta = (A, B, g, k), c = 0.8.  data[0] = number of draws n (<= 16384), data[1..7] = observed octiles.
+ * Draw n standard normals (Philox block b of the simulator's stream -> one Box-Muller pair: draws 2b, 2b+1),
+ * map each through the g-and-k quantile function
+ *     x = A + B (1 + 0.8 (1 - e^{-g z}) / (1 + e^{-g z})) (1 + z^2)^k z
+ * evaluated as written below (FP64, the portable exp / log of this file: the arithmetic of a Julia Float64
+ * dist!), take the 7 octiles as order statistics x_(ceil(n*j/8)) (1-based), distance = sqrt(mean squared diff).
+ * The CUDA functor performs the same operations in the same order: bit-identical distances. */
+static int cmp_dbl(const void* a, const void* b)
+{
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+static double model_gk(const double* th, const double* data, simrng_t* r)
+{
+    int n = (int)data[0];
+    n = n < 8 ? 8 : (n > 16384 ? 16384 : n);
+    double* x = (double*)malloc(sizeof(double) * (size_t)(n + 2));
+    const double A = th[0], B = th[1], g = th[2], k = th[3];
+    for (int i = 0; i < n; i += 2) {
+        double z[2];
+        stream_n2(&r->s, (uint32_t)(i / 2), &z[0], &z[1]);
+        for (int j = 0; j < 2; ++j) {
+            const double zz = z[j];
+            const double gz = g * zz;
+            const double e = pexp(-fabs(gz));
+            double t = (1.0 - e) / (1.0 + e);
+            t = gz < 0.0 ? -t : t;
+            const double c = 1.0 + 0.8 * t;
+            const double l = plog(1.0 + zz * zz);
+            const double p = pexp(k * l);
+            x[i + j] = A + ((B * c) * p) * zz;
+        }
+    }
+    qsort(x, (size_t)n, sizeof(double), cmp_dbl);
+    double acc = 0.0;
+    for (int j = 1; j <= 7; ++j) {
+        int idx = (n * j + 7) / 8; /* ceil(n*j/8), 1-based */
+        double dq = x[idx - 1] - data[j];
+        acc += dq * dq;
+    }
+    free(x);
+    return sqrt(acc / 7.0);
+}
+
+/* --- g-and-k, relaxed-precision mode "gk_f32"  -------------------------------- */
+/* The same definition with the draws in FP32: Philox block b -> four 24-bit uniforms -> two Box-Muller pairs
+ * (draws 4b .. 4b+3), portable FP32 log / exp / sin / cos below (IEEE single operations and fmaf only;
+ * -ffp-contract=off), octiles of the FP32 draws, distance in FP64.  Restated operation by operation in
+ * abcdez.jl_b200/csrc/gk.cu. */
 static int cmp_float(const void* a, const void* b)
 {
     float x = *(const float*)a, y = *(const float*)b;
@@ -610,26 +657,98 @@ static inline void philox_f4(const stream_t* s, uint32_t block, float u[4])
     for (int i = 0; i < 4; ++i) u[i] = (float)(o[i] >> 8) * 0x1.0p-24f;
 }
 
-static double model_gk(const double* th, const double* data, simrng_t* r)
+static inline float gk_logf_pos(float x)
+{
+    uint32_t b; memcpy(&b, &x, 4);
+    int e = (int)((b >> 23) & 0xffu) - 127;
+    uint32_t mb = (b & 0x007fffffu) | 0x3f800000u;
+    float m; memcpy(&m, &mb, 4);
+    if (m > 0x1.6a09e6p+0f) { m = m * 0.5f; e += 1; }
+    const float f = m - 1.0f;
+    const float s = f / (2.0f + f);
+    const float z = s * s;
+    float p = 2.0f / 9.0f;
+    p = fmaf(p, z, 2.0f / 7.0f);
+    p = fmaf(p, z, 2.0f / 5.0f);
+    p = fmaf(p, z, 2.0f / 3.0f);
+    const float r = (s * z) * p;
+    const float lm = 2.0f * s + r;
+    return ((float)e * 0x1.62e4p-1f + lm) + (float)e * 0x1.7f7d1cp-20f;
+}
+
+static inline float gk_expf(float x)
+{
+    if (x > 88.0f) return INFINITY;
+    if (x < -87.0f) return 0.0f;
+    const float k = floorf(x * 0x1.715476p+0f + 0.5f);
+    const float r = (x - k * 0x1.62e4p-1f) - k * 0x1.7f7d1cp-20f;
+    float p = 1.0f / 5040.0f;
+    p = fmaf(p, r, 1.0f / 720.0f);
+    p = fmaf(p, r, 1.0f / 120.0f);
+    p = fmaf(p, r, 1.0f / 24.0f);
+    p = fmaf(p, r, 1.0f / 6.0f);
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    uint32_t sb = (uint32_t)((int)k + 127) << 23;
+    float sc; memcpy(&sc, &sb, 4);
+    return p * sc;
+}
+
+static inline void gk_sincos2pif(float u, float* sn, float* cs)
+{
+    const float q = floorf(4.0f * u + 0.5f);
+    const float r = u - 0.25f * q;
+    const float x = r * 0x1.921fb6p+2f;
+    const float x2 = x * x;
+    float ps = -1.0f / 39916800.0f;
+    ps = fmaf(ps, x2, 1.0f / 362880.0f);
+    ps = fmaf(ps, x2, -1.0f / 5040.0f);
+    ps = fmaf(ps, x2, 1.0f / 120.0f);
+    ps = fmaf(ps, x2, -1.0f / 6.0f);
+    float pc = -1.0f / 3628800.0f;
+    pc = fmaf(pc, x2, 1.0f / 40320.0f);
+    pc = fmaf(pc, x2, -1.0f / 720.0f);
+    pc = fmaf(pc, x2, 1.0f / 24.0f);
+    pc = fmaf(pc, x2, -0.5f);
+    const float s = x + x * (x2 * ps);
+    const float c = 1.0f + x2 * pc;
+    const int k = (int)q & 3;
+    const int swap = (k & 1) != 0;
+    const float a = swap ? c : s, b = swap ? s : c;
+    *sn = (k & 2) ? -a : a;
+    *cs = ((k + 1) & 2) ? -b : b;
+}
+
+static double model_gk_f32(const double* th, const double* data, simrng_t* r)
 {
     int n = (int)data[0];
+    n = n < 8 ? 8 : (n > 16384 ? 16384 : n);
     float* x = (float*)malloc(sizeof(float) * (size_t)(n + 4));
-    float A = (float)th[0], B = (float)th[1], g = (float)th[2], k = (float)th[3];
+    const float A = (float)th[0], B = (float)th[1], g = (float)th[2], k = (float)th[3];
     for (int i = 0; i < n; i += 4) {
-        float u[4];
-        philox_f4(&r->s, r->blk++, u);
-        float r1 = sqrtf(-2.0f * logf(1.0f - u[0])), r2 = sqrtf(-2.0f * logf(1.0f - u[2]));
-        float z[4] = { r1 * cosf(6.2831853f * u[1]), r1 * sinf(6.2831853f * u[1]),
-                       r2 * cosf(6.2831853f * u[3]), r2 * sinf(6.2831853f * u[3]) };
+        float u[4], s1, c1, s2, c2;
+        philox_f4(&r->s, (uint32_t)(i / 4), u);
+        const float r1 = sqrtf(-2.0f * gk_logf_pos(1.0f - u[0])), r2 = sqrtf(-2.0f * gk_logf_pos(1.0f - u[2]));
+        gk_sincos2pif(u[1], &s1, &c1);
+        gk_sincos2pif(u[3], &s2, &c2);
+        const float z[4] = { r1 * c1, r1 * s1, r2 * c2, r2 * s2 };
         for (int j = 0; j < 4; ++j) {
-            float zz = z[j];
-            x[i + j] = A + B * (1.0f + 0.8f * tanhf(0.5f * g * zz)) * powf(1.0f + zz * zz, k) * zz;
+            const float zz = z[j];
+            const float gz = g * zz;
+            const float e = gk_expf(-fabsf(gz));
+            float t = (1.0f - e) / (1.0f + e);
+            t = gz < 0.0f ? -t : t;
+            const float c = 1.0f + 0.8f * t;
+            const float l = gk_logf_pos(1.0f + zz * zz);
+            const float p = gk_expf(k * l);
+            x[i + j] = A + ((B * c) * p) * zz;
         }
     }
     qsort(x, (size_t)n, sizeof(float), cmp_float);
     double acc = 0.0;
     for (int j = 1; j <= 7; ++j) {
-        int idx = (n * j + 7) / 8; /* ceil(n*j/8), 1-based */
+        int idx = (n * j + 7) / 8;
         double dq = (double)x[idx - 1] - data[j];
         acc += dq * dq;
     }
@@ -713,7 +832,9 @@ static double simulate(int model, const double* th, const double* data, simrng_t
         }
         return acc / 31.0;
     }
-    case M_LOTKA_VOLTERRA: return model_lv(th, data, r);
+    case M_LOTKA_VOLTERRA: lv_linear = 0; return model_lv(th, data, r);
+    case M_LOTKA_VOLTERRA_LIN: lv_linear = 1; return model_lv(th, data, r);
+    case M_GK_F32:         return model_gk_f32(th, data, r);
     case M_BIRTH_DEATH:    return model_bd(th, data, r, (double*)blob);
     case M_GK:             return model_gk(th, data, r);
     case M_SOCKS:          return model_socks(th, data, r);

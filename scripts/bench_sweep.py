@@ -15,6 +15,8 @@ cases = {
     "birth_death": (A.Factored(*[A.host.Uniform(0.0, 2.0)] * 2), [20.0, 8, 0.5, 5000.0] + [22, 25, 24, 30, 33, 31, 36, 40], 113),
     "gk": (A.Factored(*[A.host.Uniform(0.0, 10.0)] * 3, A.host.Uniform(0.0, 2.0)),
            [10000.0, 1.86, 2.39, 2.73, 3.0, 3.67, 4.86, 7.9], 161),
+    "gk_f32": (A.Factored(*[A.host.Uniform(0.0, 10.0)] * 3, A.host.Uniform(0.0, 2.0)),
+               [10000.0, 1.86, 2.39, 2.73, 3.0, 3.67, 4.86, 7.9], 161),
 }
 prior, data, bytes_per = cases[model_name]
 pop = A.Population(prior, A.Model(model_name, data), N)

@@ -38,6 +38,8 @@ MODEL_CASES = {
     "wiener": ([("uniform", 0.0, 1.0), ("uniform", 0.0, 4.0)], list(np.sqrt(0.25 * np.arange(31.0) ** 2 + 4.0 * np.arange(31.0)))),
     "lotka_volterra": ([("uniform", 0.0, 2.0)] * 4,
                        [1.0, 0.5, 0.01, 50, 8, 0.05] + list(np.tile([1.2, 0.6], 8))),
+    "lotka_volterra_lin": ([("uniform", 0.0, 2.0)] * 4,
+                           [1.0, 0.5, 0.01, 50, 8, 0.05] + list(np.tile([1.2, 0.6], 8))),
     "birth_death": ([("uniform", 0.0, 2.0), ("uniform", 0.0, 2.0)], [20.0, 8, 0.5, 5000.0] + [22, 25, 24, 30, 33, 31, 36, 40]),
     "socks": ([("negbin", 4.5, 0.13), ("beta", 15.0, 2.0)], [0.0, 11.0]),
 }
@@ -285,6 +287,30 @@ def test_mc_sweep_parity(A, oracle, gpu_ctx, name):
         np.testing.assert_allclose(g["theta"], want["theta"], rtol=1e-12, atol=0)
         np.testing.assert_allclose(g["delta"], want["delta"], rtol=1e-9, atol=1e-10)
         pop.close()
+
+
+@pytest.mark.parametrize("N,ties", [(4096, False), (4097, False), (30011, True), (300007, False)])
+def test_mc_sweep_sorted_order_at_scale(A, oracle, gpu_ctx, N, ties):
+    """The library's own sort behind src/abcdez_mc.jl:23 (bitonic in shared memory up to 4096 particles, LSD radix
+    above; ties in index order): one Philox-driven abcdemc_swarm! sweep equals the oracle's, whose base-particle draw
+    walks the qsort-ed (delta, index) order."""
+    name = "gauss1d"
+    spec, data = MODEL_CASES[name]
+    th, lp, dl, bl, _ = oracle.init(spec, name, data, N, seed=52)
+    if ties:
+        dl = np.round(dl, 1)                                      # heavy ties: the order inside a tie is the index order
+    eps_target = float(np.quantile(dl, 0.2)); eps_pop = max(eps_target, float(dl.min()))
+    g0 = 2.38 / math.sqrt(2)
+    want = oracle.mc_sweep(spec, name, data, th, lp, dl, eps_pop, eps_target, g0, seed=62, epoch=3)
+    pop = A.Population(to_prior(A, spec), A.Model(name, data), N)
+    pop.upload(theta=th, logpi=lp, delta=dl)
+    pop.set(eps=1.0, gamma0=g0, seed=62, epoch=3)
+    r = pop.mc_sweep(eps_pop, eps_target)
+    g = pop.download()
+    assert np.array_equal(r["flags"], want["flags"]) and r["nsims"] == want["nsims"]
+    np.testing.assert_array_equal(g["theta"], want["theta"])
+    np.testing.assert_allclose(g["delta"], want["delta"], rtol=1e-12, atol=0)
+    pop.close()
 
 
 # ---------------------------------------------------------------------------------------------
