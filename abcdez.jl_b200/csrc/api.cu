@@ -1094,6 +1094,10 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
         host_iters++;
+        if (o->profile) {
+            while (evs.size() < nev + 4) { cudaEvent_t e; RUN_CU(cudaEventCreate(&e)); evs.push_back(e); }
+            RUN_CU(cudaEventRecord(evs[nev], st));
+        }
         if (o->fused_head || shard) {                                        // :301-324 in one cooperative kernel
             const int nl = launch_head(st, pop->dev, ctx->sm_count);
             if (nl < 0) {    // nothing else may run on stale eps / alive state: abort the run at once
@@ -1107,17 +1111,19 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
             launches += launch_reweight(st, pop->dev);                       // :305-324
             launches += launch_compact(st, pop->dev);
         }
-        launches += launch_resample(st, pop->dev, pop->DS, pop->NB, nullptr, (uint32_t)host_iters, mode, 0);   // :324-326
-        // profile: one CUDA-event pair around the iteration's sweep launches (skipped sweeps return at once)
+        // profile: CUDA events around the head, the resampling launches and the iteration's sweep launches
+        // (skipped launches return at once)
         if (o->profile) {
-            while (evs.size() < nev + 2) { cudaEvent_t e; RUN_CU(cudaEventCreate(&e)); evs.push_back(e); }
-            RUN_CU(cudaEventRecord(evs[nev], st));
+            while (evs.size() < nev + 4) { cudaEvent_t e; RUN_CU(cudaEventCreate(&e)); evs.push_back(e); }
+            RUN_CU(cudaEventRecord(evs[nev + 1], st));
         }
+        launches += launch_resample(st, pop->dev, pop->DS, pop->NB, nullptr, (uint32_t)host_iters, mode, 0);   // :324-326
+        if (o->profile) RUN_CU(cudaEventRecord(evs[nev + 2], st));
         for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
             pop->ops->smc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj);
             launches++;
         }
-        if (o->profile) { RUN_CU(cudaEventRecord(evs[nev + 1], st)); nev += 2; }
+        if (o->profile) { RUN_CU(cudaEventRecord(evs[nev + 3], st)); nev += 4; }
         if (host_iters % sync_every == 0) {
             // pipelined stop poll: request a copy of the control block behind this batch, then look at the copy
             // requested behind the PREVIOUS batch -- the host stays one batch ahead of the device, so the device
@@ -1171,9 +1177,13 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         float ms = 0.f;
         RUN_CU(cudaEventElapsedTime(&ms, e_init0, e_loop0)); res->init_ms = ms;
         RUN_CU(cudaEventElapsedTime(&ms, e_loop0, e_loop1)); res->total_ms = ms;
-        double sw = 0.0;
-        for (size_t i = 0; i + 1 < nev; i += 2) { RUN_CU(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); sw += ms; }
-        res->sweep_ms = sw;
+        double sw = 0.0, hd = 0.0, rs = 0.0;
+        for (size_t i = 0; i + 3 < nev; i += 4) {
+            RUN_CU(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); hd += ms;
+            RUN_CU(cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2])); if (ms > 0.012f) rs += ms;   // (launches that return at the flag take ~2 us)
+            RUN_CU(cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3])); sw += ms;
+        }
+        res->sweep_ms = sw; res->head_ms = hd; res->resample_ms = rs;
     }
     res->eps = c->eps; res->logZ = c->logZ; res->iters = c->iters; res->nsims = c->nsims_total;
     res->status = c->status; res->n_resamples = c->n_resamples; res->n_sweeps = c->n_sweeps; res->n_launches = launches;

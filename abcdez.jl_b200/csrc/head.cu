@@ -161,10 +161,13 @@ __device__ __noinline__ void tail_select(const unsigned long long* L, unsigned M
     if (M <= (unsigned)CAND_DIRECT) {
         // few keys (the usual case with the adaptive window): rank them directly, one key per thread
         __syncthreads();
-        const unsigned long long my = tid < M ? L[tid] : ~0ull;
-        unsigned r = 0;
-        for (unsigned k = 0; k < M; ++k) { const unsigned long long o = L[k]; r += (o < my || (o == my && k < tid)) ? 1u : 0u; }
-        if (tid < M && (unsigned long long)r == rank) s->mn = my;
+        if ((tid & ~31u) < M) {                             // (warps without a key skip the M-step loop)
+            const unsigned long long my = tid < M ? L[tid] : ~0ull;
+            unsigned r = 0;
+#pragma unroll 4
+            for (unsigned k = 0; k < M; ++k) { const unsigned long long o = L[k]; r += (o < my || (o == my && k < tid)) ? 1u : 0u; }
+            if (tid < M && (unsigned long long)r == rank) s->mn = my;
+        }
         __syncthreads();
         prefix = s->mn;
         __syncthreads();
@@ -324,22 +327,35 @@ struct HeadShare {
 // distances of the round's tiles [tb, tb + nt) -> keys; with ext != nullptr also extrema(delta) over all particles
 // and the NaN check (ext[0] = min key, ext[1] = max key, ext[2] = NaN among alive)
 static __device__ __noinline__ void load_keys(const PopDev& P, const double* __restrict__ dl, unsigned tb, unsigned nt, HeadShare* sh,
-                                              unsigned long long* ext)
+                                              unsigned long long* ext, bool with_w)
 {
     const unsigned tid = threadIdx.x;
     const uint32_t N = P.N;
     unsigned long long kmn = ~0ull, kmx = 0ull, nan_seen = 0ull;
-#pragma unroll 1
-    for (unsigned t = 0; t < nt; ++t) {
+    // every global load of the round is issued before the first use: one L2 round trip, not one per tile
+    double v[KT][4]; uint32_t al[KT]; double w[KT][4];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {
         const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
-        double v[4] = { 0.0, 0.0, 0.0, 0.0 }; uint32_t al = 0u;
-        if (i0 < N) { load4_f64(dl, i0, N, v); al = load4_u8(P.alive, i0, N); }
+        al[t] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[t][k] = 0.0; w[t][k] = 0.0; }
+        if ((unsigned)t < nt && i0 < N) {
+            load4_f64(dl, i0, N, v[t]); al[t] = load4_u8(P.alive, i0, N);
+            if (with_w) load4_f64(P.W, i0, N, w[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {
+        if ((unsigned)t >= nt) break;
+        const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const bool valid = i0 + k < N, ok = valid && ((al >> (8 * k)) & 0xff);
-            const unsigned long long key = f64_key(v[k]);
-            if (ext && valid) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; if (ok && isnan(v[k])) nan_seen = 1ull; }
+            const bool valid = i0 + k < N, ok = valid && ((al[t] >> (8 * k)) & 0xff);
+            const unsigned long long key = f64_key(v[t][k]);
+            if (ext && valid) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; if (ok && isnan(v[t][k])) nan_seen = 1ull; }
             sh->key[t][k][tid] = ok ? key : DEAD_KEY;
+            if (with_w) sh->w[t][k][tid] = w[t][k];
         }
     }
     if (ext) { ext[0] = kmn; ext[1] = kmx; ext[2] = nan_seen; }
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         for (unsigned r = 0; r < rounds; ++r) {
             unsigned tb; const unsigned nt = round_tiles(r, tb);
             unsigned long long ext[3];
-            load_keys(P, dl, tb, nt, sh, ext);
+            load_keys(P, dl, tb, nt, sh, ext, single);          // (single round: the weights come along, for pass A)
             kmn = ext[0] < kmn ? ext[0] : kmn; kmx = ext[1] > kmx ? ext[1] : kmx; nan_seen |= ext[2];
 #pragma unroll 1
             for (unsigned t = 0; t < nt; ++t) {
@@ -465,7 +481,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             hist_clear(&s);
             for (unsigned r = 0; r < rounds; ++r) {
                 unsigned tb; const unsigned nt = round_tiles(r, tb);
-                if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+                if (!single) load_keys(P, dl, tb, nt, sh, nullptr, false);
 #pragma unroll 1
                 for (unsigned t = 0; t < nt; ++t)
 #pragma unroll
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         hist_clear(&s);
         for (unsigned r = 0; r < rounds; ++r) {
             unsigned tb; const unsigned nt = round_tiles(r, tb);
-            if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+            if (!single) load_keys(P, dl, tb, nt, sh, nullptr, false);
 #pragma unroll 1
             for (unsigned t = 0; t < nt; ++t)
 #pragma unroll
@@ -517,7 +533,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
         unsigned long long mab = ~0ull, cmn = ~0ull, cmx = 0ull;
         for (unsigned r = 0; r < rounds; ++r) {
             unsigned tb; const unsigned nt = round_tiles(r, tb);
-            if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+            if (!single) load_keys(P, dl, tb, nt, sh, nullptr, false);
 #pragma unroll 1
             for (unsigned t = 0; t < nt; ++t) {
 #pragma unroll
@@ -699,12 +715,15 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     // ---- reweight pass A: ws, wprod (kept in shared memory when the share is a single round), per-tile sums and alive counts ----
     for (unsigned r = 0; r < rounds; ++r) {
         unsigned tb; const unsigned nt = round_tiles(r, tb);
-        if (!single) load_keys(P, dl, tb, nt, sh, nullptr);
+        if (!single) load_keys(P, dl, tb, nt, sh, nullptr, false);
 #pragma unroll 1
         for (unsigned t = 0; t < nt; ++t) {
             const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
             double w[4] = { 0.0, 0.0, 0.0, 0.0 };
-            if (i0 < N) load4_f64(P.W, i0, N, w);
+            if (single) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = sh->w[t][k][tid];           // prefetched with the distances
+            } else if (i0 < N) load4_f64(P.W, i0, N, w);
             double acc = 0.0; unsigned cnt = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -736,11 +755,12 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     unsigned n_alive, my_off;
     {
         double a = 0.0; unsigned tot = 0, pre = 0;
-#pragma unroll 2
-        for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) {
-            a += __ldcg(&P.partial[b]);
-            const unsigned tc = __ldcg(&P.tile_cnt[b]);
-            tot += tc; if (b < t0) pre += tc;
+        for (unsigned b0 = tid; b0 < ntiles; b0 += 4 * HEAD_THREADS) {      // four independent loads in flight per thread; same summation order
+            double pv[4]; unsigned tc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned b = b0 + j * HEAD_THREADS; pv[j] = b < ntiles ? __ldcg(&P.partial[b]) : 0.0; tc[j] = b < ntiles ? __ldcg(&P.tile_cnt[b]) : 0u; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned b = b0 + j * HEAD_THREADS; if (b < ntiles) { a += pv[j]; tot += tc[j]; if (b < t0) pre += tc[j]; } }
         }
         wnorm = block_sum_all(a, &s);                                                             // :309
         tot = warp_sum_u(tot); pre = warp_sum_u(pre);
@@ -857,7 +877,13 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
     // ---- the last CTA to finish: ESS, the decisions of :318-324 -------------------------------------------
     if (last_block(&c->acc.ticket[5], G)) {
         double a = 0.0;
-        for (unsigned b = tid; b < ntiles; b += HEAD_THREADS) a += __ldcg(&partial2[b]);
+        for (unsigned b0 = tid; b0 < ntiles; b0 += 4 * HEAD_THREADS) {
+            double pv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned b = b0 + j * HEAD_THREADS; pv[j] = b < ntiles ? __ldcg(&partial2[b]) : 0.0; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (b0 + j * HEAD_THREADS < ntiles) a += pv[j];
+        }
         double sumsq = block_sum_all(a, &s);
         if (sharded) {                                      // sum(Wns^2) in rank order, the common alive weight
             ++seq;

@@ -55,7 +55,7 @@ class _SmcResult(C.Structure):
                 ("hist_len", C.c_int32), ("status", C.c_int32),
                 ("n_resamples", C.c_int64), ("n_sweeps", C.c_int64), ("n_launches", C.c_int64),
                 ("sweep_ms", C.c_double), ("total_ms", C.c_double), ("init_ms", C.c_double),
-                ("hist_dropped", C.c_int32), ("reserved0", C.c_int32)]
+                ("hist_dropped", C.c_int32), ("reserved0", C.c_int32), ("head_ms", C.c_double), ("resample_ms", C.c_double)]
 
 
 class _McOpts(C.Structure):
@@ -593,7 +593,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     if r.status == ERR_NO_ALIVE and verbose:
         print("Warning: No alive particles")                                 # src/abcdez_smc.jl:375
     stats = dict(n_resamples=r.n_resamples, n_sweeps=r.n_sweeps, n_launches=r.n_launches, sweep_ms=r.sweep_ms,
-                 total_ms=r.total_ms, init_ms=r.init_ms, seed=o.seed, rank=ctx.rank, world=ctx.world,
+                 total_ms=r.total_ms, init_ms=r.init_ms, head_ms=r.head_ms, resample_ms=r.resample_ms, seed=o.seed, rank=ctx.rank, world=ctx.world,
                  nparticles=Nglobal, hist_dropped=r.hist_dropped)
     if r.hist_dropped and verbose:
         print(f"Warning: {r.hist_dropped} history records did not fit hist_cap={hist_cap}; the histories are truncated")

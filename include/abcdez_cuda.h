@@ -162,7 +162,7 @@ typedef struct {
     int32_t verboseout;      /* 1: fill the history arrays */
     int32_t max_iters;       /* 0 = unbounded (benchmark guard, not in the reference) */
     int32_t exact_scan;      /* 1: sequential FP64 cumsum for Epanechnikov resampling (parity mode) */
-    int32_t profile;         /* 1: time the sweep launches of every iteration with a CUDA-event pair */
+    int32_t profile;         /* 1: time the head, resampling and sweep launches of every iteration with CUDA events */
     int32_t sync_every;      /* host polls the stop flag every this many iterations (default 1) */
     int32_t fused_head;      /* 1 (default): eps quantile + reweight + ESS + alive list in one cooperative kernel;
                                 0: the stage kernels one by one (same results bit for bit) */
@@ -189,6 +189,8 @@ typedef struct {
     double init_ms;
     int32_t hist_dropped;    /* history records that did not fit hist_cap (the histories are truncated, not mislabelled) */
     int32_t reserved0;
+    double head_ms;          /* profile=1: summed CUDA-event time of the head kernel (eps select + reweight + ESS + alive list) */
+    double resample_ms;      /* profile=1: ... of the resampling launches of the iterations that did resample */
 } abcdez_smc_result;
 
 void abcdez_smc_opts_default(abcdez_smc_opts* o);
