@@ -12,6 +12,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace abcdez;
@@ -40,6 +41,9 @@ static int fail(int code, const std::string& msg)
     } while (0)
 
 extern "C" const char* abcdez_last_error(void) { return g_err.c_str(); }
+
+// stage-level calls on an abcdez_init_multi context run on its first GPU
+static inline abcdez_ctx* first_gpu(abcdez_ctx* c) { return (c && !c->subs.empty()) ? c->subs[0] : c; }
 extern "C" int abcdez_version(void) { return ABCDEZ_VERSION; }
 
 // ---------------------------------------------------------------------------------------
@@ -58,7 +62,7 @@ extern "C" int abcdez_init(int device, void* stream, abcdez_ctx** out)
     abcdez_ctx* c = new (std::nothrow) abcdez_ctx();
     if (!c) return fail(ABCDEZ_ERR_CUDA, "abcdez_init: out of host memory");
     c->device = device;
-    c->rank = 0; c->world = 1; c->comm = nullptr;
+    c->rank = 0; c->world = 1; c->comm = nullptr; c->group = nullptr;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else {
         cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -75,6 +79,12 @@ extern "C" int abcdez_init(int device, void* stream, abcdez_ctx** out)
 extern "C" int abcdez_destroy(abcdez_ctx* ctx)
 {
     if (!ctx) return ABCDEZ_OK;
+    if (!ctx->subs.empty()) {                             // abcdez_init_multi: the sub-contexts own everything
+        for (abcdez_ctx* sub : ctx->subs) abcdez_destroy(sub);
+        if (ctx->group) local_group_destroy(ctx->group);
+        delete ctx;
+        return ABCDEZ_OK;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->comm) comm_destroy(ctx->comm);
@@ -89,8 +99,70 @@ extern "C" int abcdez_destroy(abcdez_ctx* ctx)
 extern "C" int abcdez_sync(abcdez_ctx* ctx)
 {
     CHECK_ARG(ctx != nullptr, "abcdez_sync: ctx is NULL");
+    if (!ctx->subs.empty()) { for (abcdez_ctx* sub : ctx->subs) { CU(cudaSetDevice(sub->device)); CU(cudaStreamSynchronize(sub->stream)); } return ABCDEZ_OK; }
     CU(cudaStreamSynchronize(ctx->stream));
     return ABCDEZ_OK;
+}
+
+// ---- single-process multi-GPU context (SURVEY.md 8b "Threading") -----------------------------------------
+// One call from one host thread uses every GPU: the context fans a run out to one worker thread per GPU, each
+// driving its own sub-context (stream, arena) exactly as one process per GPU would; peers are mapped with
+// cudaDeviceEnablePeerAccess instead of CUDA IPC and the host-level collectives are an in-process rendezvous
+// (comm.cu), so neither NCCL nor a process launcher is involved.  Same kernels, same in-kernel NVLink exchanges,
+// same results as the one-process-per-GPU runs (and as oracle(islands = n_gpus)).
+extern "C" int abcdez_init_multi(int n_gpus, const int* device_ids, abcdez_ctx** out)
+{
+    CHECK_ARG(out != nullptr, "abcdez_init_multi: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(ABCDEZ_ERR_CUDA, std::string("abcdez_init_multi: no CUDA device (") + cudaGetErrorString(e) + "); libabcdez_cuda has no CPU fallback");
+    if (n_gpus <= 0) n_gpus = n < XCHG_MAXR ? n : XCHG_MAXR;          // all visible GPUs (one NVSwitch domain: at most 8)
+    CHECK_ARG(n_gpus <= XCHG_MAXR, "abcdez_init_multi: at most 8 GPUs");
+    std::vector<int> ids(n_gpus);
+    for (int r = 0; r < n_gpus; ++r) {
+        ids[r] = device_ids ? device_ids[r] : r;
+        CHECK_ARG(ids[r] >= 0 && ids[r] < n, "abcdez_init_multi: device index out of range");
+        for (int q = 0; q < r; ++q) CHECK_ARG(ids[q] != ids[r], "abcdez_init_multi: a device is listed twice");
+    }
+    for (int r = 0; r < n_gpus; ++r)
+        for (int q = 0; q < n_gpus; ++q) {
+            int can = 1;
+            if (q != r) CU(cudaDeviceCanAccessPeer(&can, ids[r], ids[q]));
+            if (!can) return fail(ABCDEZ_ERR_UNSUPPORTED, "abcdez_init_multi: the GPUs cannot access each other's memory (no NVLink / PCIe peer access)");
+        }
+    abcdez_ctx* top = new (std::nothrow) abcdez_ctx();
+    if (!top) return fail(ABCDEZ_ERR_CUDA, "abcdez_init_multi: out of host memory");
+    top->device = ids[0]; top->rank = 0; top->world = 1; top->comm = nullptr; top->group = nullptr;
+    for (int r = 0; r < n_gpus; ++r) {
+        abcdez_ctx* sub = nullptr;
+        int rc = abcdez_init(ids[r], nullptr, &sub);
+        if (rc) { std::string why = g_err; abcdez_destroy(top); return fail(rc, why); }
+        top->subs.push_back(sub);
+    }
+    if (n_gpus == 1) { *out = top; return ABCDEZ_OK; }    // (a single GPU needs no communicator: runs go straight to the sub-context)
+    top->group = local_group_create(n_gpus);
+    std::vector<int> rcs(n_gpus, 0); std::vector<std::string> whys(n_gpus);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_gpus; ++r)
+        th.emplace_back([&, r] {
+            abcdez_ctx* sub = top->subs[r];
+            cudaSetDevice(sub->device);
+            rcs[r] = comm_create_local(r, n_gpus, top->group, sub->device, sub->stream, &sub->comm, &whys[r]);
+            if (!rcs[r]) { sub->rank = r; sub->world = n_gpus; }
+        });
+    for (std::thread& t : th) t.join();
+    for (int r = 0; r < n_gpus; ++r)
+        if (rcs[r]) { std::string why = whys[r]; int rc = rcs[r]; abcdez_destroy(top); return fail(rc, "abcdez_init_multi: " + why); }
+    cudaSetDevice(ids[0]);
+    *out = top;
+    return ABCDEZ_OK;
+}
+
+extern "C" int abcdez_ctx_gpus(const abcdez_ctx* ctx)
+{
+    if (!ctx) return 0;
+    return ctx->subs.empty() ? 1 : (int)ctx->subs.size();
 }
 
 // ---- sharded runs: one process per GPU -------------------------------------------------
@@ -105,6 +177,7 @@ extern "C" int abcdez_nccl_unique_id(void* id128)
 extern "C" int abcdez_comm_init(abcdez_ctx* ctx, int rank, int world, const void* id128)
 {
     CHECK_ARG(ctx != nullptr, "abcdez_comm_init: ctx is NULL");
+    CHECK_ARG(ctx->subs.empty(), "abcdez_comm_init: an abcdez_init_multi context already spans its GPUs");
     CHECK_ARG(world >= 1 && world <= XCHG_MAXR && rank >= 0 && rank < world, "abcdez_comm_init: need 0 <= rank < world <= 8");
     CHECK_ARG(ctx->comm == nullptr, "abcdez_comm_init: the context already has a communicator");
     ctx->rank = rank; ctx->world = world;
@@ -188,6 +261,7 @@ struct DevBuf {
 static int prior_op(abcdez_ctx* ctx, const abcdez_prior* p, int64_t N, int op, const double* in, double* out,
                     uint64_t seed, uint32_t epoch, int64_t id0)
 {
+    ctx = first_gpu(ctx);
     CHECK_ARG(ctx && p && out, "prior op: NULL argument");
     CHECK_ARG(N >= 0, "prior op: N < 0");
     if (N == 0) return ABCDEZ_OK;
@@ -299,6 +373,7 @@ extern "C" int abcdez_model_destroy(abcdez_model* m) { delete m; return ABCDEZ_O
 extern "C" int abcdez_model_compile(abcdez_ctx* ctx, const char* name, const char* struct_name, const char* cuda_src,
                                     int d, int blob_bytes, int* id, char* log, size_t log_cap)
 {
+    ctx = first_gpu(ctx);
     CHECK_ARG(name && struct_name && cuda_src && id, "abcdez_model_compile: NULL argument");
     CHECK_ARG(d >= 1 && d <= ABCDEZ_MAXD, "abcdez_model_compile: d must be in 1..16");
     CHECK_ARG(blob_bytes >= 0 && blob_bytes <= ABCDEZ_MAXBLOB && blob_bytes % 8 == 0, "abcdez_model_compile: blob_bytes must be a multiple of 8 in 0..64");
@@ -318,6 +393,7 @@ extern "C" int abcdez_simulate(abcdez_ctx* ctx, const abcdez_model* m, int64_t N
                                uint64_t seed, uint32_t epoch, uint32_t tag, int64_t id0, double* dist_out,
                                uint8_t* blobs_out)
 {
+    ctx = first_gpu(ctx);
     CHECK_ARG(ctx && m && theta_pushed && dist_out, "abcdez_simulate: NULL argument");
     CHECK_ARG(N >= 0, "abcdez_simulate: N < 0");
     if (N == 0) return ABCDEZ_OK;
@@ -398,6 +474,7 @@ extern "C" int abcdez_pop_destroy(abcdez_pop* pop)
 static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, int64_t N,
                            int64_t id0, int hist_cap, abcdez_pop** out, int64_t Ng = 0)
 {
+    ctx = first_gpu(ctx);
     CHECK_ARG(ctx && prior && model && out, "abcdez_pop_create: NULL argument");
     CHECK_ARG(N >= 1 && N < (int64_t)0x7fffffff, "abcdez_pop_create: N must be in 1..2^31-2 per GPU");
     CHECK_ARG(prior->dev.d == model->ops->d, "abcdez_pop_create: length(prior) != model dimension");
@@ -839,6 +916,7 @@ extern "C" int abcdez_pop_resample(abcdez_pop* pop, const double* uniforms, uint
 extern "C" int abcdez_wsample_stratified(abcdez_ctx* ctx, int64_t N, const double* weights, const double* uniforms,
                                          int mode, int64_t* inds_out)
 {
+    ctx = first_gpu(ctx);
     CHECK_ARG(ctx && weights && uniforms && inds_out, "abcdez_wsample_stratified: NULL argument");
     CHECK_ARG(N >= 1 && N < (int64_t)0x7fffffff, "abcdez_wsample_stratified: N out of range");
     CHECK_ARG(mode >= 0 && mode <= 2, "abcdez_wsample_stratified: mode must be 0, 1 or 2");
@@ -940,9 +1018,47 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
                         const abcdez_smc_opts* o, abcdez_smc_result* res, const void* state_in, size_t state_in_bytes,
                         void* state_out, size_t state_out_cap, size_t* state_out_bytes);
 
+// abcdez_init_multi contexts: one worker thread per GPU runs the sharded implementation on its sub-context and fills its
+// block of the caller's buffers; scalars and histories (identical on every rank) come from rank 0
+static int smc_run_multi(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                         const abcdez_smc_opts* o, abcdez_smc_result* res)
+{
+    const int R = (int)ctx->subs.size();
+    if (R == 1) return smc_run_impl(ctx->subs[0], prior, model, eps_target, o, res, nullptr, 0, nullptr, 0, nullptr);
+    const int d = prior->dev.d, B = model->ops->blob;
+    std::vector<abcdez_smc_result> rr(R, *res);
+    std::vector<int> rcs(R, 0); std::vector<std::string> whys(R);
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r) {
+        int64_t lo = 0, hi = 0;
+        abcdez_shard_range(o->nparticles, r, R, &lo, &hi);
+        if (rr[r].P) rr[r].P += lo * d;
+        if (rr[r].Wns) rr[r].Wns += lo;
+        if (rr[r].C) rr[r].C += lo;
+        if (rr[r].blobs) rr[r].blobs += lo * B;
+        if (r > 0) { rr[r].h_eps = rr[r].h_dmin = rr[r].h_dmax = rr[r].h_logZ = rr[r].h_ess = rr[r].h_facc = rr[r].h_gamma0 = nullptr; rr[r].h_Kmcmc = nullptr; }
+        th.emplace_back([&, r] {
+            rcs[r] = smc_run_impl(ctx->subs[r], prior, model, eps_target, o, &rr[r], nullptr, 0, nullptr, 0, nullptr);
+            if (rcs[r]) whys[r] = g_err;
+        });
+    }
+    for (std::thread& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < R; ++r) if (rcs[r]) return fail(rcs[r], whys[r]);
+    const abcdez_smc_result& a = rr[0];
+    res->eps = a.eps; res->logZ = a.logZ; res->iters = a.iters; res->nsims = a.nsims; res->hist_len = a.hist_len; res->status = a.status;
+    res->n_resamples = a.n_resamples; res->n_sweeps = a.n_sweeps; res->hist_dropped = a.hist_dropped;
+    res->sweep_ms = a.sweep_ms; res->total_ms = a.total_ms; res->init_ms = a.init_ms; res->head_ms = a.head_ms; res->resample_ms = a.resample_ms;
+    res->n_launches = 0;
+    for (int r = 0; r < R; ++r) { res->n_launches += rr[r].n_launches; if (rr[r].total_ms > res->total_ms) res->total_ms = rr[r].total_ms; }
+    return ABCDEZ_OK;
+}
+
 extern "C" int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
                               const abcdez_smc_opts* o, abcdez_smc_result* res)
 {
+    CHECK_ARG(ctx && prior && model && o && res, "abcdez_smc_run: NULL argument");
+    if (!ctx->subs.empty()) return smc_run_multi(ctx, prior, model, eps_target, o, res);
     return smc_run_impl(ctx, prior, model, eps_target, o, res, nullptr, 0, nullptr, 0, nullptr);
 }
 
@@ -951,6 +1067,12 @@ extern "C" int abcdez_smc_run_state(abcdez_ctx* ctx, const abcdez_prior* prior, 
                                     int64_t state_in_bytes, void* state_out, int64_t state_out_cap, int64_t* state_out_bytes)
 {
     CHECK_ARG(state_in_bytes >= 0 && state_out_cap >= 0, "abcdez_smc_run_state: negative size");
+    CHECK_ARG(ctx != nullptr, "abcdez_smc_run_state: ctx is NULL");
+    if (!ctx->subs.empty()) {
+        if (ctx->subs.size() > 1 && (state_in || state_out)) return fail(ABCDEZ_ERR_UNSUPPORTED, "abcdez_smc_run_state: run-state snapshots are single-GPU in this build");
+        if (ctx->subs.size() > 1) return smc_run_multi(ctx, prior, model, eps_target, o, res);
+        ctx = ctx->subs[0];
+    }
     CHECK_ARG(!state_out || state_out_bytes, "abcdez_smc_run_state: state_out needs state_out_bytes");
     size_t ob = 0;
     int rc = smc_run_impl(ctx, prior, model, eps_target, o, res, state_in, (size_t)state_in_bytes, state_out, (size_t)state_out_cap,
@@ -1237,8 +1359,42 @@ extern "C" void abcdez_mc_opts_default(abcdez_mc_opts* o)
     o->nparticles = 50; o->generations = 20; o->seed = 1;
 }
 
+static int mc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                       const abcdez_mc_opts* o, abcdez_mc_result* res);
+
 extern "C" int abcdez_mc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
                              const abcdez_mc_opts* o, abcdez_mc_result* res)
+{
+    CHECK_ARG(ctx && prior && model && o && res, "abcdez_mc_run: NULL argument");
+    if (ctx->subs.empty()) return mc_run_impl(ctx, prior, model, eps_target, o, res);
+    const int R = (int)ctx->subs.size();
+    if (R == 1) return mc_run_impl(ctx->subs[0], prior, model, eps_target, o, res);
+    const int d = prior->dev.d, B = model->ops->blob;
+    std::vector<abcdez_mc_result> rr(R, *res);
+    std::vector<int> rcs(R, 0); std::vector<std::string> whys(R);
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r) {
+        int64_t lo = 0, hi = 0;
+        abcdez_shard_range(o->nparticles, r, R, &lo, &hi);
+        if (rr[r].P) rr[r].P += lo * d;
+        if (rr[r].C) rr[r].C += lo;
+        if (rr[r].blobs) rr[r].blobs += lo * B;
+        th.emplace_back([&, r] {
+            rcs[r] = mc_run_impl(ctx->subs[r], prior, model, eps_target, o, &rr[r]);
+            if (rcs[r]) whys[r] = g_err;
+        });
+    }
+    for (std::thread& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < R; ++r) if (rcs[r]) return fail(rcs[r], whys[r]);
+    res->reached_eps = rr[0].reached_eps; res->nsims = rr[0].nsims; res->dmin = rr[0].dmin; res->dmax = rr[0].dmax;
+    res->sweep_ms = rr[0].sweep_ms; res->total_ms = rr[0].total_ms; res->n_launches = 0;
+    for (int r = 0; r < R; ++r) res->n_launches += rr[r].n_launches;
+    return ABCDEZ_OK;
+}
+
+static int mc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
+                       const abcdez_mc_opts* o, abcdez_mc_result* res)
 {
     CHECK_ARG(ctx && prior && model && o && res, "abcdez_mc_run: NULL argument");
     CHECK_ARG(0.0 <= eps_target, "\xcf\xb5_target must be non-negative");      // src/abcdez_mc.jl:108

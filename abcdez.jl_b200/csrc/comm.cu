@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,9 +66,47 @@ static bool nccl_load(std::string* why)
     return true;
 }
 
+// ---- single-process groups (abcdez_init_multi): the ranks are threads of one process, one per GPU -------------
+// Host-level collectives become an in-process rendezvous and peers are mapped with cudaDeviceEnablePeerAccess
+// (plain device pointers are valid on every GPU of the process) instead of NCCL + CUDA IPC.  The kernels, the
+// mailboxes and the exchange protocol are the same.
+struct LocalGroup {
+    int world = 1;
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0;
+    unsigned gen = 0;
+    std::vector<char> buf;
+};
+
+LocalGroup* local_group_create(int world) { LocalGroup* g = new LocalGroup(); g->world = world; return g; }
+void local_group_destroy(LocalGroup* g) { delete g; }
+
+static void local_barrier(LocalGroup* g)
+{
+    std::unique_lock<std::mutex> lk(g->m);
+    const unsigned gen = g->gen;
+    if (++g->count == g->world) { g->count = 0; g->gen++; g->cv.notify_all(); }
+    else g->cv.wait(lk, [&] { return g->gen != gen; });
+}
+
+static void local_allgather(LocalGroup* g, int rank, const void* in, void* out, size_t bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(g->m);
+        if (g->buf.size() < bytes * (size_t)g->world) g->buf.resize(bytes * (size_t)g->world);
+    }
+    local_barrier(g);                                    // the buffer has its final size before anyone writes
+    memcpy(g->buf.data() + bytes * (size_t)rank, in, bytes);
+    local_barrier(g);
+    memcpy(out, g->buf.data(), bytes * (size_t)g->world);
+    local_barrier(g);                                    // everyone has read before the next collective overwrites
+}
+
 // ---- communicator state of one context ----------------------------------------------------------------
 struct Comm {
     int rank = 0, world = 1;
+    LocalGroup* local = nullptr;                  // non-null: single-process group (no NCCL, no IPC)
     ncclComm_t nccl = nullptr;
     char* mbox = nullptr;                         // own mailbox (cudaMalloc, exported)
     char* peer_mbox[XCHG_MAXR] = {};              // every rank's mailbox in this process' address space
@@ -90,6 +130,11 @@ const char* comm_error(const Comm* cm) { return cm ? cm->err.c_str() : ""; }
 // host-level all-gather of `bytes` bytes per rank (through device staging, on the context stream)
 int comm_allgather(Comm* cm, cudaStream_t st, const void* in, void* out, size_t bytes)
 {
+    if (cm->local) {
+        CM_CU(cudaStreamSynchronize(st));                 // same ordering as the NCCL path: this rank's stream has drained
+        local_allgather(cm->local, cm->rank, in, out, bytes);
+        return ABCDEZ_OK;
+    }
     size_t need = bytes * (size_t)(cm->world + 1);
     if (cm->stage_bytes < need) {
         if (cm->stage) cudaFree(cm->stage);
@@ -154,9 +199,45 @@ int comm_create(int rank, int world, const void* id128, cudaStream_t st, Comm** 
 static void close_peer_slabs(Comm* cm)
 {
     for (int q = 0; q < cm->world; ++q) {
-        if (q != cm->rank && cm->peer_slab[q]) cudaIpcCloseMemHandle(cm->peer_slab[q]);
+        if (!cm->local && q != cm->rank && cm->peer_slab[q]) cudaIpcCloseMemHandle(cm->peer_slab[q]);
         cm->peer_slab[q] = nullptr;
     }
+}
+
+// one rank (thread) of a single-process group; collective over the group's threads
+int comm_create_local(int rank, int world, LocalGroup* group, int device, cudaStream_t st, Comm** out, std::string* why)
+{
+    if (world > XCHG_MAXR) { *why = "at most 8 GPUs (one NVSwitch domain)"; return ABCDEZ_ERR_BAD_ARG; }
+    Comm* cm = new Comm();
+    cm->rank = rank; cm->world = world; cm->local = group;
+    auto run = [&]() -> int {
+        int devs[XCHG_MAXR] = { 0 };
+        local_allgather(group, rank, &device, devs, sizeof(int));
+        for (int q = 0; q < world; ++q) {
+            if (q == rank) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(devs[q], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return comm_fail(cm, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
+        CM_CU(cudaMalloc((void**)&cm->mbox, XCHG_MBOX_BYTES));
+        CM_CU(cudaMemsetAsync(cm->mbox, 0, XCHG_MBOX_BYTES, st));
+        CM_CU(cudaMalloc((void**)&cm->seq, 64));
+        CM_CU(cudaMemsetAsync(cm->seq, 0, 64, st));
+        CM_CU(cudaMalloc((void**)&cm->d_peers, sizeof(PeerTable)));
+        CM_CU(cudaStreamSynchronize(st));
+        char* all[XCHG_MAXR] = { nullptr };
+        local_allgather(group, rank, &cm->mbox, all, sizeof(char*));
+        for (int q = 0; q < world; ++q) cm->peer_mbox[q] = all[q];
+        return ABCDEZ_OK;
+    };
+    int rc = run();
+    // (every rank reaches this barrier, failed or not, so that nobody waits for a rank that gave up)
+    int ok = rc == ABCDEZ_OK, oks[XCHG_MAXR];
+    local_allgather(group, rank, &ok, oks, sizeof(int));
+    for (int q = 0; q < world; ++q) if (!oks[q] && rc == ABCDEZ_OK) { rc = ABCDEZ_ERR_NCCL; cm->err = "a peer rank failed to set up its mailbox"; }
+    if (rc) { *why = cm->err; comm_destroy(cm); return rc; }
+    *out = cm;
+    return ABCDEZ_OK;
 }
 
 void comm_destroy(Comm* cm)
@@ -164,7 +245,7 @@ void comm_destroy(Comm* cm)
     if (!cm) return;
     close_peer_slabs(cm);
     for (int q = 0; q < cm->world; ++q)
-        if (q != cm->rank && cm->peer_mbox[q]) cudaIpcCloseMemHandle(cm->peer_mbox[q]);
+        if (!cm->local && q != cm->rank && cm->peer_mbox[q]) cudaIpcCloseMemHandle(cm->peer_mbox[q]);
     if (cm->nccl) g_nccl.CommDestroy(cm->nccl);
     if (cm->slab) cudaFree(cm->slab);
     if (cm->mbox) cudaFree(cm->mbox);
@@ -190,6 +271,13 @@ int comm_shared_slab(Comm* cm, cudaStream_t st, size_t need, char** slab)
         cm->slab = nullptr; cm->slab_bytes = 0;
         CM_CU(cudaMalloc((void**)&cm->slab, mx));
         cm->slab_bytes = mx;
+        if (cm->local) {                                  // same process: the peers' device pointers are usable as they are
+            char* all[XCHG_MAXR] = { nullptr };
+            rc = comm_allgather(cm, st, &cm->slab, all, sizeof(char*)); if (rc) return rc;
+            for (int q = 0; q < cm->world; ++q) cm->peer_slab[q] = all[q];
+            *slab = cm->slab;
+            return ABCDEZ_OK;
+        }
         cudaIpcMemHandle_t h, hs[XCHG_MAXR];
         CM_CU(cudaIpcGetMemHandle(&h, cm->slab));
         rc = comm_allgather(cm, st, &h, hs, sizeof h); if (rc) return rc;

@@ -604,19 +604,23 @@ gk_simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double
 template <class T>
 static unsigned gk_grid(int64_t N, size_t smem)
 {
-    static size_t cached_smem = 0; static int cached_grid = 0;
-    if (cached_smem != smem || !cached_grid) {
-        cudaFuncSetAttribute(gk_init_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
-        cudaFuncSetAttribute(gk_smc_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
-        cudaFuncSetAttribute(gk_mc_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
-        cudaFuncSetAttribute(gk_simulate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T)));
-        int dev = 0, sms = 148, per = 1;
-        cudaGetDevice(&dev);
+    // per device: function attributes and occupancy belong to the device's context (abcdez_init_multi drives several)
+    static size_t cached_smem[64] = { 0 }; static int cached_grid[64] = { 0 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (cached_smem[slot] != smem || !cached_grid[slot]) {
+        const int mx = (int)(sizeof(GkSmem) + GK_MAXN * sizeof(T));
+        cudaFuncSetAttribute(gk_init_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(gk_smc_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(gk_mc_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(gk_simulate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        int sms = 148, per = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gk_smc_sweep_kernel<T>, GK_THREADS, smem) != cudaSuccess || per < 1) per = 1;
-        cached_grid = sms * per; cached_smem = smem;
+        cached_grid[slot] = sms * per; cached_smem[slot] = smem;
     }
-    return (unsigned)(N < cached_grid ? N : cached_grid);
+    return (unsigned)(N < cached_grid[slot] ? N : cached_grid[slot]);
 }
 
 template <class T>

@@ -44,10 +44,16 @@ namespace cg = cooperative_groups;
 namespace abcdez {
 
 constexpr int HEAD_THREADS = BK_THREADS;
-constexpr int HEAD_MIN_BLOCKS = 2;                // resident CTAs per SM the register budget is cut for
-constexpr int KT = 4;                             // tiles per round: 16 particles per thread stay in registers
+#ifndef ABCDEZ_HEAD_MIN_BLOCKS
+#define ABCDEZ_HEAD_MIN_BLOCKS 2
+#endif
+#ifndef ABCDEZ_HEAD_KT
+#define ABCDEZ_HEAD_KT 4
+#endif
+constexpr int HEAD_MIN_BLOCKS = ABCDEZ_HEAD_MIN_BLOCKS;   // resident CTAs per SM the register budget is cut for
+constexpr int KT = ABCDEZ_HEAD_KT;                // tiles per round: KT x 4 particles per thread stay on chip
 constexpr int KE = KT * 4;
-constexpr int CAND_SMEM = 2048;                   // candidates staged in shared memory for the per-CTA tail; longer
+constexpr int CAND_SMEM = KT >= 4 ? 2048 : 1024;                   // candidates staged in shared memory for the per-CTA tail; longer
                                                   // lists are first refined grid-cooperatively, one digit per round
 constexpr int CAND_DIRECT = 256;                  // ... and at most this many are ranked directly (one per thread)
 constexpr int NW = HEAD_THREADS / 32;
@@ -90,11 +96,15 @@ __device__ __noinline__ void pick_bin(const unsigned (&loc)[SEL_BINS / HEAD_THRE
     __syncthreads();
     unsigned bef = incl - tot;
     for (unsigned q = 0; q < wp; ++q) bef += s->part[q];
-    unsigned cum = bef;
+    // (populations are below 2^31 particles: a rank beyond 32 bits is beyond every total)
+    const unsigned r32 = rank > 0xfffffffeull ? 0xffffffffu : (unsigned)rank;
+    if (r32 - bef < tot && r32 >= bef) {                  // the rank falls into one of this thread's bins
+        unsigned cum = bef;
 #pragma unroll
-    for (int k = 0; k < per; ++k) {
-        if (loc[k] && rank >= cum && rank < (unsigned long long)cum + loc[k]) { s->found_bin = threadIdx.x * per + k; s->found_before = cum; s->found_cnt = loc[k]; }
-        cum += loc[k];
+        for (int k = 0; k < per; ++k) {
+            if (r32 - cum < loc[k]) { s->found_bin = threadIdx.x * per + k; s->found_before = cum; s->found_cnt = loc[k]; break; }
+            cum += loc[k];
+        }
     }
     __syncthreads();
     bin = s->found_bin; before = s->found_before;
@@ -349,9 +359,10 @@ static __device__ __noinline__ void load_keys(const PopDev& P, const double* __r
     for (int t = 0; t < KT; ++t) {
         if ((unsigned)t >= nt) break;
         const size_t i0 = (size_t)(tb + t) * TILE + (size_t)tid * 4;
+        const int nvalid = i0 + 4 <= N ? 4 : (i0 < N ? (int)(N - i0) : 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const bool valid = i0 + k < N, ok = valid && ((al[t] >> (8 * k)) & 0xff);
+            const bool valid = k < nvalid, ok = valid && ((al[t] >> (8 * k)) & 0xff);
             const unsigned long long key = f64_key(v[t][k]);
             if (ext && valid) { kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; if (ok && isnan(v[t][k])) nan_seen = 1ull; }
             sh->key[t][k][tid] = ok ? key : DEAD_KEY;
@@ -809,9 +820,10 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
             double w[4] = { 0.0, 0.0, 0.0, 0.0 };
             if (!single && i0 < N) load4_f64(P.W, i0, N, w);
             double acc = 0.0; uint32_t nal = 0u; unsigned cnt = 0;
+            const int nvalid = i0 + 4 <= N ? 4 : (i0 < N ? (int)(N - i0) : 0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (i0 + k < N) {
+                if (k < nvalid) {
                     const double wp_ = single ? sh->w[t][k][tid] : w[k];
                     const double q = (wp_ == 0.0 && rwn != 0.0) ? wp_ : pdiv_r(wp_, wnorm, rwn);      // :310 (0 / wnorm without the detour)
                     const bool a = (q > 0.0);                                                     // :311
@@ -856,13 +868,15 @@ __global__ void __launch_bounds__(HEAD_THREADS, HEAD_MIN_BLOCKS) head_kernel(con
                 for (int q = 0; q < NW; ++q) { const unsigned wc = s.wcnt[t][q]; if (q < (int)wp) woff += wc; ttot += wc; }
                 unsigned pos = off + woff + incl - cnt;                       // alive before element i0
                 unsigned dpos = n_alive + ((unsigned)i0 - pos);               // dead before element i0
+                const int nvalid = i0 + 4 <= N ? 4 : (i0 < N ? (int)(N - i0) : 0);
+                const uint32_t i32 = (uint32_t)i0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (i0 + k < N) {
+                    if (k < nvalid) {
                         // (the bounds only bite when the alive counts of pass A disagree with these flags: NaN weights,
                         // reported as an error below -- the list must still not be overrun)
-                        if ((nal >> (8 * k)) & 0xff) { if (pos < N) P.alive_list[pos] = (uint32_t)(i0 + k); pos++; }
-                        else { if (dpos < N) P.alive_list[dpos] = (uint32_t)(i0 + k); dpos++; }
+                        if ((nal >> (8 * k)) & 0xff) { if (pos < N) P.alive_list[pos] = i32 + k; pos++; }
+                        else { if (dpos < N) P.alive_list[dpos] = i32 + k; dpos++; }
                     }
                 }
                 off += ttot;

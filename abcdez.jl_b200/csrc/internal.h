@@ -160,6 +160,10 @@ size_t mc_sort_tmp_bytes(int64_t N);
 
 // sharded runs, host side (comm.cu)
 struct Comm;
+struct LocalGroup;                                // the ranks of a single-process multi-GPU context (threads)
+LocalGroup* local_group_create(int world);
+void local_group_destroy(LocalGroup* g);
+int comm_create_local(int rank, int world, LocalGroup* group, int device, cudaStream_t st, Comm** out, std::string* why);
 int nccl_unique_id(void* id128, std::string* why);
 int comm_create(int rank, int world, const void* id128, cudaStream_t st, Comm** out, std::string* why);
 void comm_destroy(Comm* cm);
@@ -189,6 +193,9 @@ struct abcdez_ctx {
     bool h_ctrl_busy;
     abcdez::Ctrl* h_poll[2];            // pinned copies of the control block for the pipelined stop poll of abcdez_smc_run
     cudaEvent_t poll_ev[2];
+    // abcdez_init_multi: this context only fans a run out to one sub-context (and host thread) per GPU
+    std::vector<abcdez_ctx*> subs;
+    abcdez::LocalGroup* group;
 };
 
 struct abcdez_prior {

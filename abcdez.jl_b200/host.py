@@ -70,7 +70,7 @@ class _McResult(C.Structure):
 
 # every symbol include/abcdez_cuda.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "abcdez_init", "abcdez_destroy", "abcdez_version", "abcdez_last_error", "abcdez_sync",
+    "abcdez_init", "abcdez_init_multi", "abcdez_ctx_gpus", "abcdez_destroy", "abcdez_version", "abcdez_last_error", "abcdez_sync",
     "abcdez_nccl_unique_id", "abcdez_comm_init", "abcdez_shard_range", "abcdez_comm_selftest",
     "abcdez_prior_create", "abcdez_prior_destroy", "abcdez_prior_sample", "abcdez_prior_logpdf", "abcdez_prior_push",
     "abcdez_model_count", "abcdez_model_name", "abcdez_model_lookup", "abcdez_model_info", "abcdez_model_bind",
@@ -219,6 +219,22 @@ class Context:
         _check(lib().abcdez_init(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = device
         self.rank, self.world = 0, 1
+        self.n_gpus = 1
+
+    @classmethod
+    def multi(cls, n_gpus: int = 0, device_ids: Optional[Sequence[int]] = None) -> "Context":
+        """Single-process multi-GPU context (abcdez_init_multi): `abcdesmc` / `abcdemc` on it run ONE population
+        sharded over the GPUs and return the whole population.  n_gpus = 0: every visible GPU."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        ids = None if device_ids is None else np.ascontiguousarray(device_ids, dtype=np.int32)
+        if ids is not None:
+            n_gpus = ids.size
+        _check(lib().abcdez_init_multi(int(n_gpus), _p(ids), C.byref(self._h)))
+        self.device = int(ids[0]) if ids is not None else 0
+        self.rank, self.world = 0, 1                     # one caller: the result is the whole population
+        self.n_gpus = int(lib().abcdez_ctx_gpus(self._h))
+        return self
 
     # ---- sharded runs (one process per GPU), include/abcdez_cuda.h "sharded runs" -----------------
     @staticmethod
@@ -270,6 +286,17 @@ def default_context() -> Context:
         dev = int(os.environ.get("LOCAL_RANK", "0"))
         _default_ctx = Context(dev)
     return _default_ctx
+
+
+_multi_ctx: Optional[Context] = None
+
+
+def default_multi_context() -> Context:
+    """`parallel=true` (src/abcdez_smc.jl:237): every GPU visible to this process, one population across them."""
+    global _multi_ctx
+    if _multi_ctx is None:
+        _multi_ctx = Context.multi(0)
+    return _multi_ctx
 
 
 # ---------------------------------------------------------------------------------------------
@@ -535,7 +562,8 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     """`abcdesmc!(prior, dist!, ϵ_target, varexternal; kwargs...)`, src/abcdez_smc.jl:215-394.
 
     `dist` is a :class:`Model`; `varexternal` is accepted for signature compatibility (the device
-    functors keep their scratch in registers); `parallel` is ignored (the GPU is always parallel).
+    functors keep their scratch in registers); `parallel=True` without an explicit `ctx` runs the population
+    sharded over every GPU visible to the process (`Context.multi`; one GPU: the plain single-GPU run).
 
     Run-state snapshots (not in the reference): `return_state=True` attaches the state the run ended in
     (`result.state`, bytes; typically after `max_iters` iterations) and `state=<bytes>` continues from one --
@@ -547,7 +575,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
         raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
     if not isinstance(dist, Model):
         raise ABCdeZError(ERR_UNSUPPORTED, "dist! must be a registered device functor: abcdez Model(name, data)")
-    ctx = ctx or default_context()
+    ctx = ctx or (default_multi_context() if parallel else default_context())
     fprior, scalar = _as_prior(prior)
     if Kmcmc_min <= facc_min and verbose:
         print("Warning: Kmcmc_min should be larger than facc_min")            # src/abcdez_smc.jl:232
@@ -616,7 +644,7 @@ def abcdemc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 50, 
     """`abcdemc!(prior, dist!, ϵ_target, varexternal; kwargs...)`, src/abcdez_mc.jl:102-172."""
     if not isinstance(dist, Model):
         raise ABCdeZError(ERR_UNSUPPORTED, "dist! must be a registered device functor: abcdez Model(name, data)")
-    ctx = ctx or default_context()
+    ctx = ctx or (default_multi_context() if parallel else default_context())
     fprior, scalar = _as_prior(prior)
     N, d, B = int(nparticles), len(fprior), dist.blob_bytes
     o = _McOpts(N, int(generations), _seed_from(rng))

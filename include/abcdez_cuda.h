@@ -81,6 +81,16 @@ int abcdez_version(void);
 const char* abcdez_last_error(void);       /* thread-local message of the last failure */
 int abcdez_sync(abcdez_ctx* ctx);          /* cudaStreamSynchronize on the context stream */
 
+/* Single-process multi-GPU context: `parallel=true` of src/abcdez_smc.jl:237 / src/abcdez_mc.jl:112 as "all GPUs of
+ * this process".  n_gpus <= 0: every visible GPU (at most 8); device_ids NULL: 0 .. n_gpus-1.  abcdez_smc_run /
+ * abcdez_mc_run on such a context run ONE population sharded over the GPUs (contiguous blocks, rank-local DE partners,
+ * everything else global -- the same kernels and in-kernel NVLink exchanges as the one-process-per-GPU runs below) and
+ * fill the caller's buffers with the WHOLE population's rows; one host call, no process launcher, no NCCL (peers are
+ * mapped with cudaDeviceEnablePeerAccess; one internal worker thread per GPU).  Stage-level calls (abcdez_pop_*) and
+ * run-state snapshots need a single-GPU context. */
+int abcdez_init_multi(int n_gpus, const int* device_ids, abcdez_ctx** out);
+int abcdez_ctx_gpus(const abcdez_ctx* ctx);   /* GPUs behind a context (1 for abcdez_init contexts) */
+
 /* ---- sharded runs: one process per GPU, particles in contiguous blocks ----------------
  * Replaces the `parallel=true` executor of src/abcdez_smc.jl:237 / src/abcdez_mc.jl:112 across GPUs.
  * abcdez_nccl_unique_id: rank 0 creates a 128-byte ncclUniqueId; the caller distributes it (MPI,

@@ -55,3 +55,44 @@ def test_sharded_runs_match_island_oracle():
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     assert r.stdout.count("multi-gpu parity ok") == world
+
+
+@pytest.mark.gpu
+def test_single_process_multi_gpu_context_matches_island_oracle(A, oracle):
+    """abcdez_init_multi (SURVEY.md 8b "Threading"): ONE host call drives every GPU -- the same sharded kernels and
+    in-kernel exchanges as the one-process-per-GPU runs, peers mapped with cudaDeviceEnablePeerAccess.  The whole
+    population comes back, identical to oracle(islands = n_gpus); the Python `parallel=True` maps to it."""
+    import math
+    import numpy as np
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    R = 2 if n < 4 else 4
+    ctx = A.Context.multi(R)
+    assert ctx.n_gpus == R
+    cases = [([("normal", 0.0, math.sqrt(10.0))], "gauss1d", [3.0, 1.0], 0.3, 20011, {}),
+             ([("normal", 0.0, 2.0)] * 10, "gauss_corr10", list(np.linspace(-1, 1, 10)) + [0.5], 2.5, 40000, {}),
+             ([("uniform", 0.0, 2.0)] * 2, "birth_death", [20.0, 8, 0.5, 5000.0, 22, 25, 24, 30, 33, 31, 36, 40], 3.0, 8000, {}),
+             ([("normal", 0.0, math.sqrt(10.0))], "gauss1d", [3.0, 1.0], 0.3, 3001, dict(kind="epa"))]
+    cls = {"normal": A.host.Normal, "uniform": A.host.Uniform}
+    for spec, name, data, eps, N, kw in cases:
+        prior = A.Factored(*[cls[s_[0]](*s_[1:]) for s_ in spec])
+        kind = kw.get("kind", "indicator_strict")
+        want = oracle.smc_run(spec, name, data, eps, nparticles=N, seed=31, islands=R, nsims_max=10**9, kind=kind)
+        got = A.abcdesmc(prior, A.Model(name, data), eps, None, nparticles=N, rng=31, nsims_max=10**9, verbose=False, ctx=ctx,
+                         ABCk=kind, exact_scan=True)
+        assert (got.iters, got.nsims) == (want.iters, want.nsims), name
+        assert np.array_equal(got.eps_hist, want.hist["eps"])
+        assert got.P.shape[0] == N and np.array_equal(got.Wns > 0, want.Wns > 0)
+        np.testing.assert_allclose(got.P.reshape(N, -1), want.P, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(got.C, want.C, rtol=1e-9, atol=1e-10)
+        assert abs(got.logZ - want.logZ) <= 1e-9 * abs(want.logZ)
+    wm = oracle.mc_run(cases[0][0], "gauss1d", [3.0, 1.0], 0.3, nparticles=4003, generations=30, seed=32, islands=R)
+    gm = A.abcdemc(A.host.Normal(0.0, math.sqrt(10.0)), A.Model("gauss1d", [3.0, 1.0]), 0.3, None, nparticles=4003, generations=30, rng=32,
+                   verbose=False, ctx=ctx)
+    assert gm.nsims == wm.nsims and gm.P.shape[0] == 4003
+    np.testing.assert_allclose(gm.C, wm.C, rtol=1e-9, atol=1e-10)
+    # stage-level calls on the multi context run on its first GPU
+    assert np.isfinite(A.Factored(A.host.Normal(0.0, 1.0)).logpdf([0.3], ctx=ctx))
+    ctx.close()
