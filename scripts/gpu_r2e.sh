@@ -1,9 +1,7 @@
 #!/bin/bash
-# round 2, call e (2 GPUs): single-process multi-GPU context, head occupancy variants A/B, sanitizers, bench lines of configs 3/4/5
+# round 2, call e (1 GPU): head occupancy variants A/B, sanitizers, bench lines of configs 3/4/5
 set -u
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -s 2>&1 | tail -30 ) > gpurun_out/r2e_pytest_multi.log
-tail -n 12 gpurun_out/r2e_pytest_multi.log
 ( timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "head or reweight or quantile" 2>&1 | tail -5 ) > gpurun_out/r2e_pytest_head.log
 cat gpurun_out/r2e_pytest_head.log
 for lib in abcdez.jl_b200/libabcdez_cuda*.so; do
