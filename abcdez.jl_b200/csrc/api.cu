@@ -4,6 +4,7 @@
 // abcdez_mc_run (abcdemc!, src/abcdez_mc.jl:102-172).
 #include "internal.h"
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -85,6 +86,8 @@ extern "C" int abcdez_destroy(abcdez_ctx* ctx)
         delete ctx;
         return ABCDEZ_OK;
     }
+    for (abcdez_ctx* w : ctx->batch) abcdez_destroy(w);
+    ctx->batch.clear();
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->comm) comm_destroy(ctx->comm);
@@ -974,7 +977,7 @@ extern "C" void abcdez_smc_opts_default(abcdez_smc_opts* o)
     o->nparticles = 100; o->alpha = 0.95; o->delta_ess = 0.5; o->nsims_max = 10000000; o->Kmcmc = 3;
     o->Kmcmc_min = 1.0; o->kernel = ABCDEZ_INDICATOR_STRICT; o->facc_stop = 0.0; o->facc_min = 0.0;
     o->facc_tune = 0.975; o->seed = 1; o->verboseout = 1; o->max_iters = 0; o->exact_scan = 0; o->profile = 0;
-    o->sync_every = 1; o->fused_head = 1;
+    o->sync_every = 1; o->fused_head = 1; o->systematic_resampling = 0; o->partner_segments = 0;
 }
 
 // ---- run state snapshots (the reference has no equivalent) -------------------------------
@@ -1126,7 +1129,8 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     int hist_cap = o->verboseout ? (res->hist_cap > 0 ? res->hist_cap : 0) : 0;
     int dev_hist = hist_cap > 0 ? hist_cap : 1;
     if (state_in || state_out) {
-        if (shard) return fail(ABCDEZ_ERR_UNSUPPORTED, "abcdez_smc_run_state: run-state snapshots are single-GPU in this build");
+        // sharded contexts: every rank dumps / restores its own block behind its own copy of the control block (the schedule
+        // scalars in it are identical on all ranks, the counts are the rank's); the mailbox sequence restarts with every run
         const size_t need = smc_state_size(N, row_stride(prior->dev.d), model->ops->blob / 8, dev_hist);
         if (state_out && state_out_cap < need) return fail(ABCDEZ_ERR_BAD_ARG, "abcdez_smc_run_state: state_out is smaller than abcdez_smc_state_bytes()");
         if (state_in) {
@@ -1177,6 +1181,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         if (no_alive) c->status = ABCDEZ_ERR_NO_ALIVE;
     }
     pop->dev.keys = philox_keys(c->seed);
+    pop->dev.flags = (o->partner_segments ? POP_PARTNER_SEGMENTS : 0u) | (o->systematic_resampling ? POP_SYSTEMATIC : 0u);
     rc = push_ctrl(pop);
     std::vector<cudaEvent_t>& evs = ctx->ev_pool;
     size_t nev = 0;
@@ -1347,6 +1352,99 @@ done:
                 (long long)N, t_create, t_loop, t_result, ms_since(t_begin), res->total_ms);
     return rc;
 #undef RUN_CU
+}
+
+// ---------------------------------------------------------------------------------------
+// after the run: equally weighted posterior sample, batched replicate / multi-model runs
+// ---------------------------------------------------------------------------------------
+__global__ void strata_uniforms_kernel(const __grid_constant__ PhiloxKeys keys, int64_t N, double* __restrict__ u)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Stream rs(keys, (uint32_t)i, 0u, TAG_RESAMPLE);
+    double a, b; rs.u2(0u, a, b);
+    u[i] = a;
+}
+__global__ void gather_rows_kernel(int64_t N, int d, const double* __restrict__ P, const long long* __restrict__ inds, double* __restrict__ out)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * d) return;
+    const int64_t i = e / d; const int k = (int)(e - i * d);
+    long long src = inds[i] - 1;                          // wsample_stratified! indices are 1-based; "i = 0" (r == 0) clamps to the first row
+    src = src < 0 ? 0 : (src >= N ? N - 1 : src);
+    out[e] = P[src * d + k];
+}
+
+// P[weightinds(Wns)] of test/runtests.jl:13-19,287-291 on the device: stratified resampling of the weighted particles into an
+// equally weighted sample (Philox uniforms of `seed`); inds_out (optional) receives the 1-based source indices
+extern "C" int abcdez_posterior_sample(abcdez_ctx* ctx, int64_t N, int d, const double* P, const double* Wns, uint64_t seed,
+                                       double* P_out, int64_t* inds_out)
+{
+    ctx = first_gpu(ctx);
+    CHECK_ARG(ctx && P && Wns && P_out, "abcdez_posterior_sample: NULL argument");
+    CHECK_ARG(N >= 1 && N < (int64_t)0x7fffffff && d >= 1 && d <= ABCDEZ_MAXD, "abcdez_posterior_sample: N or d out of range");
+    {
+        double sum = 0.0;
+        for (int64_t i = 0; i < N; ++i) sum += Wns[i];
+        CHECK_ARG(fabs(sum - 1.0) < 1e-8, "Sum of weights expected to be 1.0 (approximately)");       // test/runtests.jl:14
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N; const unsigned nt = (unsigned)((N + TILE - 1) / TILE);
+    DevBuf dw, du, dc, dp, dt, di, dP, dO;
+    CU(dw.alloc(n * 8)); CU(du.alloc(n * 8)); CU(dc.alloc(n * 8)); CU(dp.alloc((size_t)nt * 8 + 64)); CU(dt.alloc(2 * sizeof(SeqTab)));
+    CU(di.alloc(n * 8)); CU(dP.alloc(n * d * 8)); CU(dO.alloc(n * d * 8));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(dw.p, Wns, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dP.p, P, n * d * 8, cudaMemcpyHostToDevice, st));
+    strata_uniforms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(philox_keys(seed), N, du.as<double>());
+    launch_strat_indices(st, N, dw.as<double>(), du.as<double>(), dc.as<double>(), dp.as<double>(), dt.as<SeqTab>(), 2, di.as<long long>());
+    gather_rows_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(N, d, dP.as<double>(), di.as<long long>(), dO.as<double>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(P_out, dO.p, n * d * 8, cudaMemcpyDeviceToHost, st));
+    if (inds_out) CU(cudaMemcpyAsync(inds_out, di.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ABCDEZ_OK;
+}
+
+// Batched runs: `nruns` independent abcdesmc! runs (replicates of one model for the evidence uncertainty, docs/src/index.md:214-220;
+// several models for a comparison, examples/minimal_example.jl:27-65) in flight together.  A 1000-particle run is a chain of
+// ~800 launches of a few microseconds each and leaves the GPU almost empty; here up to 16 worker threads, each with its own
+// stream and arena on the same GPU, pull runs from the list, so their kernels overlap on the device.  Every run gives exactly
+// the result of its own abcdez_smc_run call.  status[i] (optional) receives the status of run i; the return value is the first failure.
+extern "C" int abcdez_smc_run_batch(abcdez_ctx* ctx, int nruns, const abcdez_prior* const* priors, const abcdez_model* const* models,
+                                    const double* eps_targets, const abcdez_smc_opts* opts, abcdez_smc_result* results, int* status)
+{
+    ctx = first_gpu(ctx);
+    CHECK_ARG(ctx && priors && models && eps_targets && opts && results, "abcdez_smc_run_batch: NULL argument");
+    CHECK_ARG(nruns >= 1 && nruns <= 65536, "abcdez_smc_run_batch: nruns out of range");
+    CHECK_ARG(ctx->comm == nullptr, "abcdez_smc_run_batch: batched runs are single-GPU");
+    const int W = nruns < 16 ? nruns : 16;
+    while ((int)ctx->batch.size() < W) {                  // worker contexts live as long as the parent (arenas are reused)
+        abcdez_ctx* w = nullptr;
+        int rc = abcdez_init(ctx->device, nullptr, &w);
+        if (rc) return rc;
+        ctx->batch.push_back(w);
+    }
+    std::vector<int> rcs(nruns, 0); std::vector<std::string> whys(nruns);
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int w = 0; w < W; ++w)
+        th.emplace_back([&, w] {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= nruns) break;
+                rcs[i] = smc_run_impl(ctx->batch[w], priors[i], models[i], eps_targets[i], &opts[i], &results[i], nullptr, 0, nullptr, 0, nullptr);
+                if (rcs[i]) whys[i] = g_err;
+            }
+        });
+    for (std::thread& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    int first = ABCDEZ_OK;
+    for (int i = 0; i < nruns; ++i) {
+        if (status) status[i] = rcs[i];
+        if (rcs[i] && !first) { first = rcs[i]; g_err = "abcdez_smc_run_batch: run " + std::to_string(i) + ": " + whys[i]; }
+    }
+    return first;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -389,7 +389,7 @@ resample_uniform_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
     for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         double u, u2;
         if (inj_u) u = inj_u[si];
-        else { Stream rs(P.keys, P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }
+        else { Stream rs(P.keys, (P.flags & POP_SYSTEMATIC) ? 0u : P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }   // systematic: ONE uniform for all strata
         double r = stratum_draw(&P.tabs[1], sval, si, u);
         unsigned long long k = seqtab_first_ge(&s_w, r);                     // :48-51 in closed form
         uint32_t src;
@@ -442,7 +442,7 @@ resample_uniform_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
     for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         const uint32_t sg = P.id0 + si;                                      // global stratum
         double u, u2;
-        Stream rs(P.keys, sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
+        Stream rs(P.keys, (P.flags & POP_SYSTEMATIC) ? 0u : sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
         double r = stratum_draw(&P.tabs[1], sval, sg, u);
         unsigned long long k = seqtab_first_ge(&s_w, r);                     // :48-51 in closed form
         int q = 0; uint32_t src = 0u;                                        // r == 0: global particle 0 (the reference leaves i = 0)
@@ -564,7 +564,7 @@ resample_general_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
     for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         const uint32_t sg = P.id0 + si;                                      // global stratum
         double u, u2;
-        Stream rs(P.keys, sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
+        Stream rs(P.keys, (P.flags & POP_SYSTEMATIC) ? 0u : sg, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2);
         const double r = stratum_draw(&P.tabs[1], sval, sg, u);
         int q = 0; uint32_t src = 0u;                                        // r <= 0: global particle 0 (the "i = 0" quirk, clamped)
         if (r > 0.0) {
@@ -676,7 +676,7 @@ resample_general_kernel(PopDev P, int DS, int NB, const double* __restrict__ inj
     for (uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; si < N; si += gridDim.x * blockDim.x) {
         double u, u2;
         if (inj_u) u = inj_u[si];
-        else { Stream rs(P.keys, P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }
+        else { Stream rs(P.keys, (P.flags & POP_SYSTEMATIC) ? 0u : P.id0 + si, epoch, TAG_RESAMPLE); rs.u2(0u, u, u2); }   // systematic: ONE uniform for all strata
         double r = stratum_draw(&P.tabs[1], sval, si, u);
         uint32_t src = search_cumsum(P.cumsum, N, r);
         gather_particle(P, cur, DS, NB, si, src);

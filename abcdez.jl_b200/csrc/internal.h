@@ -96,7 +96,9 @@ struct PopDev {
     XchgDev x;
     const PeerTable* peers;       // device table, sharded runs only
     PhiloxKeys keys;              // round keys of the run's seed (== philox_keys(ctrl->seed)); constant-bank operands of the streams
+    uint32_t flags;               // relaxed-parity modes of the run (POP_*), SURVEY.md 8f rank 4
 };
+enum : uint32_t { POP_PARTNER_SEGMENTS = 1u, POP_SYSTEMATIC = 2u };
 
 struct SweepInj {
     const int32_t* a; const int32_t* b; const int32_t* s;
@@ -196,6 +198,7 @@ struct abcdez_ctx {
     // abcdez_init_multi: this context only fans a run out to one sub-context (and host thread) per GPU
     std::vector<abcdez_ctx*> subs;
     abcdez::LocalGroup* group;
+    std::vector<abcdez_ctx*> batch;     // abcdez_smc_run_batch: worker contexts (own stream + arena) on this GPU
 };
 
 struct abcdez_prior {

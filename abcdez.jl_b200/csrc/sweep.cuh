@@ -244,7 +244,13 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // (101.8 -> 95.1 us per sweep).  Straightening further -- simulator and accept draw unconditional for all-Normal
 // priors, the stale-row repair moved behind the accept test -- costs registers and was slower (113.6 us; the repair
 // move alone 99.3 us, the unconditional accept draw alone neutral).
-template <class M, bool DISC, int PK, bool INJ = true>
+// SEG (relaxed-parity mode; opts.partner_segments): warp-coherent partner segments.  One pair
+// of random bases per warp, lane l takes the l-th alive particle behind each base, so the two partner gathers of a
+// warp read 32 neighbouring rows instead of 64 random ones (the gathers are what keeps the parity kernel off its
+// roofline, profiles/README.md).  Every particle's partners are still uniform over the alive set and distinct from
+// it and from each other (a lane whose segment entries collide redraws individually); only their joint law across
+// the lanes of a warp differs from the reference's independent draws -- the Jacobi update does not care.
+template <class M, bool DISC, int PK, bool INJ = true, bool SEG = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                  const __grid_constant__ SweepInj inj)
@@ -288,16 +294,28 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                 // of both share ONE Philox block; the rejection loops continue from block 1
                 Stream ps(seed, pid, epoch, TAG_PARTNER);
                 double u1, u2, ua, ub; uint32_t att = 1;
-                ps.u2(0u, ua, ub);
-                a = wsample_alive(P.alive_list, n_alive, N, ua);
-                b = wsample_alive(P.alive_list, n_alive, N, ub);
+                if (SEG) {
+                    Stream ws(seed, P.id0 + (j & ~31u), epoch, TAG_SEGMENT);   // the warp's stream: every lane computes the same bases
+                    ws.u2(0u, ua, ub);
+                    const uint32_t lane = threadIdx.x & 31;
+                    uint32_t ka = (uint32_t)(ua * (double)n_alive), kb = (uint32_t)(ub * (double)n_alive);
+                    ka = ((ka >= n_alive ? n_alive - 1 : ka) + lane) % n_alive;       // positions in the alive list, wrapping
+                    kb = ((kb >= n_alive ? n_alive - 1 : kb) + lane) % n_alive;
+                    a = (n_alive == N) ? ka : P.alive_list[ka];
+                    b = (n_alive == N) ? kb : P.alive_list[kb];
+                    att = 0;                                                // a collision falls back to the particle's own draws, from block 0
+                } else {
+                    ps.u2(0u, ua, ub);
+                    a = wsample_alive(P.alive_list, n_alive, N, ua);
+                    b = wsample_alive(P.alive_list, n_alive, N, ub);
+                }
                 if (a == i || b == a || b == i) {                          // ~3 / n_alive: one rare branch around both loops
                     while (a == i) {                                       // :119-122
                         if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
                         ps.u2(att++, u1, u2);
                         a = wsample_alive(P.alive_list, n_alive, N, u1);
                     }
-                    att = 1;
+                    att = SEG ? 0 : 1;
                     while (b == a || b == i) {                             // :123-126
                         if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
                         ps.u2(att++, u1, u2);
@@ -528,9 +546,11 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
     else if (all_normal) {
         if (injected) smc_sweep_kernel<M, false, PK_NORMAL, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else if (P.flags & POP_PARTNER_SEGMENTS) smc_sweep_kernel<M, false, PK_NORMAL, false, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
         else smc_sweep_kernel<M, false, PK_NORMAL, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
     } else if (all_uniform) {
         if (injected) smc_sweep_kernel<M, false, PK_UNIFORM, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else if (P.flags & POP_PARTNER_SEGMENTS) smc_sweep_kernel<M, false, PK_UNIFORM, false, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
         else smc_sweep_kernel<M, false, PK_UNIFORM, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
     } else smc_sweep_kernel<M, false, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
 }

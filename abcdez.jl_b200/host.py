@@ -43,7 +43,8 @@ class _SmcOpts(C.Structure):
                 ("kernel", C.c_int32), ("facc_stop", C.c_double), ("facc_min", C.c_double),
                 ("facc_tune", C.c_double), ("seed", C.c_uint64), ("verboseout", C.c_int32),
                 ("max_iters", C.c_int32), ("exact_scan", C.c_int32), ("profile", C.c_int32),
-                ("sync_every", C.c_int32), ("fused_head", C.c_int32)]
+                ("sync_every", C.c_int32), ("fused_head", C.c_int32), ("systematic_resampling", C.c_int32),
+                ("partner_segments", C.c_int32)]
 
 
 class _SmcResult(C.Structure):
@@ -75,7 +76,8 @@ EXPORTS = [
     "abcdez_prior_create", "abcdez_prior_destroy", "abcdez_prior_sample", "abcdez_prior_logpdf", "abcdez_prior_push",
     "abcdez_model_count", "abcdez_model_name", "abcdez_model_lookup", "abcdez_model_info", "abcdez_model_bind",
     "abcdez_model_destroy", "abcdez_model_compile", "abcdez_simulate", "abcdez_kernel_pdf", "abcdez_kernel_logpdf",
-    "abcdez_smc_opts_default", "abcdez_smc_run", "abcdez_smc_state_bytes", "abcdez_smc_run_state",
+    "abcdez_smc_opts_default", "abcdez_smc_run", "abcdez_smc_state_bytes", "abcdez_smc_run_state", "abcdez_smc_run_batch",
+    "abcdez_posterior_sample",
     "abcdez_mc_opts_default", "abcdez_mc_run",
     "abcdez_pop_create", "abcdez_pop_destroy", "abcdez_pop_upload", "abcdez_pop_download", "abcdez_pop_set",
     "abcdez_pop_init", "abcdez_pop_smc_sweep", "abcdez_pop_mc_sweep", "abcdez_pop_eps_quantile",
@@ -558,7 +560,8 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
              facc_min=0.0, facc_tune=0.975, verbose: bool = True, verboseout: bool = True, rng=None,
              parallel: bool = False, ctx: Optional[Context] = None, max_iters: int = 0, exact_scan: bool = False,
              profile: bool = False, sync_every: int = 1, hist_cap: int = 8192, fused_head: bool = True,
-             state=None, return_state: bool = False, **greek) -> SMCResult:
+             state=None, return_state: bool = False, systematic_resampling: bool = False, partner_segments: bool = False,
+             **greek) -> SMCResult:
     """`abcdesmc!(prior, dist!, ϵ_target, varexternal; kwargs...)`, src/abcdez_smc.jl:215-394.
 
     `dist` is a :class:`Model`; `varexternal` is accepted for signature compatibility (the device
@@ -591,6 +594,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     o.facc_tune = facc_tune; o.seed = _seed_from(rng); o.verboseout = int(verboseout); o.max_iters = int(max_iters)
     o.exact_scan = int(exact_scan); o.profile = int(profile); o.sync_every = int(sync_every)
     o.fused_head = int(fused_head)
+    o.systematic_resampling = int(systematic_resampling); o.partner_segments = int(partner_segments)   # relaxed-parity modes
     Np = max(N, 1)
     P = np.empty((Np, d)); W = np.empty(Np); Cc = np.empty(Np); bl = np.zeros((Np, max(B, 1)), dtype=np.uint8)
     h = {k: np.zeros(hist_cap) for k in ("eps", "dmin", "dmax", "logZ", "ess", "facc", "gamma0")}
@@ -694,8 +698,15 @@ def weightinds(weights, rng=None, ctx: Optional[Context] = None):
 
 
 def posterior_sample(result: "SMCResult", rng=None, ctx: Optional[Context] = None):
-    """Equally weighted posterior sample of an `abcdesmc!` result: `P[weightinds(Wns)]` (test/runtests.jl:287-291)."""
-    return np.asarray(result.P)[weightinds(result.Wns, rng, ctx)]
+    """Equally weighted posterior sample of an `abcdesmc!` result: `P[weightinds(Wns)]` (test/runtests.jl:287-291),
+    resampled and gathered on the device (abcdez_posterior_sample)."""
+    ctx = ctx or default_context()
+    P = _f64(result.P); P2 = P.reshape(P.shape[0], -1)
+    W = _f64(result.Wns)
+    out = np.empty_like(P2)
+    _check(lib().abcdez_posterior_sample(ctx._h, C.c_int64(P2.shape[0]), int(P2.shape[1]), _p(P2), _p(W), C.c_uint64(_seed_from(rng)),
+                                         _p(out), None))
+    return out.reshape(P.shape)
 
 
 def evidence_at(result: "SMCResult", eps: float) -> float:
@@ -725,12 +736,57 @@ def model_probabilities(results_or_logZs, prior_probs=None, eps: Optional[float]
     return w / w.sum()
 
 
-def evidence_uncertainty(prior, dist, eps_target, repeats: int = 8, rng=None, **kw):
+def abcdesmc_batch(runs, *, ctx: Optional[Context] = None, verboseout: bool = False, hist_cap: int = 8192):
+    """Several independent `abcdesmc!` runs in flight together on one GPU (abcdez_smc_run_batch): replicates of one model
+    for the evidence uncertainty, several models for a comparison.  `runs` is a list of dicts with the arguments of
+    :func:`abcdesmc` (`prior`, `dist`, `eps_target` and keyword options); returns the list of results -- each exactly
+    what its own `abcdesmc` call returns."""
+    ctx = ctx or default_context()
+    n = len(runs)
+    opts = (_SmcOpts * n)(); res = (_SmcResult * n)()
+    ph = (C.c_void_p * n)(); mh = (C.c_void_p * n)(); eps = (C.c_double * n)(); st = (C.c_int * n)()
+    keep = []
+    for i, r in enumerate(runs):
+        r = dict(r)
+        fprior, scalar = _as_prior(r.pop("prior")); dist = r.pop("dist"); eps[i] = float(r.pop("eps_target"))
+        N = int(r.get("nparticles", 100)); d, B = len(fprior), dist.blob_bytes
+        o = opts[i]
+        lib().abcdez_smc_opts_default(C.byref(o))
+        o.nparticles = N; o.alpha = r.get("alpha", 0.95); o.delta_ess = r.get("delta_ess", 0.5); o.nsims_max = int(r.get("nsims_max", 10**7))
+        o.Kmcmc = int(r.get("Kmcmc", 3)); o.Kmcmc_min = float(r.get("Kmcmc_min", 1.0)); o.kernel = _kernel_kind(r.get("ABCk", IndicatorStrict0toEps))
+        o.facc_stop = r.get("facc_stop", 0.0); o.facc_min = r.get("facc_min", 0.0); o.facc_tune = r.get("facc_tune", 0.975)
+        o.seed = _seed_from(r.get("rng")); o.verboseout = int(verboseout)
+        P = np.empty((N, d)); W = np.empty(N); Cc = np.empty(N); bl = np.zeros((N, max(B, 1)), dtype=np.uint8)
+        h = {k: np.zeros(hist_cap) for k in ("eps", "dmin", "dmax", "logZ", "ess", "facc", "gamma0")}; hK = np.zeros(hist_cap, dtype=np.int32)
+        q = res[i]
+        q.P, q.Wns, q.C, q.blobs = _p(P), _p(W), _p(Cc), _p(bl)
+        q.hist_cap = hist_cap if verboseout else 0
+        q.h_eps, q.h_dmin, q.h_dmax, q.h_logZ = _p(h["eps"]), _p(h["dmin"]), _p(h["dmax"]), _p(h["logZ"])
+        q.h_ess, q.h_facc, q.h_gamma0, q.h_Kmcmc = _p(h["ess"]), _p(h["facc"]), _p(h["gamma0"]), _p(hK)
+        ph[i] = fprior.handle(ctx); mh[i] = dist.handle(ctx)
+        keep.append((P, W, Cc, bl, h, hK, scalar, B, fprior, dist))
+    _check(lib().abcdez_smc_run_batch(ctx._h, n, ph, mh, eps, opts, res, st))
+    out = []
+    for i, (P, W, Cc, bl, h, hK, scalar, B, _, _) in enumerate(keep):
+        q = res[i]
+        r = SMCResult(P[:, 0] if scalar else P, W, Cc, q.eps, q.logZ, _blob_view(bl, B), iters=q.iters, nsims=q.nsims, status=q.status,
+                      stats=dict(n_resamples=q.n_resamples, n_sweeps=q.n_sweeps, n_launches=q.n_launches, total_ms=q.total_ms, seed=opts[i].seed))
+        if verboseout:
+            m = q.hist_len
+            r.eps_hist = h["eps"][:m]; r.ranges_eps = np.stack([h["dmin"][:m], h["dmax"][:m]], axis=1); r.logZs = h["logZ"][:m]
+            r.esss = h["ess"][:m]; r.faccs = h["facc"][:m]; r.gamma0s = h["gamma0"][:m]; r.Kmcmcs = hK[:m]
+        out.append(r)
+    return out
+
+
+def evidence_uncertainty(prior, dist, eps_target, repeats: int = 8, rng=None, ctx: Optional[Context] = None, **kw):
     """The docs' advice (docs/src/index.md:214-220): repeat `abcdesmc!` and summarise the log evidences.
-    Returns (mean, std, list of logZ); each repeat uses its own Philox key."""
+    Returns (mean, std, list of logZ); each repeat uses its own Philox key.  The repeats run as ONE batch
+    (abcdez_smc_run_batch): their kernels overlap on the GPU instead of queueing run after run."""
     base = _seed_from(rng)
-    lz = [abcdesmc(prior, dist, eps_target, None, rng=(base + 0x9E3779B97F4A7C15 * (k + 1)) % 2**64, verbose=False, **kw).logZ
-          for k in range(int(repeats))]
+    runs = [dict(prior=prior, dist=dist, eps_target=eps_target, rng=(base + 0x9E3779B97F4A7C15 * (k + 1)) % 2**64, **kw)
+            for k in range(int(repeats))]
+    lz = [r.logZ for r in abcdesmc_batch(runs, ctx=ctx)]
     return float(np.mean(lz)), float(np.std(lz, ddof=1)) if len(lz) > 1 else 0.0, lz
 
 

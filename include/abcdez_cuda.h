@@ -176,6 +176,12 @@ typedef struct {
     int32_t sync_every;      /* host polls the stop flag every this many iterations (default 1) */
     int32_t fused_head;      /* 1 (default): eps quantile + reweight + ESS + alive list in one cooperative kernel;
                                 0: the stage kernels one by one (same results bit for bit) */
+    /* relaxed-parity performance modes (default 0 = the reference's algorithm, bit for bit) */
+    int32_t systematic_resampling;  /* 1: ONE uniform for all strata (systematic resampling) instead of one per stratum
+                                       (wsample_stratified!, src/abcdez_smc.jl:15-56) */
+    int32_t partner_segments;       /* 1: warp-coherent DE partners -- one pair of random bases per warp, lane l takes the
+                                       l-th alive particle behind each (src/abcdez_smc.jl:119-126 draws every particle's
+                                       partners independently); marginally the same law, coalesced gathers */
 } abcdez_smc_opts;
 
 typedef struct {
@@ -207,13 +213,28 @@ void abcdez_smc_opts_default(abcdez_smc_opts* o);
 int abcdez_smc_run(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
                    const abcdez_smc_opts* opts, abcdez_smc_result* res);
 
+/* Batched runs: nruns independent abcdesmc! runs in flight together on one GPU -- replicates of one
+ * model for the evidence uncertainty (docs/src/index.md:214-220) or several models for a comparison
+ * (examples/minimal_example.jl:27-65).  priors / models / eps_targets / opts / results are arrays of nruns entries; every run
+ * gives exactly the result of its own abcdez_smc_run call (same seeds -> same bits); status (optional) gets each run's status. */
+int abcdez_smc_run_batch(abcdez_ctx* ctx, int nruns, const abcdez_prior* const* priors, const abcdez_model* const* models,
+                         const double* eps_targets, const abcdez_smc_opts* opts, abcdez_smc_result* results, int* status);
+
+/* Equally weighted posterior sample of an abcdesmc! result on the device: P[weightinds(Wns)] of test/runtests.jl:13-19,
+ * 287-291 (stratified resampling with the Philox uniforms of `seed`).  P, P_out: N x d; inds_out (optional): the 1-based
+ * source indices as wsample_stratified! returns them. */
+int abcdez_posterior_sample(abcdez_ctx* ctx, int64_t N, int d, const double* P, const double* Wns, uint64_t seed,
+                            double* P_out, int64_t* inds_out);
+
 /* Run-state snapshots (no equivalent in the reference): abcdez_smc_run that can stop between two
  * iterations and continue later, decision by decision like the uninterrupted run.  state_out (host, capacity >=
  * abcdez_smc_state_bytes(prior, model, nparticles, result.hist_cap or 1)) receives the state the run ended in --
  * typically after opts.max_iters iterations; state_in restores one instead of drawing from the prior.  On a
  * restored run eps_target, nsims_max, facc_stop and max_iters (iterations of THIS call) are taken from the call,
  * the seed from the snapshot, and every other option must equal the snapshot's; histories cover the whole run.
- * Either pointer may be NULL (both NULL == abcdez_smc_run).  Single-GPU contexts only. */
+ * Either pointer may be NULL (both NULL == abcdez_smc_run).  On a sharded context (abcdez_comm_init) the call is collective and
+ * every rank dumps / restores the snapshot of its own block (abcdez_smc_state_bytes with the rank's particle count);
+ * abcdez_init_multi contexts do not take snapshots. */
 int64_t abcdez_smc_state_bytes(const abcdez_prior* prior, const abcdez_model* model, int64_t nparticles, int32_t hist_cap);
 int abcdez_smc_run_state(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_model* model, double eps_target,
                          const abcdez_smc_opts* opts, abcdez_smc_result* res, const void* state_in, int64_t state_in_bytes,

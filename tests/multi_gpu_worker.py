@@ -148,6 +148,18 @@ def gpu_main():
         if rank == 0:
             print(f"sharded {name} {kind} N={N} world={world}: iters {got.iters} nsims {got.nsims} logZ {got.logZ:.6f} == oracle(islands={world}); "
                   f"parallel scan: iters {fast.iters} logZ {fast.logZ:.6f}")
+    # run-state snapshots of a sharded run: every rank keeps its own block; the resumed run is the uninterrupted one
+    name, spec, data, eps_t, N, seed, kw = CASES[2]
+    prior = A.Factored(*[fams[s[0]](*s[1:]) for s in spec])
+    kws = dict(nparticles=N, rng=seed, verbose=False, ctx=ctx, nsims_max=10**9)
+    whole = A.abcdesmc(prior, A.Model(name, data), eps_t, None, **kws)
+    part = A.abcdesmc(prior, A.Model(name, data), eps_t, None, max_iters=11, return_state=True, **kws)
+    assert part.iters == 11 and part.state is not None
+    rest = A.abcdesmc(prior, A.Model(name, data), eps_t, None, state=part.state, **kws)
+    assert (rest.iters, rest.nsims, rest.logZ, rest.eps) == (whole.iters, whole.nsims, whole.logZ, whole.eps)
+    assert np.array_equal(rest.P, whole.P) and np.array_equal(rest.Wns, whole.Wns) and np.array_equal(rest.eps_hist, whole.eps_hist)
+    if rank == 0:
+        print(f"sharded run-state snapshot: cut at 11 of {whole.iters} iterations, resumed run == uninterrupted run, world {world}")
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
