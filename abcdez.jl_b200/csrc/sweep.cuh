@@ -257,14 +257,18 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t N = P.N;
+    // this thread's entry of the particle list is requested together with the control block's scalars (it is only
+    // meaningful while some particles are dead, but always readable): one memory round trip less before the work starts
+    const uint32_t listed = j < N ? P.alive_list[j] : 0u;
     if (c->stop | c->sweeps_done) return;                  // skipped sweep (early exit :352 / stop :376)
     const int cur = c->cur, nxt = cur ^ 1;
-    const uint32_t N = P.N, n_alive = c->n_alive;
+    const uint32_t n_alive = c->n_alive;
     const double* __restrict__ th = P.theta[cur];
     __shared__ SweepSmem s_red;
     sweep_smem_init(&s_red);
 
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nsim = 0, nacc = 0; int err = 0;
     // every schedule scalar the particle work needs, loaded back to back (one L2 round trip, not six)
     const PhiloxKeys& seed = P.keys;
@@ -272,7 +276,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
     const double gamma0 = c->gamma0, gsig = c->gsig, eps = c->eps;
     const int kind = c->kind;
     if (j < N) {
-        const uint32_t i = (n_alive == N) ? j : P.alive_list[j];
+        const uint32_t i = (n_alive == N) ? j : listed;
         const uint8_t mv = P.moved[i];
         if (j >= n_alive) {                                                // dead particle (:114)
             if (mv) {                                                      // repair its stale row, once
