@@ -500,6 +500,7 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     // context arena when it is free, else from a private allocation
     struct Piece { void** ptr; size_t bytes; };
     const size_t scratch_need = std::max((size_t)29 * n + 64, n * (size_t)pop->D * 8);
+    const bool split = model->ops->split != 0;
     Piece pieces[] = {
         { (void**)&P.theta[0], n * pop->DS * 8 }, { (void**)&P.theta[1], n * pop->DS * 8 },
         { (void**)&P.logpi[0], n * 8 }, { (void**)&P.logpi[1], n * 8 },
@@ -511,6 +512,9 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
         { (void**)&P.sel_hist, 7 * SEL_BINS * 4 }, { (void**)&P.cumsum, n * 8 }, { (void**)&P.inds, n * 4 },
         { (void**)&P.hist, (size_t)(hist_cap > 0 ? hist_cap : 1) * 8 * 8 }, { (void**)&P.tabs, 2 * sizeof(SeqTab) },
         { (void**)&pop->scratch, scratch_need },
+        // queue-driven sweeps of heavy simulators (ModelOps::split): theta', its log prior, the simulated distance / blob, the queue
+        { (void**)&P.prop_theta, split ? n * pop->DS * 8 : 0 }, { (void**)&P.prop_lp, split ? n * 8 : 0 }, { (void**)&P.prop_dp, split ? n * 8 : 0 },
+        { (void**)&P.prop_blob, split ? n * pop->NB * 8 : 0 }, { (void**)&P.prop_flag, split ? n + 4 : 0 }, { (void**)&P.queue, split ? n * 4 : 0 },
     };
     size_t total = 0;
     for (const Piece& pc : pieces) total += (pc.bytes + 255) & ~(size_t)255;
@@ -536,6 +540,7 @@ static int pop_create_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abc
     {
         size_t off = 0;
         for (const Piece& pc : pieces) { *pc.ptr = pop->slab + off; off += (pc.bytes + 255) & ~(size_t)255; }
+        if (!split) { P.prop_theta = P.prop_lp = P.prop_dp = P.prop_blob = nullptr; P.prop_flag = nullptr; P.queue = nullptr; }
     }
     pop->scratch_bytes = scratch_need;
     P.cand[0] = reinterpret_cast<unsigned long long*>(P.cumsum);
@@ -1248,7 +1253,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         if (o->profile) RUN_CU(cudaEventRecord(evs[nev + 2], st));
         for (int k = 0; k < o->Kmcmc; ++k) {                                 // :336-353
             pop->ops->smc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj);
-            launches++;
+            launches += pop->ops->split ? 3 : 1;                             // (heavy simulators: propose, simulate, accept)
         }
         if (o->profile) { RUN_CU(cudaEventRecord(evs[nev + 3], st)); nev += 4; }
         if (host_iters % sync_every == 0) {

@@ -97,6 +97,13 @@ struct PopDev {
     const PeerTable* peers;       // device table, sharded runs only
     PhiloxKeys keys;              // round keys of the run's seed (== philox_keys(ctrl->seed)); constant-bank operands of the streams
     uint32_t flags;               // relaxed-parity modes of the run (POP_*), SURVEY.md 8f rank 4
+    // queue-driven sweeps of heavy simulators (SPLIT models, sweep.cuh): the proposals that passed the prior
+    double* prop_theta;           // N rows (row_stride): theta' of the sweep in flight
+    double* prop_lp;              // N: log prior of theta'
+    double* prop_dp;              // N: simulated distance
+    double* prop_blob;            // N x (BLOB/8)
+    uint8_t* prop_flag;           // N: 1 = in the queue
+    uint32_t* queue;              // particle indices whose proposal must be simulated
 };
 enum : uint32_t { POP_PARTNER_SEGMENTS = 1u, POP_SYSTEMATIC = 2u };
 
@@ -127,6 +134,7 @@ struct ModelOps {
     void (*simulate)(const ModelOps&, cudaStream_t, const PriorDev*, const ModelData&, int64_t N, const double* theta_pushed,
                      uint64_t seed, uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs);
     void* dyn;                    // runtime-compiled models: their loaded module (rtc.cu); nullptr for the static registry
+    int split;                    // 1: abcdesmc_swarm! runs as propose -> queue-driven simulate -> accept (3 launches per sweep)
 };
 const ModelOps* model_ops(int id);
 int model_count();

@@ -143,6 +143,7 @@ struct Wiener {
 template <bool LINEAR>
 struct LotkaVolterraT {
     static constexpr int D = 4, BLOB = 0, NOISE = 0;
+    static constexpr bool SPLIT = true, STEPPED = false;    // heavy simulator: proposals outside the prior's support must not idle lanes
     static constexpr const char* name = LINEAR ? "lotka_volterra_lin" : "lotka_volterra";
     __device__ static __forceinline__ void rhs(const double* th, double x, double y, double& dx, double& dy)
     {
@@ -176,34 +177,57 @@ struct LotkaVolterraT {
 typedef LotkaVolterraT<false> LotkaVolterra;
 typedef LotkaVolterraT<true> LotkaVolterraLin;
 
-// config 5: linear birth-death process, Gillespie SSA (divergent trajectory lengths)
+// config 5: linear birth-death process, Gillespie SSA (divergent trajectory lengths).
+// The simulator is written as begin / step / finish -- one step is one event attempt or the closing of one observation
+// window, and consumes at most one Philox block -- so that the queue-driven sweep (sweep.cuh, SPLIT models) can refill a
+// lane with the next pending simulation the moment its trajectory ends instead of idling until the longest trajectory of
+// its warp is through.  run() is the same three functions in a loop: one definition, identical arithmetic.
 struct BirthDeath {
     static constexpr int D = 2, BLOB = 16, NOISE = 0;
+    static constexpr bool SPLIT = true, STEPPED = true;
     static constexpr const char* name = "birth_death";
+    struct State { double n, t, acc, events, lam_mu, th0, dt, maxev; int j, nobs; };
+    __device__ static __forceinline__ void begin(State& s, const double* th, const double* data)
+    {
+        s.n = data[0]; s.nobs = (int)data[1]; s.dt = data[2]; s.maxev = data[3];
+        s.t = 0.0; s.acc = 0.0; s.events = 0.0; s.lam_mu = th[0] + th[1]; s.th0 = th[0]; s.j = 0;
+    }
+    // false when the trajectory is complete
+    __device__ static __forceinline__ bool step(State& s, const double* data, SimRng& r)
+    {
+        if (s.j >= s.nobs) return false;
+        const double tobs = s.dt * (double)(s.j + 1);
+        bool close = true;
+        if (s.n > 0.0 && s.events < s.maxev) {
+            double rate = s.lam_mu * s.n, u1, u2;
+            r.u2(u1, u2);
+            double tn = s.t + (-plog_unit(1.0 - u1)) / rate;    // 1 - u1 in [2^-53, 1]
+            if (!(tn > tobs)) {                                   // (a pending event beyond the observation time is discarded: memoryless)
+                s.t = tn;
+                s.n += (u2 * s.lam_mu < s.th0) ? 1.0 : -1.0;
+                s.events += 1.0;
+                close = false;
+            }
+        }
+        if (close) {
+            s.t = tobs;
+            double dn = s.n - data[4 + s.j];
+            s.acc += dn * dn;
+            s.j += 1;
+        }
+        return s.j < s.nobs;
+    }
+    __device__ static __forceinline__ double finish(const State& s, double* blob)
+    {
+        blob[0] = s.n; blob[1] = s.events;
+        return sqrt(s.acc / (double)s.nobs);
+    }
     __device__ static double run(const double* th, const double* data, SimRng& r, double* blob)
     {
-        double n = data[0];
-        int nobs = (int)data[1];
-        double dt = data[2], maxev = data[3];
-        double t = 0.0, acc = 0.0, events = 0.0;
-        double lam_mu = th[0] + th[1];
-        for (int j = 0; j < nobs; ++j) {
-            double tobs = dt * (double)(j + 1);
-            while (n > 0.0 && events < maxev) {
-                double rate = lam_mu * n, u1, u2;
-                r.u2(u1, u2);
-                double tn = t + (-plog_unit(1.0 - u1)) / rate;    // 1 - u1 in [2^-53, 1]
-                if (tn > tobs) break;
-                t = tn;
-                n += (u2 * lam_mu < th[0]) ? 1.0 : -1.0;
-                events += 1.0;
-            }
-            t = tobs;
-            double dn = n - data[4 + j];
-            acc += dn * dn;
-        }
-        blob[0] = n; blob[1] = events;
-        return sqrt(acc / (double)nobs);
+        State s;
+        begin(s, th, data);
+        while (step(s, data, r)) {}
+        return finish(s, blob);
     }
 };
 

@@ -523,6 +523,244 @@ simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* _
 
 #ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------------------------------
+// abcdesmc_swarm! for HEAVY simulators (M::SPLIT): propose -> queue-driven simulate -> accept
+// ---------------------------------------------------------------------------------------
+// In the fused kernel a lane whose proposal leaves the prior's support (src/abcdez_smc.jl:135: `continue`) idles while the
+// rest of its warp simulates -- with box priors that is 50-75 % of the lanes early in a run -- and a stochastic simulator
+// keeps every warp busy until its LONGEST trajectory ends (birth-death SSA: 2.1 of 32 lanes active on average, ncu).
+// Here the sweep is three launches over the same arithmetic and the same Philox streams (bit-identical results):
+//   propose   partners, jitter, DE proposal, prior; proposals inside the support go into a queue (theta', log prior kept)
+//   simulate  a persistent grid works the queue off: equal-length simulators stride over it with dense warps; STEPPED
+//             simulators (begin / step / finish) run ONE merged loop per lane -- "fetch the next pending simulation" or
+//             "advance mine by one step" -- so a lane is refilled the moment its trajectory ends
+//   accept    MH accept against the current eps kernel, counters, and the sweep's control logic in the last CTA
+template <class M, class = void> struct model_is_split { static constexpr bool value = false; };
+template <class M> struct model_is_split<M, decltype((void)M::SPLIT)> { static constexpr bool value = M::SPLIT; };
+template <class M, class = void> struct model_is_stepped { static constexpr bool value = false; };
+template <class M> struct model_is_stepped<M, decltype((void)M::STEPPED)> { static constexpr bool value = M::STEPPED; };
+
+template <class M, bool DISC, int PK, bool SEG>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr)
+{
+    constexpr int D = M::D, NB = M::BLOB / 8;
+    Ctrl* c = P.ctrl;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t N = P.N;
+    const uint32_t listed = j < N ? P.alive_list[j] : 0u;
+    if (c->stop | c->sweeps_done) return;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const uint32_t n_alive = c->n_alive;
+    const double* __restrict__ th = P.theta[cur];
+    const PhiloxKeys& seed = P.keys;
+    const uint32_t epoch = c->sweep_epoch;
+    const double gamma0 = c->gamma0, gsig = c->gsig;
+    bool queued = false; uint32_t i = 0;
+    if (j < N) {
+        i = (n_alive == N) ? j : listed;
+        const uint8_t mv = P.moved[i];
+        if (j >= n_alive) {                                                // dead particle (:114): repair its stale row, once
+            if (mv) {
+                double row[D];
+                load_row<D>(th, i, row);
+                store_row<D>(P.theta[nxt], i, row);
+                copy_scalars<NB>(P, cur, nxt, i, P.logpi[cur][i], P.delta[cur][i]);
+                P.moved[i] = 0;
+            }
+        } else {
+            const uint32_t pid = P.id0 + i;
+            int err = 0;
+            uint32_t a, b;
+            Stream ps(seed, pid, epoch, TAG_PARTNER);
+            double u1, u2, ua, ub; uint32_t att = 1;
+            if (SEG) {
+                Stream ws(seed, P.id0 + (j & ~31u), epoch, TAG_SEGMENT);
+                ws.u2(0u, ua, ub);
+                const uint32_t lane = threadIdx.x & 31;
+                uint32_t ka = (uint32_t)(ua * (double)n_alive), kb = (uint32_t)(ub * (double)n_alive);
+                ka = ((ka >= n_alive ? n_alive - 1 : ka) + lane) % n_alive;
+                kb = ((kb >= n_alive ? n_alive - 1 : kb) + lane) % n_alive;
+                a = (n_alive == N) ? ka : P.alive_list[ka];
+                b = (n_alive == N) ? kb : P.alive_list[kb];
+                att = 0;
+            } else {
+                ps.u2(0u, ua, ub);
+                a = wsample_alive(P.alive_list, n_alive, N, ua);
+                b = wsample_alive(P.alive_list, n_alive, N, ub);
+            }
+            if (a == i || b == a || b == i) {
+                while (a == i) {                                           // :119-122
+                    if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                    ps.u2(att++, u1, u2);
+                    a = wsample_alive(P.alive_list, n_alive, N, u1);
+                }
+                att = SEG ? 0 : 1;
+                while (b == a || b == i) {                                 // :123-126
+                    if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                    ps.u2(att++, u1, u2);
+                    b = wsample_alive(P.alive_list, n_alive, N, u2);
+                }
+            }
+            Stream ms(seed, pid, epoch, TAG_MOVE);
+            double z, z2;
+            ms.n2(0u, z, z2);
+            const double g = gamma0 * (1.0 + z * gsig);                    // :128
+            double thp[D];
+            load_row<D>(th, i, thp);
+            if (mv) {                                                      // repair the stale row in g+1
+                store_row<D>(P.theta[nxt], i, thp);
+                copy_scalars<NB>(P, cur, nxt, i, P.logpi[cur][i], P.delta[cur][i]);
+            }
+            uint8_t flag = 0;
+            if (err) atomicMax(&c->acc.err, err);
+            else {
+                de_proposal<D>(th, a, b, g, thp);                          // :128
+                double xs[DISC ? D : 1];
+                const double* x = thp;
+                if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
+                const double lp = prior_logpdf_k<D, PK>(pr, x);            // :134
+                if (!(lp < 0.0 && isinf(lp))) {                            // :135
+                    store_row<D>(P.prop_theta, i, thp);
+                    P.prop_lp[i] = lp;
+                    flag = 1; queued = true;
+                }
+            }
+            P.prop_flag[i] = flag;
+        }
+    }
+    // queue slots: one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, queued);
+    if (m) {
+        const unsigned lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&c->acc.queue_len, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (queued) P.queue[base + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+}
+
+template <class M, bool DISC>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md)
+{
+    constexpr int D = M::D, NB = M::BLOB / 8;
+    Ctrl* c = P.ctrl;
+    if (c->stop | c->sweeps_done) return;
+    const unsigned len = __ldcg(&c->acc.queue_len);
+    const PhiloxKeys& seed = P.keys;
+    const uint32_t epoch = c->sweep_epoch;
+    if constexpr (!model_is_stepped<M>::value) {
+        // equal-length simulations: a static stride over the queue keeps every warp dense
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < len; q += gridDim.x * blockDim.x) {
+            const uint32_t i = P.queue[q];
+            double thp[D], xs[DISC ? D : 1], blp[NB > 0 ? NB : 1];
+            load_row<D>(P.prop_theta, i, thp);
+            const double* x = thp;
+            if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
+            SimRng r(seed, P.id0 + i, epoch, TAG_MODEL);
+            P.prop_dp[i] = M::run(x, md.v, r, blp);                        // :137
+#pragma unroll
+            for (int k = 0; k < NB; ++k) P.prop_blob[(size_t)i * NB + k] = blp[k];
+        }
+    } else {
+        // STEPPED simulators: one merged loop per lane -- fetch the next pending simulation, or advance mine by one step
+        typename M::State st;
+        SimRng r(seed, 0u, epoch, TAG_MODEL);
+        uint32_t i = 0;
+        bool have = false, drained = false;
+        const unsigned lane = threadIdx.x & 31;
+        for (;;) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have && !drained);
+            if (need) {                                                    // one atomic per warp and refill round
+                unsigned base = 0;
+                if (lane == (unsigned)(__ffs(need) - 1)) base = atomicAdd(&c->acc.queue_next, (unsigned)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+                if (!have && !drained) {
+                    const unsigned q = base + __popc(need & ((1u << lane) - 1u));
+                    if (q < len) {
+                        i = P.queue[q];
+                        double thp[D], xs[DISC ? D : 1];
+                        load_row<D>(P.prop_theta, i, thp);
+                        const double* x = thp;
+                        if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
+                        r = SimRng(seed, P.id0 + i, epoch, TAG_MODEL);
+                        M::begin(st, x, md.v);
+                        have = true;
+                    } else drained = true;
+                }
+            }
+            if (have) {
+#pragma unroll 1
+                for (int burst = 0; burst < 8 && have; ++burst) {          // a few steps between refill votes
+                    if (!M::step(st, md.v, r)) {
+                        double blp[NB > 0 ? NB : 1];
+                        P.prop_dp[i] = M::finish(st, blp);
+#pragma unroll
+                        for (int k = 0; k < NB; ++k) P.prop_blob[(size_t)i * NB + k] = blp[k];
+                        have = false;
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, drained && !have)) break;
+        }
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+smc_accept_kernel(const __grid_constant__ PopDev P)
+{
+    constexpr int D = M::D, NB = M::BLOB / 8;
+    Ctrl* c = P.ctrl;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t N = P.N;
+    const uint32_t listed = j < N ? P.alive_list[j] : 0u;
+    if (c->stop | c->sweeps_done) return;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const uint32_t n_alive = c->n_alive;
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
+    unsigned nsim = 0, nacc = 0;
+    const double eps = c->eps; const int kind = c->kind;
+    if (j < n_alive && j < N) {
+        const uint32_t i = (n_alive == N) ? j : listed;
+        const uint8_t mv = P.moved[i];
+        if (P.prop_flag[i]) {
+            const double lp = P.prop_lp[i], dp = P.prop_dp[i];
+            const double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
+            nsim = 1;                                                      // :138
+            double w = lp - lpi;                                           // :140-141, left to right
+            w = w + abck_logpdf(kind, eps, dp);
+            w = w - abck_logpdf(kind, eps, dli);
+            bool acc = (0.0 <= w);
+            if (!acc) {                                                    // :145, uniform only when w < 0
+                Stream ms(P.keys, P.id0 + i, c->sweep_epoch, TAG_MOVE);
+                double u, u2;
+                ms.u2(1u, u, u2);
+                acc = ((u == 0.0 ? -INFINITY : plog_unit(u)) < w);
+            }
+            if (acc) {                                                     // :146-150
+                double thp[D];
+                load_row<D>(P.prop_theta, i, thp);
+                store_row<D>(P.theta[nxt], i, thp);
+                P.logpi[nxt][i] = lp;
+                P.delta[nxt][i] = dp;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = P.prop_blob[(size_t)i * NB + k];
+                nacc = 1;
+            }
+        }
+        if ((uint8_t)nacc != mv) P.moved[i] = (uint8_t)nacc;
+    }
+    const bool last = sweep_finish<false>(c, &s_red, nsim, nacc, 0ull, 0ull, 0);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, false);
+    if (last) {
+        c->acc.queue_len = 0u; c->acc.queue_next = 0u;                     // the next sweep's queue
+        ctrl_after_smc_sweep(P, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // launchers + registry
 // ---------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t N, int threads) { return (unsigned)((N + threads - 1) / threads); }
@@ -540,6 +778,27 @@ static void l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const Prio
 {
     init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, philox_keys(seed), dp);
 }
+template <class M, bool DISC, int PK>
+static void l_smc_split(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md)
+{
+    const unsigned g = grid_for(P.N, SWEEP_THREADS);
+    if (P.flags & POP_PARTNER_SEGMENTS) smc_propose_kernel<M, DISC, PK, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr);
+    else smc_propose_kernel<M, DISC, PK, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr);
+    // persistent grid for the queue: SMs x resident CTAs (per device)
+    static int cached[64] = { 0 };
+    int dev = 0; cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (!cached[slot]) {
+        int sms = 148, per = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, simulate_queue_kernel<M, DISC>, SWEEP_THREADS, 0) != cudaSuccess || per < 1) per = 1;
+        cached[slot] = sms * per;
+    }
+    const unsigned gq = g < (unsigned)cached[slot] ? g : (unsigned)cached[slot];
+    simulate_queue_kernel<M, DISC><<<gq, SWEEP_THREADS, 0, st>>>(P, pr, md);
+    smc_accept_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P);
+}
+
 template <class M>
 static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj)
 {
@@ -547,6 +806,15 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     bool all_normal = true, all_uniform = true;
     for (int k = 0; k < M::D; ++k) { all_normal = all_normal && pr.family[k] == ABCDEZ_NORMAL; all_uniform = all_uniform && pr.family[k] == ABCDEZ_UNIFORM; }
     const bool injected = inj.a || inj.b || inj.s || inj.z || inj.u || inj.flags;
+    if constexpr (model_is_split<M>::value) {
+        // heavy simulators: queue-driven sweep (three launches, same results); stage calls with injected randomness keep the fused kernel
+        if (!injected && P.prop_theta) {
+            if (prior_has_discrete<M::D>(pr)) l_smc_split<M, true, PK_GENERIC>(st, P, pr, md);
+            else if (all_uniform) l_smc_split<M, false, PK_UNIFORM>(st, P, pr, md);
+            else l_smc_split<M, false, PK_GENERIC>(st, P, pr, md);
+            return;
+        }
+    }
     if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
     else if (all_normal) {
         if (injected) smc_sweep_kernel<M, false, PK_NORMAL, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
@@ -579,7 +847,7 @@ static ModelOps make_ops()
 {
     ModelOps o;
     o.name = M::name; o.d = M::D; o.blob = M::BLOB;
-    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr;
+    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr; o.split = model_is_split<M>::value ? 1 : 0;
     return o;
 }
 

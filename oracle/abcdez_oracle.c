@@ -1132,7 +1132,6 @@ int orc_quantile_alive(int64_t N, const double* delta, const uint8_t* alive, dou
     int64_t n = 0;
     for (int64_t i = 0; i < N; ++i) if (alive[i]) { if (isnan(delta[i])) { free(v); return 3; } v[n++] = delta[i]; }
     if (n == 0) { free(v); return 4; }
-    qsort(v, (size_t)n, sizeof(double), cmp_double);
     double m = 1.0 - p;                     /* alpha + p*(1-alpha-beta), alpha=beta=1 */
     double aleph = fma((double)n, p, m);
     int64_t j = (int64_t)trunc(aleph);
@@ -1143,7 +1142,23 @@ int orc_quantile_alive(int64_t N, const double* delta, const uint8_t* alive, dou
     if (g > 1.0) g = 1.0;
     double a, b;
     if (n == 1) { a = v[0]; b = v[0]; j = 1; }
-    else { a = v[j - 1]; b = v[j]; }
+    else {
+        /* Statistics.quantile partial-sorts (sort!(v, 1:n, PartialQuickSort(j:j+1))): v[j] by quickselect, then v[j+1] is
+         * the minimum of what the selection left above position j -- the same two order statistics as a full sort */
+        int64_t lo = 0, hi = n - 1, k = j - 1;
+        while (lo < hi) {
+            double piv = v[lo + (hi - lo) / 2];
+            int64_t i = lo, t = hi;
+            while (i <= t) {
+                while (cmp_double(&v[i], &piv) < 0) ++i;
+                while (cmp_double(&v[t], &piv) > 0) --t;
+                if (i <= t) { double tmp = v[i]; v[i] = v[t]; v[t] = tmp; ++i; --t; }
+            }
+            if (k <= t) hi = t; else if (k >= i) lo = i; else break;
+        }
+        a = v[k]; b = v[k + 1];
+        for (int64_t i = k + 2; i < n; ++i) if (cmp_double(&v[i], &b) < 0) b = v[i];
+    }
     double q = (isfinite(a) && isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
     free(v);
     if (q_out) *q_out = q;
