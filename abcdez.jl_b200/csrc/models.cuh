@@ -229,6 +229,15 @@ struct BirthDeath {
         while (step(s, data, r)) {}
         return finish(s, blob);
     }
+    // scheduling hint for the queue-driven sweep (never affects a result): trajectories expected to be long are handed out
+    // first, so that no lane starts a 5000-event trajectory when the rest of the queue is already drained.
+    // E[events] ~ n0 (lambda + mu) (e^{rT} - 1) / r with r = lambda - mu, T = nobs dt
+    __device__ static __forceinline__ bool heavy(const double* th, const double* data)
+    {
+        const double r = th[0] - th[1], T = data[1] * data[2];
+        const double growth = fabs(r) > 1e-9 ? (exp(r * T) - 1.0) / r : T;
+        return data[0] * (th[0] + th[1]) * growth > 0.2 * data[3];
+    }
 };
 
 // test/runtests.jl:427-437 (socks): sequential picks without replacement

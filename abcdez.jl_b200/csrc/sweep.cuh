@@ -538,10 +538,19 @@ template <class M, class = void> struct model_is_split { static constexpr bool v
 template <class M> struct model_is_split<M, decltype((void)M::SPLIT)> { static constexpr bool value = M::SPLIT; };
 template <class M, class = void> struct model_is_stepped { static constexpr bool value = false; };
 template <class M> struct model_is_stepped<M, decltype((void)M::STEPPED)> { static constexpr bool value = M::STEPPED; };
+// optional scheduling hint M::heavy(theta, data): such simulations go to the FRONT of the queue (longest first)
+template <class M, class = void> struct model_has_heavy { static constexpr bool value = false; };
+template <class M> struct model_has_heavy<M, decltype((void)&M::heavy)> { static constexpr bool value = true; };
+// queue layout: heavy entries fill [0, heavy) from the front, the others [N - light, N) from the back; entry q of the
+// hand-out order is queue[q] for q < heavy and queue[N - 1 - (q - heavy)] behind them
+__device__ __forceinline__ uint32_t queue_entry(const PopDev& P, unsigned q, unsigned heavy)
+{
+    return q < heavy ? P.queue[q] : P.queue[P.N - 1u - (q - heavy)];
+}
 
 template <class M, bool DISC, int PK, bool SEG>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
-smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr)
+smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
@@ -555,7 +564,7 @@ smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pri
     const PhiloxKeys& seed = P.keys;
     const uint32_t epoch = c->sweep_epoch;
     const double gamma0 = c->gamma0, gsig = c->gsig;
-    bool queued = false; uint32_t i = 0;
+    bool queued = false, hvy = false; uint32_t i = 0;
     if (j < N) {
         i = (n_alive == N) ? j : listed;
         const uint8_t mv = P.moved[i];
@@ -623,19 +632,26 @@ smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pri
                     store_row<D>(P.prop_theta, i, thp);
                     P.prop_lp[i] = lp;
                     flag = 1; queued = true;
+                    if constexpr (model_has_heavy<M>::value) hvy = M::heavy(x, md.v);
                 }
             }
             P.prop_flag[i] = flag;
         }
     }
-    // queue slots: one atomic per warp
-    const unsigned m = __ballot_sync(0xffffffffu, queued);
-    if (m) {
-        const unsigned lane = threadIdx.x & 31;
+    // queue slots: one atomic per warp and class (heavy entries from the front, the others from the back)
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mh = __ballot_sync(0xffffffffu, queued && hvy), ml = __ballot_sync(0xffffffffu, queued && !hvy);
+    if (mh) {
         unsigned base = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&c->acc.queue_len, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (queued) P.queue[base + __popc(m & ((1u << lane) - 1u))] = i;
+        if (lane == (unsigned)(__ffs(mh) - 1)) base = atomicAdd(&c->acc.queue_heavy, (unsigned)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
+        if (queued && hvy) P.queue[base + __popc(mh & ((1u << lane) - 1u))] = i;
+    }
+    if (ml) {
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(ml) - 1)) base = atomicAdd(&c->acc.queue_len, (unsigned)__popc(ml));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ml) - 1);
+        if (queued && !hvy) P.queue[N - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = i;
     }
 }
 
@@ -646,13 +662,13 @@ simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ 
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
     if (c->stop | c->sweeps_done) return;
-    const unsigned len = __ldcg(&c->acc.queue_len);
+    const unsigned heavy = __ldcg(&c->acc.queue_heavy), len = heavy + __ldcg(&c->acc.queue_len);
     const PhiloxKeys& seed = P.keys;
     const uint32_t epoch = c->sweep_epoch;
     if constexpr (!model_is_stepped<M>::value) {
         // equal-length simulations: a static stride over the queue keeps every warp dense
         for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < len; q += gridDim.x * blockDim.x) {
-            const uint32_t i = P.queue[q];
+            const uint32_t i = queue_entry(P, q, heavy);
             double thp[D], xs[DISC ? D : 1], blp[NB > 0 ? NB : 1];
             load_row<D>(P.prop_theta, i, thp);
             const double* x = thp;
@@ -678,7 +694,7 @@ simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ 
                 if (!have && !drained) {
                     const unsigned q = base + __popc(need & ((1u << lane) - 1u));
                     if (q < len) {
-                        i = P.queue[q];
+                        i = queue_entry(P, q, heavy);
                         double thp[D], xs[DISC ? D : 1];
                         load_row<D>(P.prop_theta, i, thp);
                         const double* x = thp;
@@ -755,7 +771,7 @@ smc_accept_kernel(const __grid_constant__ PopDev P)
     const bool last = sweep_finish<false>(c, &s_red, nsim, nacc, 0ull, 0ull, 0);
     if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, false);
     if (last) {
-        c->acc.queue_len = 0u; c->acc.queue_next = 0u;                     // the next sweep's queue
+        c->acc.queue_len = 0u; c->acc.queue_next = 0u; c->acc.queue_heavy = 0u;   // the next sweep's queue
         ctrl_after_smc_sweep(P, c);
     }
 }
@@ -782,8 +798,8 @@ template <class M, bool DISC, int PK>
 static void l_smc_split(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md)
 {
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
-    if (P.flags & POP_PARTNER_SEGMENTS) smc_propose_kernel<M, DISC, PK, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr);
-    else smc_propose_kernel<M, DISC, PK, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr);
+    if (P.flags & POP_PARTNER_SEGMENTS) smc_propose_kernel<M, DISC, PK, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md);
+    else smc_propose_kernel<M, DISC, PK, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md);
     // persistent grid for the queue: SMs x resident CTAs (per device)
     static int cached[64] = { 0 };
     int dev = 0; cudaGetDevice(&dev);
