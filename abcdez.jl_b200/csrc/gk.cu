@@ -6,9 +6,11 @@
 //                  x = A + B (1 + 0.8 (1 - e^{-g z}) / (1 + e^{-g z})) (1 + z^2)^k z
 //              into shared memory, tracking the extrema of the order-preserving keys on the way;
 //   summaries  the 7 octiles are order statistics x_(ceil(n j / 8)); instead of sorting, a multi-select in KEY
-//              space: one 2048-bin histogram between the extrema resolves all 7 ranks to a bucket each,
-//              buckets that are still large are refined 256 ways, and the <= 64 keys left per octile are
-//              ranked directly by one warp -- 3 passes over shared memory in the usual case;
+//              space: one 2048-bin histogram resolves all 7 ranks to a bucket each -- over the window the
+//              distribution's own quantile function predicts for the octiles (~5 keys per bin), or between the
+//              sample's extrema when a rank falls outside it; buckets that are still large are refined 256 ways,
+//              and the <= 64 keys left per octile are ranked directly by one warp -- 2 passes over shared memory
+//              in the usual case;
 //   distance   sqrt(mean squared octile difference) in FP64.
 // Two registered models, same definition, different arithmetic:
 //   "gk"      FP64 with the library's portable log / exp / sin / cos (common.cuh), i.e. the arithmetic a Julia
@@ -24,7 +26,11 @@
 
 namespace abcdez {
 
-constexpr int GK_THREADS = 256;
+#ifndef ABCDEZ_GK_THREADS
+#define ABCDEZ_GK_THREADS 256
+#endif
+constexpr int GK_THREADS = ABCDEZ_GK_THREADS;     // threads of the CTA that simulates one particle
+constexpr int GK_BPT = SEL_BINS / GK_THREADS;      // histogram bins per thread in the prefix step
 constexpr int GK_MAXN = 16384;
 constexpr int GK_NQ = 7;
 constexpr int GK_LIST = 64;               // keys per octile ranked directly
@@ -37,6 +43,8 @@ struct GkSmem {
     unsigned rank[GK_NQ], cnt[GK_NQ], nlist[GK_NQ];
     unsigned part[GK_THREADS];
     unsigned long long kmin, kmax;
+    float zl[8], zh[8], invw[8];          // fast path: the z windows of the 7 octiles
+    unsigned region[8], tbin[GK_NQ], base[GK_NQ], miss[4];
     double dist;
 };
 
@@ -160,49 +168,33 @@ template <> struct GkMath<float> {
     }
 };
 
-// every thread of the CTA calls; returns the distance in every thread.  xs: n values of shared memory.
+// ---- the generic path: multi-select of the 7 octile keys over the transformed draws in xs --------------------
+// Leaves the selected keys in s->q (visible to every thread after the trailing barrier).
 template <class T>
-__device__ double gk_simulate_cta(const double* th, const double* data, const Stream& rs, T* xs, GkSmem* s)
+__device__ __noinline__ void gk_select_generic(int n, const T* xs, GkSmem* s)
 {
     using MT = GkMath<T>;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    int n = (int)data[0];
-    n = n < 8 ? 8 : (n > GK_MAXN ? GK_MAXN : n);
-    const T A = (T)th[0], B = (T)th[1], g = (T)th[2], k = (T)th[3];
-    __syncthreads();                                   // the previous particle's readers are done with xs / s
-    // ---- draws ---------------------------------------------------------------------------------------
-    unsigned long long kmn = ~0ull, kmx = 0ull;
-    for (int b = tid; b * MT::PER_BLOCK < n; b += GK_THREADS) {
-        T z[MT::PER_BLOCK];
-        MT::normals(rs, (uint32_t)b, z);
-#pragma unroll
-        for (int j = 0; j < MT::PER_BLOCK; ++j) {
-            const T x = MT::transform(A, B, g, k, z[j]);
-            const int i = b * MT::PER_BLOCK + j;
-            if (i < n) {
-                xs[i] = x;
-                const unsigned long long key = MT::key(x);
-                kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx;
-            }
-        }
-    }
+    __syncthreads();
     for (int q = tid; q < SEL_BINS; q += GK_THREADS) s->hist[q] = 0u;
     for (int q = tid; q < GK_NQ * 256; q += GK_THREADS) (&s->sub[0][0])[q] = 0u;
     if (tid == 0) { s->kmin = ~0ull; s->kmax = 0ull; }
     if (tid < GK_NQ) s->nlist[tid] = 0u;
     __syncthreads();
-    kmn = warp_min_u64(kmn); kmx = warp_max_u64(kmx);
-    if (lane == 0) { atomicMin(&s->kmin, kmn); atomicMax(&s->kmax, kmx); }
-    __syncthreads();
-    const unsigned long long kmin = s->kmin, kmax = s->kmax, width = kmax - kmin;
-    // ---- round 1: 2048 bins of 2^sh keys between the extrema ----------------------------------------------
-    const int sh = width ? max(0, 64 - __clzll((long long)width) - 11) : 0;       // (width >> sh) <= 2047
-    for (int i = tid; i < n; i += GK_THREADS) atomicAdd(&s->hist[(unsigned)((MT::key(xs[i]) - kmin) >> sh)], 1u);
-    __syncthreads();
-    {   // exclusive prefix over the 2048 bins (8 per thread, shuffle scan of the thread totals), then every octile's bin
-        unsigned loc[8], tot = 0;
+    {
+        // ---- round 1: 2048 bins of 2^sh keys between the sample's extrema --------------------------------------
+        unsigned long long kmn = ~0ull, kmx = 0ull;
+        for (int i = tid; i < n; i += GK_THREADS) { const unsigned long long key = MT::key(xs[i]); kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
+        kmn = warp_min_u64(kmn); kmx = warp_max_u64(kmx);
+        if (lane == 0) { atomicMin(&s->kmin, kmn); atomicMax(&s->kmax, kmx); }
+        __syncthreads();
+        const unsigned long long kmin = s->kmin, kmax = s->kmax, width = kmax - kmin;
+        const int sh = width ? max(0, 64 - __clzll((long long)width) - 11) : 0;       // (width >> sh) <= 2047
+        for (int i = tid; i < n; i += GK_THREADS) atomicAdd(&s->hist[(unsigned)((MT::key(xs[i]) - kmin) >> sh)], 1u);
+        __syncthreads();
+        unsigned loc[GK_BPT], tot = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { loc[q] = s->hist[tid * 8 + q]; tot += loc[q]; }
+        for (int q = 0; q < GK_BPT; ++q) { loc[q] = s->hist[tid * GK_BPT + q]; tot += loc[q]; }
         unsigned incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -211,13 +203,13 @@ __device__ double gk_simulate_cta(const double* th, const double* data, const St
         unsigned cum = incl - tot;
         for (int w = 0; w < wp; ++w) cum += s->part[w];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < GK_BPT; ++q) {
             if (loc[q]) {
 #pragma unroll
                 for (int j = 0; j < GK_NQ; ++j) {
                     const unsigned r = (unsigned)((n * (j + 1) + 7) / 8) - 1u;        // 0-based rank of octile j+1
                     if (r >= cum && r < cum + loc[q]) {
-                        const unsigned long long lo = kmin + ((unsigned long long)(tid * 8 + q) << sh);
+                        const unsigned long long lo = kmin + ((unsigned long long)(tid * GK_BPT + q) << sh);
                         const unsigned long long top = lo + ((1ull << sh) - 1ull);
                         s->lo[j] = lo; s->hi[j] = top < kmax ? top : kmax;
                         s->rank[j] = r - cum; s->cnt[j] = loc[q];
@@ -226,8 +218,8 @@ __device__ double gk_simulate_cta(const double* th, const double* data, const St
             }
             cum += loc[q];
         }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- refinement: octiles whose bucket still holds more than GK_LIST keys, 256 ways per round -------------
     for (int it = 0; it < 10; ++it) {
         unsigned long long lo[GK_NQ], hi[GK_NQ];
@@ -304,6 +296,188 @@ __device__ double gk_simulate_cta(const double* th, const double* data, const St
         }
     }
     __syncthreads();
+}
+
+// ---- the fast path: select in z space ----------------------------------------------------------------------
+// For B > 0 and k >= 0 the g-and-k quantile function x = Q(z) is increasing in z, so the order statistics
+// commute with it: x_(r) = Q(z_(r)).  The octiles of n standard normals are known in advance up to sampling
+// error -- z_(ceil(n p)) lies within a few sqrt(p (1 - p) / n) / phi(z_p) of z_p = Phi^-1(p) -- so each octile
+// gets its own 256-bin histogram over z_p +- GK_WIN_SIGMAS standard errors, filled while the normals are drawn;
+// the bucket of the wanted rank and its two neighbours (about 6 draws) are the only draws pushed through Q, and
+// they are ranked by their x keys, so floating-point wobble of Q between neighbouring draws cannot change the
+// answer (it would have to exceed a bucket, 8e-4 in z).  Result: the same order statistics, bit for bit, as
+// transforming and selecting over all n draws (what the oracle does), at ~1/3 of the arithmetic.  Anything
+// unexpected -- a rank outside its window or in an edge bucket, more than GK_LIST candidates -- falls back to the
+// generic path below, which is also the path for n < GK_FAST_N and for parameters where Q need not be monotone.
+constexpr int GK_FAST_N = 4096;                   // below this the windows of neighbouring octiles would touch
+constexpr float GK_WIN_SIGMAS = 6.0f;
+__constant__ float GK_ZP[GK_NQ] = { -1.15034938f, -0.67448975f, -0.31863936f, 0.0f, 0.31863936f, 0.67448975f, 1.15034938f };
+__constant__ float GK_SE[GK_NQ] = { 1.60657f, 1.36263f, 1.27671f, 1.25331f, 1.27671f, 1.36263f, 1.60657f };   // sqrt(p (1 - p)) / phi(z_p)
+
+template <class T> __device__ __forceinline__ bool gk_finite(T v) { return v == v && fabs((double)v) < (double)INFINITY; }
+
+// region of a draw: cnt = number of window lower bounds <= z (0..7); window cnt - 1 holds it when z <= its upper bound
+__device__ __forceinline__ unsigned gk_region(float zf, const float (&zl)[GK_NQ])
+{
+    unsigned cnt = 0;
+#pragma unroll
+    for (int j = 0; j < GK_NQ; ++j) cnt += zf >= zl[j] ? 1u : 0u;
+    return cnt;
+}
+__device__ __forceinline__ int gk_bin(float zf, float zl, float invw)
+{
+    const int b = (int)((zf - zl) * invw);                    // monotone in zf; the same expression in both passes
+    return b > 255 ? 255 : b;
+}
+
+// every thread of the CTA calls; returns the distance in every thread.  xs: n values of shared memory.
+template <class T>
+__device__ double gk_simulate_cta(const double* th, const double* data, const Stream& rs, T* xs, GkSmem* s)
+{
+    using MT = GkMath<T>;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    int n = (int)data[0];
+    n = n < 8 ? 8 : (n > GK_MAXN ? GK_MAXN : n);
+    const T A = (T)th[0], B = (T)th[1], g = (T)th[2], k = (T)th[3];
+    const bool fast = n >= GK_FAST_N && gk_finite(A) && gk_finite(g) && B > (T)0 && gk_finite(B) && k >= (T)0 && gk_finite(k);
+    __syncthreads();                                   // the previous particle's readers are done with xs / s
+    bool done = false;
+    if (fast) {
+        for (int q = tid; q < GK_NQ * 256; q += GK_THREADS) (&s->sub[0][0])[q] = 0u;
+        if (tid < 8) s->region[tid] = 0u;
+        if (tid < 3) s->miss[tid] = 0u;
+        if (tid < GK_NQ) {
+            const float h = GK_WIN_SIGMAS * GK_SE[tid] / sqrtf((float)n);
+            s->zl[tid] = GK_ZP[tid] - h; s->zh[tid] = GK_ZP[tid] + h; s->invw[tid] = 128.0f / h;
+            s->nlist[tid] = 0u;
+        }
+        __syncthreads();
+        float zl[GK_NQ];
+#pragma unroll
+        for (int j = 0; j < GK_NQ; ++j) zl[j] = s->zl[j];
+        // ---- draws: the normals go to shared memory, window hits into their histograms ------------------------
+        unsigned long long pk = 0ull;                          // 8 region counters of 8 bits (<= n / 256 <= 64 draws per thread)
+        for (int b = tid; b * MT::PER_BLOCK < n; b += GK_THREADS) {
+            T z[MT::PER_BLOCK];
+            MT::normals(rs, (uint32_t)b, z);
+#pragma unroll
+            for (int j = 0; j < MT::PER_BLOCK; ++j) {
+                const int i = b * MT::PER_BLOCK + j;
+                if (i < n) {
+                    xs[i] = z[j];
+                    const float zf = (float)z[j];
+                    const unsigned cnt = gk_region(zf, zl);
+                    pk += 1ull << (8u * cnt);
+                    if (cnt) {
+                        const unsigned w = cnt - 1u;
+                        if (zf <= s->zh[w]) atomicAdd(&s->sub[w][gk_bin(zf, s->zl[w], s->invw[w])], 1u);
+                    }
+                }
+            }
+        }
+        {   // region totals: 16-bit fields, 32 lanes x 64 draws fit
+            unsigned long long ev = pk & 0x00ff00ff00ff00ffull, od = (pk >> 8) & 0x00ff00ff00ff00ffull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ev += __shfl_xor_sync(0xffffffffu, ev, o); od += __shfl_xor_sync(0xffffffffu, od, o); }
+            if (lane < 8) {
+                const unsigned long long src = (lane & 1) ? od : ev;
+                const unsigned v = (unsigned)((src >> (16 * (lane >> 1))) & 0xffffull);
+                if (v) atomicAdd(&s->region[lane], v);
+            }
+        }
+        __syncthreads();
+        // ---- warp j: the bucket of octile j's rank ----------------------------------------------------------
+        if (wp < GK_NQ) {
+            const int j = wp;
+            unsigned below = 0;
+            for (int m = 0; m <= j; ++m) below += s->region[m];                       // draws left of window j
+            const unsigned r = (unsigned)((n * (j + 1) + 7) / 8) - 1u;                // 0-based rank of octile j+1
+            unsigned loc[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = s->sub[j][lane * 8 + q]; tot += loc[q]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const unsigned inwin = __shfl_sync(0xffffffffu, incl, 31);
+            if (r < below || r - below >= inwin) { if (lane == 0) s->miss[0] = 1u; }
+            else {
+                const unsigned rw = r - below;
+                unsigned cum = incl - tot;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (rw >= cum && rw < cum + loc[q]) {
+                        const int bin = lane * 8 + q;
+                        if (bin == 0 || bin == 255) s->miss[0] = 1u;
+                        else { s->tbin[j] = (unsigned)bin; s->base[j] = below + cum - s->sub[j][bin - 1]; s->rank[j] = r; }
+                    }
+                    cum += loc[q];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- candidates: the draws of that bucket and its neighbours -----------------------------------------
+        if (!s->miss[0]) {
+            for (int i = tid; i < n; i += GK_THREADS) {
+                const float zf = (float)xs[i];
+                const unsigned cnt = gk_region(zf, zl);
+                if (cnt) {
+                    const unsigned w = cnt - 1u;
+                    if (zf <= s->zh[w]) {
+                        const int d = gk_bin(zf, s->zl[w], s->invw[w]) - (int)s->tbin[w];
+                        if (d >= -1 && d <= 1) {
+                            const unsigned idx = atomicAdd(&s->nlist[w], 1u);
+                            if (idx < (unsigned)GK_LIST) s->list[w][idx] = (unsigned long long)i;
+                            else s->miss[1] = 1u;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- warp j pushes octile j's candidates through Q and ranks them by x --------------------------------
+        if (wp < GK_NQ && !s->miss[0] && !s->miss[1]) {
+            const int j = wp;
+            const unsigned m = s->nlist[j], r = s->rank[j], base = s->base[j];
+            unsigned long long my[GK_LIST / 32];
+#pragma unroll
+            for (int h = 0; h < GK_LIST / 32; ++h) {
+                const unsigned me = lane + 32 * h;
+                my[h] = me < m ? MT::key(MT::transform(A, B, g, k, xs[(int)s->list[j][me]])) : ~0ull;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < GK_LIST / 32; ++h) { const unsigned me = lane + 32 * h; if (me < m) s->list[j][me] = my[h]; }
+            __syncwarp();
+            if (r < base || r - base >= m) { if (lane == 0) s->miss[2] = 1u; }
+            else {
+#pragma unroll
+                for (int h = 0; h < GK_LIST / 32; ++h) {
+                    const unsigned me = lane + 32 * h;
+                    if (me < m) {
+                        unsigned before = 0;
+                        for (unsigned o = 0; o < m; ++o) { const unsigned long long ot = s->list[j][o]; before += (ot < my[h] || (ot == my[h] && o < me)) ? 1u : 0u; }
+                        if (before == r - base) s->q[j] = my[h];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        done = !(s->miss[0] | s->miss[1] | s->miss[2]);
+        if (!done) for (int i = tid; i < n; i += GK_THREADS) xs[i] = MT::transform(A, B, g, k, xs[i]);   // -> generic path
+    } else {
+        // ---- draws, all pushed through Q ------------------------------------------------------------------------
+        for (int b = tid; b * MT::PER_BLOCK < n; b += GK_THREADS) {
+            T z[MT::PER_BLOCK];
+            MT::normals(rs, (uint32_t)b, z);
+#pragma unroll
+            for (int j = 0; j < MT::PER_BLOCK; ++j) {
+                const T x = MT::transform(A, B, g, k, z[j]);
+                const int i = b * MT::PER_BLOCK + j;
+                if (i < n) xs[i] = x;
+            }
+        }
+    }
+    if (!done) gk_select_generic<T>(n, xs, s);
     if (tid == 0) {
         double acc = 0.0;
 #pragma unroll

@@ -324,16 +324,24 @@ def _gk_octiles(theta, n=200000, seed=1):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("model", ["gk", "gk_f32"])
-@pytest.mark.parametrize("n", [10000, 16384, 1001, 8])
+@pytest.mark.parametrize("n", [10000, 16384, 4096, 4095, 1001, 8])
 def test_gk_simulate_parity(A, oracle, gpu_ctx, model, n):
     """One dist! evaluation per row: same Philox blocks, the same portable arithmetic operation by operation (FP64 for
     "gk" -- the precision of a Julia dist! --, FP32 for the relaxed mode "gk_f32"), a key-space multi-select vs qsort
-    for the octiles: the distances are BIT-IDENTICAL (north star: <= 1e-6 relative)."""
+    for the octiles: the distances are BIT-IDENTICAL (north star: <= 1e-6 relative).  From n = 4096 on the kernel
+    selects in z space and transforms only the candidates (gk.cu, "the fast path"); rows 5-12 are the parameter corners
+    of that path and of its fallback."""
     data = [float(n)] + _gk_octiles(GK_TRUE)
-    N = 300
+    N = 1200 if n >= 4096 else 300
     th = oracle.prior_sample(GK_PRIOR, N, seed=3)
     th[5] = [3.0, 0.0, 1.0, 0.5]                    # B = 0: every draw equals A (one key fills every bucket)
     th[6] = [0.0, 1.0, 0.0, 0.0]                    # plain normal draws around 0: keys on both sides of zero
+    th[7] = [3.0, -1.0, 2.0, 0.5]                   # B < 0: Q decreasing -> generic path at every n
+    th[8] = [3.0, 1.0, 2.0, -0.3]                   # k < 0 -> generic path
+    th[9] = [10.0, 1e-13, 2.0, 0.5]                 # x is a staircase of ulp(10) steps: plateaus wider than a bucket
+    th[10] = [0.0, 1.0, 50.0, 9.9]                  # steep tanh, huge (1 + z^2)^k
+    th[11] = [1e-3, 1e3, -7.0, 0.0]                 # negative g
+    th[12] = [5.0, 1.0, 0.0, 1e-300]
     want, _ = oracle.simulate(model, data, th, seed=11, epoch=2)
     got, _ = A.Model(model, data).simulate(th, seed=11, epoch=2)
     np.testing.assert_array_equal(got, want)
