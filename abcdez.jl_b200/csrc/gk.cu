@@ -32,6 +32,10 @@ namespace abcdez {
 constexpr int GK_THREADS = ABCDEZ_GK_THREADS;     // threads of the CTA that simulates one particle
 constexpr int GK_BPT = SEL_BINS / GK_THREADS;      // histogram bins per thread in the prefix step
 constexpr int GK_MAXN = 16384;
+#ifndef ABCDEZ_GK_ILP
+#define ABCDEZ_GK_ILP 2
+#endif
+constexpr int GK_ILP = ABCDEZ_GK_ILP;              // Philox blocks (Box-Muller chains) in flight per thread in the fast path
 constexpr int GK_NQ = 7;
 constexpr int GK_LIST = 64;               // keys per octile ranked directly
 
@@ -114,6 +118,7 @@ template <class T> struct GkMath;
 
 template <> struct GkMath<double> {
     static constexpr int PER_BLOCK = 2;           // draws per Philox block
+    static constexpr int MIN_CTAS = 2;            // resident CTAs per SM the register allocation must allow (= what shared memory allows at n = 10^4)
     static constexpr const char* name = "gk";
     __device__ static __forceinline__ void normals(const Stream& rs, uint32_t b, double* z) { rs.n2(b, z[0], z[1]); }
     __device__ static __forceinline__ double transform(double A, double B, double g, double k, double z)
@@ -133,6 +138,7 @@ template <> struct GkMath<double> {
 
 template <> struct GkMath<float> {
     static constexpr int PER_BLOCK = 4;
+    static constexpr int MIN_CTAS = 3;
     static constexpr const char* name = "gk_f32";
     __device__ static __forceinline__ void normals(const Stream& rs, uint32_t b, float* z)
     {
@@ -316,13 +322,14 @@ __constant__ float GK_SE[GK_NQ] = { 1.60657f, 1.36263f, 1.27671f, 1.25331f, 1.27
 
 template <class T> __device__ __forceinline__ bool gk_finite(T v) { return v == v && fabs((double)v) < (double)INFINITY; }
 
-// region of a draw: cnt = number of window lower bounds <= z (0..7); window cnt - 1 holds it when z <= its upper bound
+// region of a draw: cnt = number of window lower bounds <= z (0..7), by a 3-step binary search over the ascending
+// bounds; window cnt - 1 holds the draw when z <= its upper bound
 __device__ __forceinline__ unsigned gk_region(float zf, const float (&zl)[GK_NQ])
 {
-    unsigned cnt = 0;
-#pragma unroll
-    for (int j = 0; j < GK_NQ; ++j) cnt += zf >= zl[j] ? 1u : 0u;
-    return cnt;
+    const bool h4 = zf >= zl[3];
+    const bool h2 = zf >= (h4 ? zl[5] : zl[1]);
+    const float t = h4 ? (h2 ? zl[6] : zl[4]) : (h2 ? zl[2] : zl[0]);
+    return (h4 ? 4u : 0u) + (h2 ? 2u : 0u) + (zf >= t ? 1u : 0u);
 }
 __device__ __forceinline__ int gk_bin(float zf, float zl, float invw)
 {
@@ -357,20 +364,24 @@ __device__ double gk_simulate_cta(const double* th, const double* data, const St
         for (int j = 0; j < GK_NQ; ++j) zl[j] = s->zl[j];
         // ---- draws: the normals go to shared memory, window hits into their histograms ------------------------
         unsigned long long pk = 0ull;                          // 8 region counters of 8 bits (<= n / 256 <= 64 draws per thread)
-        for (int b = tid; b * MT::PER_BLOCK < n; b += GK_THREADS) {
-            T z[MT::PER_BLOCK];
-            MT::normals(rs, (uint32_t)b, z);
+        for (int b0 = tid; b0 * MT::PER_BLOCK < n; b0 += GK_THREADS * GK_ILP) {
+            T z[GK_ILP][MT::PER_BLOCK];
 #pragma unroll
-            for (int j = 0; j < MT::PER_BLOCK; ++j) {
-                const int i = b * MT::PER_BLOCK + j;
-                if (i < n) {
-                    xs[i] = z[j];
-                    const float zf = (float)z[j];
-                    const unsigned cnt = gk_region(zf, zl);
-                    pk += 1ull << (8u * cnt);
-                    if (cnt) {
-                        const unsigned w = cnt - 1u;
-                        if (zf <= s->zh[w]) atomicAdd(&s->sub[w][gk_bin(zf, s->zl[w], s->invw[w])], 1u);
+            for (int u = 0; u < GK_ILP; ++u) MT::normals(rs, (uint32_t)(b0 + u * GK_THREADS), z[u]);   // independent chains; a block past n is dropped below
+#pragma unroll
+            for (int u = 0; u < GK_ILP; ++u) {
+#pragma unroll
+                for (int j = 0; j < MT::PER_BLOCK; ++j) {
+                    const int i = (b0 + u * GK_THREADS) * MT::PER_BLOCK + j;
+                    if (i < n) {
+                        xs[i] = z[u][j];
+                        const float zf = (float)z[u][j];
+                        const unsigned cnt = gk_region(zf, zl);
+                        pk += 1ull << (8u * cnt);
+                        if (cnt) {
+                            const unsigned w = cnt - 1u;
+                            if (zf <= s->zh[w]) atomicAdd(&s->sub[w][gk_bin(zf, s->zl[w], s->invw[w])], 1u);
+                        }
                     }
                 }
             }
@@ -505,7 +516,7 @@ template <class T> static inline size_t gk_smem_bytes(const ModelData& md)
 
 // ---- abcde_init! (src/abcdez_init.jl:2-22), one CTA per particle ----------------------------------------
 template <class T>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, GkMath<T>::MIN_CTAS)
 gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                const __grid_constant__ PhiloxKeys seed, int draw_prior)
 {
@@ -556,7 +567,7 @@ gk_init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDe
 
 // ---- abcdesmc_swarm! (src/abcdez_smc.jl:106-153), one CTA per listed particle ------------------------------
 template <class T>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, GkMath<T>::MIN_CTAS)
 gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                     const __grid_constant__ SweepInj inj)
 {
@@ -656,7 +667,7 @@ gk_smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pr
 
 // ---- abcdemc_swarm! (src/abcdez_mc.jl:5-61), one CTA per particle -------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, GkMath<T>::MIN_CTAS)
 gk_mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                    const __grid_constant__ SweepInj inj, const __grid_constant__ McArgs mc)
 {
@@ -760,7 +771,7 @@ gk_mc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pri
 
 // ---- one dist! evaluation per row (stage-level model parity) ------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, GkMath<T>::MIN_CTAS)
 gk_simulate_kernel(const __grid_constant__ ModelData md, int64_t N, const double* __restrict__ theta_pushed, const __grid_constant__ PhiloxKeys seed,
                    uint32_t epoch, uint32_t tag, uint32_t id0, double* __restrict__ dist)
 {
