@@ -1547,7 +1547,7 @@ static int mc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_
         for (int it = 0; it < o->generations; ++it) {                        // :134
             launches += launch_mc_prepare(st, pop->dev, pop->sorted_delta, pop->order, pop->sort_tmp, pop->sort_tmp_bytes, 0);
             pop->ops->mc_sweep(*pop->ops, st, pop->dev, pop->prior, pop->data, noinj, mc);   // :149
-            launches++;
+            launches += pop->ops->split ? 3 : 1;                                   // (heavy simulators: propose, simulate, accept)
         }
     }
     RUN_CU(cudaEventRecord(e1, st));

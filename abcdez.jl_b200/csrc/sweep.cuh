@@ -657,11 +657,11 @@ smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pri
 
 template <class M, bool DISC>
 __global__ void __launch_bounds__(SWEEP_THREADS)
-simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md)
+simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md, int smc)
 {
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
-    if (c->stop | c->sweeps_done) return;
+    if (smc && (c->stop | c->sweeps_done)) return;                         // (abcdemc!: a propose kernel that returned early left the queue empty)
     const unsigned heavy = __ldcg(&c->acc.queue_heavy), len = heavy + __ldcg(&c->acc.queue_len);
     const PhiloxKeys& seed = P.keys;
     const uint32_t epoch = c->sweep_epoch;
@@ -777,9 +777,173 @@ smc_accept_kernel(const __grid_constant__ PopDev P)
 }
 
 // ---------------------------------------------------------------------------------------
+// abcdemc_swarm! for heavy simulators, the same three launches (src/abcdez_mc.jl:5-61)
+// ---------------------------------------------------------------------------------------
+template <class M, bool DISC>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+mc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+                  const __grid_constant__ McArgs mc)
+{
+    constexpr int D = M::D, NB = M::BLOB / 8;
+    Ctrl* c = P.ctrl;
+    if (mc.from_ctrl && (c->stop | c->err)) return;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const uint32_t N = P.N;
+    const double* __restrict__ th = P.theta[cur];
+    const double eps_target = mc.from_ctrl ? c->eps_target : mc.eps_target;
+    const double eps_pop = mc.from_ctrl ? fmax(eps_target, c->dmin + 0.0 * (c->dmax - c->dmin)) : mc.eps_pop;   // :146-147, alpha = 0 (:107)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool queued = false, hvy = false;
+    if (i < N) {
+        double thp[D];
+        load_row<D>(th, i, thp);
+        const double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
+        if (P.moved[i]) {                                                  // repair the stale row in g+1
+            store_row<D>(P.theta[nxt], i, thp);
+            copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
+        }
+        const uint32_t pid = P.id0 + i;
+        const PhiloxKeys& seed = P.keys;
+        const uint32_t epoch = c->sweep_epoch;
+        int err = 0;
+        uint32_t s = i;                                                    // :18
+        const double eps = (dli <= eps_target) ? eps_target : eps_pop;     // :19
+        if (dli > eps) {                                                   // :20-24
+            uint32_t lo = 0, hi = N;
+            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (mc.sorted_delta[m] <= dli) lo = m + 1; else hi = m; }
+            Stream cs(seed, pid, epoch, TAG_MC);
+            double u1, u2; cs.u2(0u, u1, u2);
+            long long k = (long long)floor(u1 * (double)lo);
+            if (k >= (long long)lo) k = (long long)lo - 1;
+            s = mc.order[k];
+        }
+        uint32_t a, b;
+        {
+            Stream ps(seed, pid, epoch, TAG_PARTNER);
+            double u1, u2, ua, ub; uint32_t att = 1;
+            auto pick = [N](double u) { long long k = (long long)floor(u * (double)N); if (k >= (long long)N) k = (long long)N - 1; return (uint32_t)k; };
+            ps.u2(0u, ua, ub);
+            a = pick(ua);
+            while (a == s) {                                               // :25-28
+                if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                ps.u2(att++, u1, u2);
+                a = pick(u1);
+            }
+            att = 1;
+            b = pick(ub);
+            while (b == a || b == s) {                                     // :29-32
+                if (att >= (uint32_t)PARTNER_MAX_ATTEMPTS) { err = ABCDEZ_ERR_PARTNER_RETRY; break; }
+                ps.u2(att++, u1, u2);
+                b = pick(u2);
+            }
+        }
+        uint8_t flag = 0;
+        if (err) atomicMax(&c->acc.err, err);
+        else {
+            Stream ms(seed, pid, epoch, TAG_MOVE);
+            if (s != i) load_row<D>(th, s, thp);                           // base particle theta_s
+            double z, z2;
+            ms.n2(0u, z, z2);
+            const double g = c->gamma0 * (1.0 + z * c->gsig);              // :34
+            de_proposal<D>(th, a, b, g, thp);
+            double xs[DISC ? D : 1];
+            const double* x = thp;
+            if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
+            const double lp = prior_logpdf<D>(pr, x);                      // :41
+            const double w_prior = lp - lpi;                               // :42 (logpi[i], not [s])
+            double u, u2;
+            ms.u2(1u, u, u2);                                              // :43, always drawn
+            if (!(plog(u) > fmin(0.0, w_prior))) {                         // :44: simulate
+                store_row<D>(P.prop_theta, i, thp);
+                P.prop_lp[i] = lp;
+                flag = 1; queued = true;
+                if constexpr (model_has_heavy<M>::value) hvy = M::heavy(x, md.v);
+            }
+        }
+        P.prop_flag[i] = flag;
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mh = __ballot_sync(0xffffffffu, queued && hvy), ml = __ballot_sync(0xffffffffu, queued && !hvy);
+    if (mh) {
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(mh) - 1)) base = atomicAdd(&c->acc.queue_heavy, (unsigned)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
+        if (queued && hvy) P.queue[base + __popc(mh & ((1u << lane) - 1u))] = i;
+    }
+    if (ml) {
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(ml) - 1)) base = atomicAdd(&c->acc.queue_len, (unsigned)__popc(ml));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ml) - 1);
+        if (queued && !hvy) P.queue[N - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = i;
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+mc_accept_kernel(const __grid_constant__ PopDev P, const __grid_constant__ McArgs mc)
+{
+    constexpr int D = M::D, NB = M::BLOB / 8;
+    Ctrl* c = P.ctrl;
+    if (mc.from_ctrl && (c->stop | c->err)) return;
+    const int cur = c->cur, nxt = cur ^ 1;
+    const uint32_t N = P.N;
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
+    const double eps_target = mc.from_ctrl ? c->eps_target : mc.eps_target;
+    const double eps_pop = mc.from_ctrl ? fmax(eps_target, c->dmin + 0.0 * (c->dmax - c->dmin)) : mc.eps_pop;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nsim = 0, nacc = 0;
+    unsigned long long kdl = 0ull;
+    if (i < N) {
+        double dli = P.delta[cur][i];
+        const uint8_t mv = P.moved[i];
+        if (P.prop_flag[i]) {
+            nsim = 1;                                                      // :44
+            const double dp = P.prop_dp[i];
+            const double eps = (dli <= eps_target) ? eps_target : eps_pop; // :19
+            if (dp <= fmax(eps, dli)) {                                    // :54-59
+                double thp[D];
+                load_row<D>(P.prop_theta, i, thp);
+                store_row<D>(P.theta[nxt], i, thp);
+                P.logpi[nxt][i] = P.prop_lp[i];
+                P.delta[nxt][i] = dp;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) P.blob[nxt][(size_t)i * NB + k] = P.prop_blob[(size_t)i * NB + k];
+                dli = dp;
+                nacc = 1;
+            }
+        }
+        if ((uint8_t)nacc != mv) P.moved[i] = (uint8_t)nacc;
+        kdl = f64_key(dli);                                                // extrema(delta), :146
+    }
+    const bool last = sweep_finish<true>(c, &s_red, nsim, nacc, i < N ? kdl : ~0ull, i < N ? kdl : 0ull, 0);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, true);
+    if (last) {
+        c->acc.queue_len = 0u; c->acc.queue_next = 0u; c->acc.queue_heavy = 0u;
+        ctrl_after_mc_sweep(P, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // launchers + registry
 // ---------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t N, int threads) { return (unsigned)((N + threads - 1) / threads); }
+
+// persistent grid of the queue-driven simulate kernel: SMs x resident CTAs (per device), at most one thread per particle
+template <class M, bool DISC>
+static inline unsigned queue_grid(unsigned g)
+{
+    static int cached[64] = { 0 };
+    int dev = 0; cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (!cached[slot]) {
+        int sms = 148, per = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, simulate_queue_kernel<M, DISC>, SWEEP_THREADS, 0) != cudaSuccess || per < 1) per = 1;
+        cached[slot] = sms * per;
+    }
+    return g < (unsigned)cached[slot] ? g : (unsigned)cached[slot];
+}
 
 template <int D>
 static inline bool prior_has_discrete(const PriorDev& pr)
@@ -800,18 +964,7 @@ static void l_smc_split(cudaStream_t st, const PopDev& P, const PriorDev& pr, co
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     if (P.flags & POP_PARTNER_SEGMENTS) smc_propose_kernel<M, DISC, PK, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md);
     else smc_propose_kernel<M, DISC, PK, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md);
-    // persistent grid for the queue: SMs x resident CTAs (per device)
-    static int cached[64] = { 0 };
-    int dev = 0; cudaGetDevice(&dev);
-    const int slot = dev >= 0 && dev < 64 ? dev : 0;
-    if (!cached[slot]) {
-        int sms = 148, per = 1;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, simulate_queue_kernel<M, DISC>, SWEEP_THREADS, 0) != cudaSuccess || per < 1) per = 1;
-        cached[slot] = sms * per;
-    }
-    const unsigned gq = g < (unsigned)cached[slot] ? g : (unsigned)cached[slot];
-    simulate_queue_kernel<M, DISC><<<gq, SWEEP_THREADS, 0, st>>>(P, pr, md);
+    simulate_queue_kernel<M, DISC><<<queue_grid<M, DISC>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, 1);
     smc_accept_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P);
 }
 
@@ -846,6 +999,23 @@ template <class M>
 static void l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, const SweepInj& inj,
                  const McArgs& mc)
 {
+    if constexpr (model_is_split<M>::value) {
+        const bool injected = inj.a || inj.b || inj.s || inj.z || inj.u || inj.flags;
+#ifndef ABCDEZ_MC_FUSED_ONLY                                               // (A/B builds)
+        if (!injected && P.prop_theta) {                                   // heavy simulators: propose -> queue-driven simulate -> accept
+            const unsigned g = grid_for(P.N, SWEEP_THREADS);
+            if (prior_has_discrete<M::D>(pr)) {
+                mc_propose_kernel<M, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, mc);
+                simulate_queue_kernel<M, true><<<queue_grid<M, true>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, 0);
+            } else {
+                mc_propose_kernel<M, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, mc);
+                simulate_queue_kernel<M, false><<<queue_grid<M, false>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, 0);
+            }
+            mc_accept_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P, mc);
+            return;
+        }
+#endif
+    }
     if (prior_has_discrete<M::D>(pr))
         mc_sweep_kernel<M, true><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, inj, mc);
     else
