@@ -1221,7 +1221,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         host_iters = c->iters;
     } else {
         pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);     // :242-252
-        launches += 1 + launch_begin_run(st, pop->dev);                      // :255-292
+        launches += (pop->ops->split == 2 ? 3 : 1) + launch_begin_run(st, pop->dev);   // :255-292 (stepped simulators: draw, simulate, finish)
     }
     RUN_CU(cudaEventRecord(e_loop0, st));
     for (;;) {                                                               // :295
@@ -1536,7 +1536,7 @@ static int mc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez_
     rc = mc_prepare(pop); if (rc) goto done;
     RUN_CU(cudaEventCreate(&e0)); RUN_CU(cudaEventCreate(&e1));
     pop->ops->init(*pop->ops, st, pop->dev, pop->prior, pop->data, o->seed, 1);         // :117-125
-    launches++;
+    launches += pop->ops->split == 2 ? 3 : 1;
     RUN_CU(cudaEventRecord(e0, st));
     {
         // The generation loop (:134-161) is a fixed launch list: extrema(delta) of the live generation come from the

@@ -134,7 +134,7 @@ struct ModelOps {
     void (*simulate)(const ModelOps&, cudaStream_t, const PriorDev*, const ModelData&, int64_t N, const double* theta_pushed,
                      uint64_t seed, uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs);
     void* dyn;                    // runtime-compiled models: their loaded module (rtc.cu); nullptr for the static registry
-    int split;                    // 1: abcdesmc_swarm! runs as propose -> queue-driven simulate -> accept (3 launches per sweep)
+    int split;                    // 1: sweeps run as propose -> queue-driven simulate -> accept (3 launches per sweep); 2: abcde_init! too (stepped simulators)
 };
 const ModelOps* model_ops(int id);
 int model_count();

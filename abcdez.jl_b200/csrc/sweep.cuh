@@ -655,16 +655,22 @@ smc_propose_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Pri
     }
 }
 
+enum { QUEUE_MC = 0, QUEUE_SMC = 1, QUEUE_INIT = 2 };
+
 template <class M, bool DISC>
 __global__ void __launch_bounds__(SWEEP_THREADS)
-simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md, int smc)
+simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md, int mode,
+                      const __grid_constant__ PhiloxKeys init_keys)
 {
+    // mode: QUEUE_SMC abcdesmc_swarm!, QUEUE_MC abcdemc_swarm! (a propose kernel that returned early left the queue empty),
+    //       QUEUE_INIT abcde_init! (streams of the init kernel: run seed, epoch 0 = first attempt, TAG_INIT_MODEL)
     constexpr int D = M::D, NB = M::BLOB / 8;
     Ctrl* c = P.ctrl;
-    if (smc && (c->stop | c->sweeps_done)) return;                         // (abcdemc!: a propose kernel that returned early left the queue empty)
+    if (mode == QUEUE_SMC && (c->stop | c->sweeps_done)) return;
     const unsigned heavy = __ldcg(&c->acc.queue_heavy), len = heavy + __ldcg(&c->acc.queue_len);
-    const PhiloxKeys& seed = P.keys;
-    const uint32_t epoch = c->sweep_epoch;
+    const PhiloxKeys& seed = mode == QUEUE_INIT ? init_keys : P.keys;
+    const uint32_t epoch = mode == QUEUE_INIT ? 0u : c->sweep_epoch;
+    const uint32_t TAG_SIM = mode == QUEUE_INIT ? (uint32_t)TAG_INIT_MODEL : (uint32_t)TAG_MODEL;
     if constexpr (!model_is_stepped<M>::value) {
         // equal-length simulations: a static stride over the queue keeps every warp dense
         for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < len; q += gridDim.x * blockDim.x) {
@@ -673,7 +679,7 @@ simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ 
             load_row<D>(P.prop_theta, i, thp);
             const double* x = thp;
             if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
-            SimRng r(seed, P.id0 + i, epoch, TAG_MODEL);
+            SimRng r(seed, P.id0 + i, epoch, TAG_SIM);
             P.prop_dp[i] = M::run(x, md.v, r, blp);                        // :137
 #pragma unroll
             for (int k = 0; k < NB; ++k) P.prop_blob[(size_t)i * NB + k] = blp[k];
@@ -681,7 +687,7 @@ simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ 
     } else {
         // STEPPED simulators: one merged loop per lane -- fetch the next pending simulation, or advance mine by one step
         typename M::State st;
-        SimRng r(seed, 0u, epoch, TAG_MODEL);
+        SimRng r(seed, 0u, epoch, TAG_SIM);
         uint32_t i = 0;
         bool have = false, drained = false;
         const unsigned lane = threadIdx.x & 31;
@@ -699,7 +705,7 @@ simulate_queue_kernel(const __grid_constant__ PopDev P, const __grid_constant__ 
                         load_row<D>(P.prop_theta, i, thp);
                         const double* x = thp;
                         if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
-                        r = SimRng(seed, P.id0 + i, epoch, TAG_MODEL);
+                        r = SimRng(seed, P.id0 + i, epoch, TAG_SIM);
                         M::begin(st, x, md.v);
                         have = true;
                     } else drained = true;
@@ -773,6 +779,111 @@ smc_accept_kernel(const __grid_constant__ PopDev P)
     if (last) {
         c->acc.queue_len = 0u; c->acc.queue_next = 0u; c->acc.queue_heavy = 0u;   // the next sweep's queue
         ctrl_after_smc_sweep(P, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// abcde_init! for STEPPED simulators (src/abcdez_init.jl:2-22): the first simulation of every particle through the queue
+// ---------------------------------------------------------------------------------------
+// (equal-length simulators keep the fused init_kernel: their warps are dense anyway.)  draw -> queue-driven simulate ->
+// finish; the redraw loop of init.jl:14-20 (non-finite distance or log prior) stays in the finish kernel, fused, for the few
+// particles that need it.  Same streams as init_kernel: bit-identical populations.
+template <class M>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+init_draw_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+                 const __grid_constant__ PhiloxKeys seed, int draw_prior)
+{
+    constexpr int D = M::D;
+    Ctrl* c = P.ctrl;
+    const int cur = c->cur;
+    const uint32_t N = P.N;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool queued = false, hvy = false;
+    if (i < N) {
+        double th[D], x[D];
+        double lp;
+        if (draw_prior) {                                  // src/abcdez_smc.jl:242-243
+            prior_sample<D>(pr, seed, P.id0 + i, 0u, th);
+            push_p<D>(pr, th, x);
+            lp = prior_logpdf<D>(pr, x);
+            store_row<D>(P.theta[cur], i, th);
+            P.logpi[cur][i] = lp;
+        } else {
+            load_row<D>(P.theta[cur], i, th);
+            push_p<D>(pr, th, x);
+            lp = P.logpi[cur][i];
+        }
+        if (isfinite(lp)) {                                // init.jl:9-13
+            store_row<D>(P.prop_theta, i, th);
+            queued = true;
+            if constexpr (model_has_heavy<M>::value) hvy = M::heavy(x, md.v);
+        }
+        P.prop_flag[i] = queued ? 1 : 0;
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mh = __ballot_sync(0xffffffffu, queued && hvy), ml = __ballot_sync(0xffffffffu, queued && !hvy);
+    if (mh) {
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(mh) - 1)) base = atomicAdd(&c->acc.queue_heavy, (unsigned)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mh) - 1);
+        if (queued && hvy) P.queue[base + __popc(mh & ((1u << lane) - 1u))] = i;
+    }
+    if (ml) {
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(ml) - 1)) base = atomicAdd(&c->acc.queue_len, (unsigned)__popc(ml));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ml) - 1);
+        if (queued && !hvy) P.queue[N - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = i;
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
+init_finish_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
+                   const __grid_constant__ PhiloxKeys seed)
+{
+    constexpr int D = M::D, NB = M::BLOB / 8;
+    Ctrl* c = P.ctrl;
+    const int cur = c->cur;
+    __shared__ SweepSmem s_red;
+    sweep_smem_init(&s_red);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned redraws = 0; int err = 0;
+    unsigned long long kdl = 0ull;
+    if (i < P.N) {
+        const uint32_t pid = P.id0 + i;
+        double blob[NB > 0 ? NB : 1];
+        double lp = P.logpi[cur][i];
+        double dl = NAN;
+        if (P.prop_flag[i]) {
+            dl = P.prop_dp[i];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) blob[k] = P.prop_blob[(size_t)i * NB + k];
+        }
+        uint32_t attempt = 0;
+        while (!isfinite(dl) || !isfinite(lp)) {           // init.jl:14-20
+            if (++attempt >= (uint32_t)INIT_MAX_ATTEMPTS) { err = ABCDEZ_ERR_INIT_RETRY; break; }
+            double th[D], x[D];
+            prior_sample<D>(pr, seed, pid, attempt, th);
+            push_p<D>(pr, th, x);
+            lp = prior_logpdf<D>(pr, x);
+            SimRng r(seed, pid, attempt, TAG_INIT_MODEL);
+            dl = M::run(x, md.v, r, blob);
+            redraws++;
+            store_row<D>(P.theta[cur], i, th);
+            P.logpi[cur][i] = lp;
+        }
+        P.delta[cur][i] = dl;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) P.blob[cur][(size_t)i * NB + k] = blob[k];
+        P.moved[i] = 1;                                    // the other buffer is stale
+        kdl = f64_key(dl);
+    }
+    const bool last = sweep_finish<true>(c, &s_red, redraws, 0u, i < P.N ? kdl : ~0ull, i < P.N ? kdl : 0ull, err);
+    if (P.x.world > 1 && __shfl_sync(0xffffffffu, (int)last, 0)) sweep_exchange_warp(P, c, true);   // global extrema, redraws, errors
+    if (last) {
+        c->acc.queue_len = 0u; c->acc.queue_next = 0u; c->acc.queue_heavy = 0u;
+        if (P.x.world == 1) sweep_collect(c, true);
+        c->redraws += (long long)c->last_nsims;
     }
 }
 
@@ -956,6 +1067,17 @@ static inline bool prior_has_discrete(const PriorDev& pr)
 template <class M>
 static void l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
+    if constexpr (model_is_split<M>::value && model_is_stepped<M>::value) {
+        if (P.prop_theta) {
+            const unsigned g = grid_for(P.N, SWEEP_THREADS);
+            const PhiloxKeys keys = philox_keys(seed);
+            init_draw_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, keys, dp);
+            if (prior_has_discrete<M::D>(pr)) simulate_queue_kernel<M, true><<<queue_grid<M, true>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, QUEUE_INIT, keys);
+            else simulate_queue_kernel<M, false><<<queue_grid<M, false>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, QUEUE_INIT, keys);
+            init_finish_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, keys);
+            return;
+        }
+    }
     init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, philox_keys(seed), dp);
 }
 template <class M, bool DISC, int PK>
@@ -964,7 +1086,7 @@ static void l_smc_split(cudaStream_t st, const PopDev& P, const PriorDev& pr, co
     const unsigned g = grid_for(P.N, SWEEP_THREADS);
     if (P.flags & POP_PARTNER_SEGMENTS) smc_propose_kernel<M, DISC, PK, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md);
     else smc_propose_kernel<M, DISC, PK, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md);
-    simulate_queue_kernel<M, DISC><<<queue_grid<M, DISC>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, 1);
+    simulate_queue_kernel<M, DISC><<<queue_grid<M, DISC>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, QUEUE_SMC, P.keys);
     smc_accept_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P);
 }
 
@@ -1006,10 +1128,10 @@ static void l_mc(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorD
             const unsigned g = grid_for(P.N, SWEEP_THREADS);
             if (prior_has_discrete<M::D>(pr)) {
                 mc_propose_kernel<M, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, mc);
-                simulate_queue_kernel<M, true><<<queue_grid<M, true>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, 0);
+                simulate_queue_kernel<M, true><<<queue_grid<M, true>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, QUEUE_MC, P.keys);
             } else {
                 mc_propose_kernel<M, false><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, mc);
-                simulate_queue_kernel<M, false><<<queue_grid<M, false>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, 0);
+                simulate_queue_kernel<M, false><<<queue_grid<M, false>(g), SWEEP_THREADS, 0, st>>>(P, pr, md, QUEUE_MC, P.keys);
             }
             mc_accept_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P, mc);
             return;
@@ -1033,7 +1155,7 @@ static ModelOps make_ops()
 {
     ModelOps o;
     o.name = M::name; o.d = M::D; o.blob = M::BLOB;
-    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr; o.split = model_is_split<M>::value ? 1 : 0;
+    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr; o.split = model_is_split<M>::value ? (model_is_stepped<M>::value ? 2 : 1) : 0;
     return o;
 }
 

@@ -114,6 +114,19 @@ def _():
         assert got.nsims == want.nsims and np.allclose(got.C, want.C, rtol=1e-12)
 
 
+@case("queue-driven sweeps of heavy simulators: init / abcdesmc! / abcdemc! of birth-death (stepped) and Lotka-Volterra")
+def _():
+    bd = ([("uniform", 0.0, 2.0)] * 2, "birth_death", [20.0, 8, 0.5, 5000.0, 22, 25, 24, 30, 33, 31, 36, 40])
+    lv = ([("uniform", 0.0, 2.0)] * 4, "lotka_volterra", [1.0, 0.5, 0.01, 50, 8, 0.05] + list(np.tile([1.2, 0.6], 8)))
+    for (spec, name, data), eps in ((bd, 5.0), (lv, 0.6)):
+        want = O.smc_run(spec, name, data, eps, nparticles=700, seed=9, nsims_max=20000)
+        got = A.abcdesmc(prior_of(spec), A.Model(name, data), eps, None, nparticles=700, rng=9, nsims_max=20000, verbose=False)
+        assert (got.iters, got.nsims) == (want.iters, want.nsims), name
+        wm = O.mc_run(spec, name, data, eps, nparticles=400, generations=5, seed=10)
+        gm = A.abcdemc(prior_of(spec), A.Model(name, data), eps, None, nparticles=400, generations=5, rng=10, verbose=False)
+        assert gm.nsims == wm.nsims and np.array_equal(gm.C, wm.C), name
+
+
 @case("g-and-k CTA-cooperative simulator (FP64 and FP32), multi-select")
 def _():
     data = [1000.0, 2.39384, 2.569082, 2.748052, 3.0, 3.4169, 4.196232, 5.900654]
