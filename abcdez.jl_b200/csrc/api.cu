@@ -982,7 +982,7 @@ extern "C" void abcdez_smc_opts_default(abcdez_smc_opts* o)
     o->nparticles = 100; o->alpha = 0.95; o->delta_ess = 0.5; o->nsims_max = 10000000; o->Kmcmc = 3;
     o->Kmcmc_min = 1.0; o->kernel = ABCDEZ_INDICATOR_STRICT; o->facc_stop = 0.0; o->facc_min = 0.0;
     o->facc_tune = 0.975; o->seed = 1; o->verboseout = 1; o->max_iters = 0; o->exact_scan = 0; o->profile = 0;
-    o->sync_every = 1; o->fused_head = 1; o->systematic_resampling = 0; o->partner_segments = 0;
+    o->sync_every = 1; o->fused_head = 1; o->systematic_resampling = 0; o->partner_segments = 0; o->fp32_state = 0;
 }
 
 // ---- run state snapshots (the reference has no equivalent) -------------------------------
@@ -1105,6 +1105,10 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
     CHECK_ARG(0.0 <= o->Kmcmc_min, "Kmcmc_min must be in 0 <= Kmcmc_min <= Inf");
     CHECK_ARG(1 <= o->nsims_max, "nsims_max must be at least 1");
     CHECK_ARG(o->kernel >= 0 && o->kernel <= 3, "unknown ABC kernel");
+    if (o->fp32_state) {
+        if (!model->ops->f32_state) return fail(ABCDEZ_ERR_UNSUPPORTED, std::string("fp32_state: model '") + model->ops->name + "' keeps FP64 particle state in this build (g-and-k and runtime-compiled models)");
+        if (state_in || state_out) return fail(ABCDEZ_ERR_UNSUPPORTED, "fp32_state: run-state snapshots hold FP64 particle state");
+    }
     {
         double mn = o->alpha < o->delta_ess ? o->alpha : o->delta_ess;
         double nmin = ceil(3.0 * (double)prior->dev.d / mn);                 // :234
@@ -1186,7 +1190,7 @@ static int smc_run_impl(abcdez_ctx* ctx, const abcdez_prior* prior, const abcdez
         if (no_alive) c->status = ABCDEZ_ERR_NO_ALIVE;
     }
     pop->dev.keys = philox_keys(c->seed);
-    pop->dev.flags = (o->partner_segments ? POP_PARTNER_SEGMENTS : 0u) | (o->systematic_resampling ? POP_SYSTEMATIC : 0u);
+    pop->dev.flags = (o->partner_segments ? POP_PARTNER_SEGMENTS : 0u) | (o->systematic_resampling ? POP_SYSTEMATIC : 0u) | (o->fp32_state ? POP_FP32_STATE : 0u);
     rc = push_ctrl(pop);
     std::vector<cudaEvent_t>& evs = ctx->ev_pool;
     size_t nev = 0;

@@ -357,12 +357,25 @@ __device__ __forceinline__ double stratum_draw(const SeqTab* edges, double sval,
     return unif0 + (unif1 - unif0) * u;
 }
 
+// one theta row from generation to generation (or from a peer's HBM); f32: the rows are floats (POP_FP32_STATE)
+__device__ __forceinline__ void copy_theta_row(const double* __restrict__ sb, double* __restrict__ db, size_t src, size_t dst, int DS, bool f32)
+{
+    if (f32) {
+        const float* s = reinterpret_cast<const float*>(sb) + src * DS;
+        float* d = reinterpret_cast<float*>(db) + dst * DS;
+        if (DS & 1) { for (int k = 0; k < DS; ++k) d[k] = s[k]; }
+        else { for (int k = 0; k < DS; k += 2) *reinterpret_cast<float2*>(d + k) = *reinterpret_cast<const float2*>(s + k); }
+    } else {
+        const double* s = sb + src * DS;
+        double* d = db + dst * DS;
+        if (DS & 1) { for (int k = 0; k < DS; ++k) d[k] = s[k]; }
+        else { for (int k = 0; k < DS; k += 2) *reinterpret_cast<double2*>(d + k) = *reinterpret_cast<const double2*>(s + k); }
+    }
+}
+
 __device__ __forceinline__ void gather_particle(const PopDev& P, int cur, int DS, int NB, uint32_t dst, uint32_t src)
 {
-    const double* s = P.theta[cur] + (size_t)src * DS;
-    double* d = P.theta[cur ^ 1] + (size_t)dst * DS;
-    if (DS & 1) { for (int k = 0; k < DS; ++k) d[k] = s[k]; }
-    else { for (int k = 0; k < DS; k += 2) *reinterpret_cast<double2*>(d + k) = *reinterpret_cast<const double2*>(s + k); }
+    copy_theta_row(P.theta[cur], P.theta[cur ^ 1], src, dst, DS, (P.flags & POP_FP32_STATE) != 0);
     P.logpi[cur ^ 1][dst] = P.logpi[cur][src];
     P.delta[cur ^ 1][dst] = P.delta[cur][src];
     for (int k = 0; k < NB; ++k) P.blob[cur ^ 1][(size_t)dst * NB + k] = P.blob[cur][(size_t)src * NB + k];
@@ -455,10 +468,7 @@ resample_uniform_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
         }
         const PeerPop& pp = P.peers->p[q];
         {
-            const double* s = pp.theta[cur] + (size_t)src * DS;
-            double* d = P.theta[cur ^ 1] + (size_t)si * DS;
-            if (DS & 1) { for (int e = 0; e < DS; ++e) d[e] = s[e]; }
-            else { for (int e = 0; e < DS; e += 2) *reinterpret_cast<double2*>(d + e) = *reinterpret_cast<const double2*>(s + e); }
+            copy_theta_row(pp.theta[cur], P.theta[cur ^ 1], src, si, DS, (P.flags & POP_FP32_STATE) != 0);
             P.logpi[cur ^ 1][si] = pp.logpi[cur][src];
             P.delta[cur ^ 1][si] = pp.delta[cur][src];
             for (int e = 0; e < NB; ++e) P.blob[cur ^ 1][(size_t)si * NB + e] = pp.blob[cur][(size_t)src * NB + e];
@@ -573,10 +583,7 @@ resample_general_sharded_kernel(const __grid_constant__ PopDev P, int DS, int NB
         }
         const PeerPop& pp = P.peers->p[q];
         {
-            const double* s = pp.theta[cur] + (size_t)src * DS;
-            double* d = P.theta[cur ^ 1] + (size_t)si * DS;
-            if (DS & 1) { for (int e = 0; e < DS; ++e) d[e] = s[e]; }
-            else { for (int e = 0; e < DS; e += 2) *reinterpret_cast<double2*>(d + e) = *reinterpret_cast<const double2*>(s + e); }
+            copy_theta_row(pp.theta[cur], P.theta[cur ^ 1], src, si, DS, (P.flags & POP_FP32_STATE) != 0);
             P.logpi[cur ^ 1][si] = pp.logpi[cur][src];
             P.delta[cur ^ 1][si] = pp.delta[cur][src];
             for (int e = 0; e < NB; ++e) P.blob[cur ^ 1][(size_t)si * NB + e] = pp.blob[cur][(size_t)src * NB + e];
@@ -903,7 +910,8 @@ __global__ void push_rows_kernel(PopDev P, PriorDev pr, int D, int DS, double* _
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)P.N * D) return;
     int64_t i = e / D; int k = (int)(e - i * D);
-    double v = P.theta[P.ctrl->cur][i * DS + k];
+    const double* th = P.theta[P.ctrl->cur];
+    double v = (P.flags & POP_FP32_STATE) ? (double)reinterpret_cast<const float*>(th)[i * DS + k] : th[i * DS + k];
     out[e] = fam_is_discrete(pr.family[k]) ? rint(v) : v;
 }
 

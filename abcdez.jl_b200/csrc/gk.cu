@@ -837,12 +837,12 @@ static void gk_l_sim(const ModelOps&, cudaStream_t st, const PriorDev*, const Mo
 
 const ModelOps* ops_gk()
 {
-    static const ModelOps o = { GkMath<double>::name, 4, 0, &gk_l_init<double>, &gk_l_smc<double>, &gk_l_mc<double>, &gk_l_sim<double>, nullptr, 0 };
+    static const ModelOps o = { GkMath<double>::name, 4, 0, &gk_l_init<double>, &gk_l_smc<double>, &gk_l_mc<double>, &gk_l_sim<double>, nullptr, 0, 0 };
     return &o;
 }
 const ModelOps* ops_gk_f32()
 {
-    static const ModelOps o = { GkMath<float>::name, 4, 0, &gk_l_init<float>, &gk_l_smc<float>, &gk_l_mc<float>, &gk_l_sim<float>, nullptr, 0 };
+    static const ModelOps o = { GkMath<float>::name, 4, 0, &gk_l_init<float>, &gk_l_smc<float>, &gk_l_mc<float>, &gk_l_sim<float>, nullptr, 0, 0 };
     return &o;
 }
 

@@ -105,7 +105,7 @@ struct PopDev {
     uint8_t* prop_flag;           // N: 1 = in the queue
     uint32_t* queue;              // particle indices whose proposal must be simulated
 };
-enum : uint32_t { POP_PARTNER_SEGMENTS = 1u, POP_SYSTEMATIC = 2u };
+enum : uint32_t { POP_PARTNER_SEGMENTS = 1u, POP_SYSTEMATIC = 2u, POP_FP32_STATE = 4u };   // relaxed-parity modes
 
 struct SweepInj {
     const int32_t* a; const int32_t* b; const int32_t* s;
@@ -134,6 +134,7 @@ struct ModelOps {
     void (*simulate)(const ModelOps&, cudaStream_t, const PriorDev*, const ModelData&, int64_t N, const double* theta_pushed,
                      uint64_t seed, uint32_t epoch, uint32_t tag, uint32_t id0, double* dist, double* blobs);
     void* dyn;                    // runtime-compiled models: their loaded module (rtc.cu); nullptr for the static registry
+    int f32_state;                // 1: init / abcdesmc_swarm! launchers honour POP_FP32_STATE (templated kernels of the static registry)
     int split;                    // 1: sweeps run as propose -> queue-driven simulate -> accept (3 launches per sweep); 2: abcde_init! too (stepped simulators)
 };
 const ModelOps* model_ops(int id);

@@ -210,7 +210,7 @@ int rtc_compile_model(const char* name, const char* struct_name, const char* cud
         if (cr) { *log = "cuModuleGetFunction failed for " + kexpr[k]; delete m; return ABCDEZ_ERR_CUDA; }
     }
     m->ops.name = m->name.c_str(); m->ops.d = d; m->ops.blob = blob_bytes;
-    m->ops.init = &dyn_init; m->ops.smc_sweep = &dyn_smc; m->ops.mc_sweep = &dyn_mc; m->ops.simulate = &dyn_sim; m->ops.dyn = m; m->ops.split = 0;
+    m->ops.init = &dyn_init; m->ops.smc_sweep = &dyn_smc; m->ops.mc_sweep = &dyn_mc; m->ops.simulate = &dyn_sim; m->ops.dyn = m; m->ops.f32_state = 0; m->ops.split = 0;
     std::lock_guard<std::mutex> lk(g_dyn_mu);
     g_dyn.push_back(m);
     *id = M_COUNT + (int)g_dyn.size() - 1;

@@ -175,7 +175,7 @@ __device__ __forceinline__ void copy_scalars(const PopDev& P, int cur, int nxt, 
 // ---------------------------------------------------------------------------------------
 // abcde_init!  src/abcdez_init.jl:2-22
 // ---------------------------------------------------------------------------------------
-template <class M>
+template <class M, bool F32 = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
             const __grid_constant__ PhiloxKeys seed, int draw_prior)
@@ -194,10 +194,11 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
         double lp;
         if (draw_prior) {                                  // src/abcdez_smc.jl:242-243
             prior_sample<D>(pr, seed, pid, 0u, th);
+            round_row_f32<D>(th, F32);
             push_p<D>(pr, th, x);
             lp = prior_logpdf<D>(pr, x);
         } else {
-            load_row<D>(P.theta[cur], i, th);
+            load_row<D>(P.theta[cur], i, th, F32);
             lp = P.logpi[cur][i];
         }
         double dl = NAN;
@@ -210,13 +211,14 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
         while (!isfinite(dl) || !isfinite(lp)) {           // init.jl:14-20
             if (++attempt >= (uint32_t)INIT_MAX_ATTEMPTS) { err = ABCDEZ_ERR_INIT_RETRY; break; }
             prior_sample<D>(pr, seed, pid, attempt, th);
+            round_row_f32<D>(th, F32);
             push_p<D>(pr, th, x);
             lp = prior_logpdf<D>(pr, x);
             SimRng r(seed, pid, attempt, TAG_INIT_MODEL);
             dl = M::run(x, md.v, r, blob);
             redraws++;
         }
-        store_row<D>(P.theta[cur], i, th);
+        store_row<D>(P.theta[cur], i, th, F32);
         P.logpi[cur][i] = lp;
         P.delta[cur][i] = dl;
 #pragma unroll
@@ -250,7 +252,7 @@ init_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev p
 // roofline, profiles/README.md).  Every particle's partners are still uniform over the alive set and distinct from
 // it and from each other (a lane whose segment entries collide redraws individually); only their joint law across
 // the lanes of a warp differs from the reference's independent draws -- the Jacobi update does not care.
-template <class M, bool DISC, int PK, bool INJ = true, bool SEG = false>
+template <class M, bool DISC, int PK, bool INJ = true, bool SEG = false, bool F32 = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS)
 smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ PriorDev pr, const __grid_constant__ ModelData md,
                  const __grid_constant__ SweepInj inj)
@@ -281,8 +283,8 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
         if (j >= n_alive) {                                                // dead particle (:114)
             if (mv) {                                                      // repair its stale row, once
                 double row[D];
-                load_row<D>(th, i, row);
-                store_row<D>(P.theta[nxt], i, row);
+                load_row<D>(th, i, row, F32);
+                store_row<D>(P.theta[nxt], i, row, F32);
                 copy_scalars<NB>(P, cur, nxt, i, P.logpi[cur][i], P.delta[cur][i]);
                 P.moved[i] = 0;
             }
@@ -335,14 +337,14 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
             const double g = gamma0 * (1.0 + z * gsig);                    // :128
             // (3) own state; repair the stale row in g+1
             double thp[D];
-            load_row<D>(th, i, thp);
+            load_row<D>(th, i, thp, F32);
             const double lpi = P.logpi[cur][i], dli = P.delta[cur][i];
             if (mv) {
-                store_row<D>(P.theta[nxt], i, thp);
+                store_row<D>(P.theta[nxt], i, thp, F32);
                 copy_scalars<NB>(P, cur, nxt, i, lpi, dli);
             }
             if (!err) {
-                de_proposal<D>(th, a, b, g, thp);                          // :128
+                de_proposal<D>(th, a, b, g, thp, F32);                     // :128 (F32: rounded to the float row that is stored)
                 double xs[DISC ? D : 1];
                 const double* x = thp;
                 if (DISC) { push_p<D>(pr, thp, xs); x = xs; }
@@ -361,7 +363,7 @@ smc_sweep_kernel(const __grid_constant__ PopDev P, const __grid_constant__ Prior
                         else { ms.u2(1u, u, u2); acc = ((u == 0.0 ? -INFINITY : plog_unit(u)) < w); }   // u in [0, 1)
                     }
                     if (acc) {                                             // :146-150
-                        store_row<D>(P.theta[nxt], i, thp);
+                        store_row<D>(P.theta[nxt], i, thp, F32);
                         P.logpi[nxt][i] = lp;
                         P.delta[nxt][i] = dp;
 #pragma unroll
@@ -1068,7 +1070,7 @@ template <class M>
 static void l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md, uint64_t seed, int dp)
 {
     if constexpr (model_is_split<M>::value && model_is_stepped<M>::value) {
-        if (P.prop_theta) {
+        if (P.prop_theta && !(P.flags & POP_FP32_STATE)) {
             const unsigned g = grid_for(P.N, SWEEP_THREADS);
             const PhiloxKeys keys = philox_keys(seed);
             init_draw_kernel<M><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, keys, dp);
@@ -1078,7 +1080,8 @@ static void l_init(const ModelOps&, cudaStream_t st, const PopDev& P, const Prio
             return;
         }
     }
-    init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, philox_keys(seed), dp);
+    if (P.flags & POP_FP32_STATE) init_kernel<M, true><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, philox_keys(seed), dp);
+    else init_kernel<M><<<grid_for(P.N, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(P, pr, md, philox_keys(seed), dp);
 }
 template <class M, bool DISC, int PK>
 static void l_smc_split(cudaStream_t st, const PopDev& P, const PriorDev& pr, const ModelData& md)
@@ -1099,12 +1102,19 @@ static void l_smc(const ModelOps&, cudaStream_t st, const PopDev& P, const Prior
     const bool injected = inj.a || inj.b || inj.s || inj.z || inj.u || inj.flags;
     if constexpr (model_is_split<M>::value) {
         // heavy simulators: queue-driven sweep (three launches, same results); stage calls with injected randomness keep the fused kernel
-        if (!injected && P.prop_theta) {
+        if (!injected && P.prop_theta && !(P.flags & POP_FP32_STATE)) {
             if (prior_has_discrete<M::D>(pr)) l_smc_split<M, true, PK_GENERIC>(st, P, pr, md);
             else if (all_uniform) l_smc_split<M, false, PK_UNIFORM>(st, P, pr, md);
             else l_smc_split<M, false, PK_GENERIC>(st, P, pr, md);
             return;
         }
+    }
+    if (P.flags & POP_FP32_STATE) {                                        // relaxed mode: float theta rows (fused kernel, production launches)
+        if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC, false, false, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else if (all_normal) smc_sweep_kernel<M, false, PK_NORMAL, false, false, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else if (all_uniform) smc_sweep_kernel<M, false, PK_UNIFORM, false, false, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        else smc_sweep_kernel<M, false, PK_GENERIC, false, false, true><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
+        return;
     }
     if (prior_has_discrete<M::D>(pr)) smc_sweep_kernel<M, true, PK_GENERIC><<<g, SWEEP_THREADS, 0, st>>>(P, pr, md, inj);
     else if (all_normal) {
@@ -1155,7 +1165,7 @@ static ModelOps make_ops()
 {
     ModelOps o;
     o.name = M::name; o.d = M::D; o.blob = M::BLOB;
-    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr; o.split = model_is_split<M>::value ? (model_is_stepped<M>::value ? 2 : 1) : 0;
+    o.init = &l_init<M>; o.smc_sweep = &l_smc<M>; o.mc_sweep = &l_mc<M>; o.simulate = &l_sim<M>; o.dyn = nullptr; o.f32_state = 1; o.split = model_is_split<M>::value ? (model_is_stepped<M>::value ? 2 : 1) : 0;
     return o;
 }
 

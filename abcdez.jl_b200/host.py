@@ -44,7 +44,7 @@ class _SmcOpts(C.Structure):
                 ("facc_tune", C.c_double), ("seed", C.c_uint64), ("verboseout", C.c_int32),
                 ("max_iters", C.c_int32), ("exact_scan", C.c_int32), ("profile", C.c_int32),
                 ("sync_every", C.c_int32), ("fused_head", C.c_int32), ("systematic_resampling", C.c_int32),
-                ("partner_segments", C.c_int32)]
+                ("partner_segments", C.c_int32), ("fp32_state", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class _SmcResult(C.Structure):
@@ -560,7 +560,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
              facc_min=0.0, facc_tune=0.975, verbose: bool = True, verboseout: bool = True, rng=None,
              parallel: bool = False, ctx: Optional[Context] = None, max_iters: int = 0, exact_scan: bool = False,
              profile: bool = False, sync_every: int = 1, hist_cap: int = 8192, fused_head: bool = True,
-             state=None, return_state: bool = False, systematic_resampling: bool = False, partner_segments: bool = False,
+             state=None, return_state: bool = False, systematic_resampling: bool = False, partner_segments: bool = False, fp32_state: bool = False,
              **greek) -> SMCResult:
     """`abcdesmc!(prior, dist!, ϵ_target, varexternal; kwargs...)`, src/abcdez_smc.jl:215-394.
 
@@ -595,6 +595,7 @@ def abcdesmc(prior, dist, eps_target, varexternal=None, *, nparticles: int = 100
     o.exact_scan = int(exact_scan); o.profile = int(profile); o.sync_every = int(sync_every)
     o.fused_head = int(fused_head)
     o.systematic_resampling = int(systematic_resampling); o.partner_segments = int(partner_segments)   # relaxed-parity modes
+    o.fp32_state = int(fp32_state)
     Np = max(N, 1)
     P = np.empty((Np, d)); W = np.empty(Np); Cc = np.empty(Np); bl = np.zeros((Np, max(B, 1)), dtype=np.uint8)
     h = {k: np.zeros(hist_cap) for k in ("eps", "dmin", "dmax", "logZ", "ess", "facc", "gamma0")}

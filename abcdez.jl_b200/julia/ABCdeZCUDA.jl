@@ -191,6 +191,7 @@ mutable struct SmcOpts
     Kmcmc_min::Cdouble; kernel::Int32; facc_stop::Cdouble; facc_min::Cdouble; facc_tune::Cdouble
     seed::UInt64; verboseout::Int32; max_iters::Int32; exact_scan::Int32; profile::Int32; sync_every::Int32
     fused_head::Int32; systematic_resampling::Int32; partner_segments::Int32
+    fp32_state::Int32; reserved1::Int32
     SmcOpts() = new()
 end
 
@@ -236,7 +237,7 @@ Same positional arguments, keyword names and defaults as the reference (src/abcd
 `dist!` is a `DeviceModel`; `varexternal` is accepted and ignored (device functors keep their scratch
 in registers); `parallel=true` runs the population sharded over every GPU of the process (`MultiContext`), the
 counterpart of the reference's `ThreadedEx()` (src/abcdez_smc.jl:237).  Not in the reference: `max_iters`, `state`,
-`return_state` (run-state snapshots) and the relaxed-parity modes `systematic_resampling`, `partner_segments`.
+`return_state` (run-state snapshots) and the relaxed-parity modes `systematic_resampling`, `partner_segments`, `fp32_state`.
 """
 function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
                    nparticles::Int=100, α=0.95, δess=0.5, nsims_max::Int=10^7, Kmcmc::Int=3, Kmcmc_min=1.0,
@@ -244,7 +245,7 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
                    verbose::Bool=true, verboseout::Bool=true, rng=Random.default_rng(), parallel::Bool=false,
                    ctx::Context=run_context(parallel), hist_cap::Int=8192,
                    max_iters::Int=0, state::Union{Nothing,Vector{UInt8}}=nothing, return_state::Bool=false,
-                   systematic_resampling::Bool=false, partner_segments::Bool=false)
+                   systematic_resampling::Bool=false, partner_segments::Bool=false, fp32_state::Bool=false)
     # max_iters / state / return_state are not in the reference: run-state snapshots (abcdez_smc_run_state); the
     # returned NamedTuple gains a `state` field when return_state=true
     Kmcmc_min > facc_min || @warn("Kmcmc_min should be larger than facc_min")         # src/abcdez_smc.jl:232
@@ -255,7 +256,7 @@ function abcdesmc!(prior, dist!::DeviceModel, ϵ_target, varexternal;
     o.nparticles = nparticles; o.alpha = α; o.delta_ess = δess; o.nsims_max = nsims_max; o.Kmcmc = Kmcmc
     o.Kmcmc_min = Kmcmc_min; o.kernel = kernel_kind(ABCk); o.facc_stop = facc_stop; o.facc_min = facc_min
     o.facc_tune = facc_tune; o.seed = seed_from(rng); o.verboseout = verboseout || verbose; o.max_iters = max_iters
-    o.systematic_resampling = systematic_resampling; o.partner_segments = partner_segments
+    o.systematic_resampling = systematic_resampling; o.partner_segments = partner_segments; o.fp32_state = fp32_state
     verbose && @info("Preparing abcde in smc mode", nparticles, α, δess, parallel)       # src/abcdez_smc.jl:238-239
     N = local_count(ctx, nparticles)                   # sharded: the rows of this rank's block
     P = Matrix{Float64}(undef, d, N); Wns = Vector{Float64}(undef, N); C = Vector{Float64}(undef, N)

@@ -139,7 +139,7 @@ def config_dict(cfg, args, particles_per_gpu, total, world, scaling):
                            f"in-kernel NVLink exchanges, rank-local DE partners), {scaling} scaling",
             "d": len(cfg["prior"]), "eps_target": cfg["eps_target"], "model": cfg["model"],
             "kernel": "IndicatorStrict0to-eps",
-            "relaxed_modes": [m for m, on in (("partner_segments", args.segments), ("systematic_resampling", args.systematic)) if on],
+            "relaxed_modes": [m for m, on in (("partner_segments", args.segments), ("systematic_resampling", args.systematic), ("fp32_state", args.fp32_state)) if on],
             "step": ("one complete abcdesmc! run (init + SMC loop to eps_target), fresh seed per step" if not args.max_iters else
                      f"init + the first {args.max_iters} SMC iterations of abcdesmc! (bounded sample of the run), fresh seed per step"),
             "l2": "particle state per run exceeds the 126 MB L2 (>= 218 B per particle); no explicit flush"}
@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--segments", action="store_true", help="relaxed-parity mode: warp-coherent partner segments (NOT the headline)")
     ap.add_argument("--systematic", action="store_true", help="relaxed-parity mode: systematic resampling (NOT the headline)")
+    ap.add_argument("--fp32-state", dest="fp32_state", action="store_true", help="relaxed-parity mode: FP32 particle state (NOT the headline)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.model:
@@ -292,7 +293,7 @@ def main():
         o = A.host._SmcOpts(); L.abcdez_smc_opts_default(C.byref(o))
         o.nparticles = Nglobal; o.nsims_max = 10**15; o.seed = seed; o.verboseout = 0; o.profile = int(profile); o.sync_every = 4
         o.max_iters = args.max_iters
-        o.partner_segments = int(args.segments); o.systematic_resampling = int(args.systematic)
+        o.partner_segments = int(args.segments); o.systematic_resampling = int(args.systematic); o.fp32_state = int(args.fp32_state)
         r = A.host._SmcResult()
         if host_out is not None:
             r.P, r.Wns, r.C = host_out[:3]

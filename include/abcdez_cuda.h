@@ -182,6 +182,11 @@ typedef struct {
     int32_t partner_segments;       /* 1: warp-coherent DE partners -- one pair of random bases per warp, lane l takes the
                                        l-th alive particle behind each (src/abcdez_smc.jl:119-126 draws every particle's
                                        partners independently); marginally the same law, coalesced gathers */
+    int32_t fp32_state;             /* 1: FP32 particle state -- the theta generations hold floats (half the bytes per row move and
+                                       per random partner gather); arithmetic, log prior, distances and weights stay FP64, every
+                                       proposal is rounded to float before it is scored.  Models of the static registry except
+                                       g-and-k; not with run-state snapshots (ABCDEZ_ERR_UNSUPPORTED otherwise) */
+    int32_t reserved1;
 } abcdez_smc_opts;
 
 typedef struct {

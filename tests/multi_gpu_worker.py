@@ -117,7 +117,9 @@ def gpu_main():
             print(f"sharded {name} N={N} world={world}: iters {got.iters} nsims {got.nsims} logZ {got.logZ:.6f} == oracle(islands={world})")
     # sharded abcdemc!: global extrema / counts, rank-local base particle and partners
     for name, spec, data, eps_t, N, seed, gens in [("gauss1d", [("normal", 0.0, math.sqrt(10.0))], [3.0, 1.0], 0.5, 4003, 13, 12),
-                                                   ("twod", [("normal", 0.0, 5.0)] * 2, [], 1.0, 3000, 17, 8)]:
+                                                   ("twod", [("normal", 0.0, 5.0)] * 2, [], 1.0, 3000, 17, 8),
+                                                   # a stepped simulator: init and sweeps through the queue on every rank
+                                                   ("birth_death", [("uniform", 0.0, 2.0)] * 2, [20.0, 4.0, 0.5, 400.0, 24.0, 30.0, 33.0, 41.0], 6.0, 2500, 19, 6)]:
         prior = A.Factored(*[fams[s_[0]](*s_[1:]) for s_ in spec])
         got = A.abcdemc(prior, A.Model(name, data), eps_t, None, nparticles=N, generations=gens, rng=seed, verbose=False, ctx=ctx)
         full = A.dist.gather_result(got)

@@ -534,7 +534,8 @@ def test_posterior_sample_on_device(A, oracle, gpu_ctx):
 # (test/runtests.jl:147,159: evidence within 10 %, posterior mean within one sample sd)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", [dict(systematic_resampling=True), dict(partner_segments=True),
-                                  dict(systematic_resampling=True, partner_segments=True)])
+                                  dict(systematic_resampling=True, partner_segments=True), dict(fp32_state=True),
+                                  dict(fp32_state=True, partner_segments=True, systematic_resampling=True)])
 def test_relaxed_modes_keep_evidence_and_posterior(A, gpu_ctx, mode):
     m = A.Model("gauss1d", [3.0, 1.0])
     lz, means = [], []
@@ -555,3 +556,24 @@ def test_relaxed_modes_keep_evidence_and_posterior(A, gpu_ctx, mode):
     w = r.Wns / r.Wns.sum(); w0 = r0.Wns / r0.Wns.sum()
     # (two independent Monte-Carlo runs: the posterior sd of a coordinate is ~0.9, the runs' effective sample sizes a few thousand)
     assert np.all(np.abs((r.P * w[:, None]).sum(0) - (r0.P * w0[:, None]).sum(0)) < 0.15)
+    if mode.get("fp32_state"):
+        assert np.array_equal(r.P, r.P.astype(np.float32).astype(np.float64))   # the particles ARE float rows
+
+
+def test_fp32_state_details(A, gpu_ctx):
+    """FP32 particle state (opts.fp32_state): discrete marginals and blobs survive the float rows, odd row strides (d = 1) and
+    resampling work, and the mode is refused where the kernels keep FP64 rows (g-and-k, snapshots)."""
+    spec, data = MODEL_CASES["normdu"]
+    r = A.abcdesmc(to_prior(A, spec), A.Model("normdu", data), 0.05, None, nparticles=3000, verbose=False, rng=3, fp32_state=True)
+    assert r.iters > 3 and np.isfinite(r.logZ) and np.array_equal(r.P, r.P.astype(np.float32).astype(np.float64))
+    assert np.array_equal(r.P[:, 1], np.rint(r.P[:, 1])) and r.P[:, 1].min() >= 1 and r.P[:, 1].max() <= 10
+    rb = A.abcdesmc(A.host.Normal(0, SQ10), A.Model("gauss1d_blob", [3.0, 1.0]), 0.3, None, nparticles=2000, verbose=False, rng=4, fp32_state=True)
+    y = rb.blobs.view(np.float64)[:, 0]
+    assert rb.stats["n_resamples"] >= 1 and np.allclose(np.abs(y - 3.0), rb.C, rtol=1e-12, atol=1e-12)   # blob = y, d = abs(y - 3): the blobs travelled with their particles
+    with pytest.raises(A.ABCdeZError) as e:
+        A.abcdesmc(A.Factored(*[A.host.Uniform(0.0, 10.0)] * 4), A.Model("gk", [1000.0] + _gk_octiles(GK_TRUE)), 1.0, None, nparticles=300,
+                   verbose=False, rng=1, fp32_state=True)
+    assert e.value.code == A.host.ERR_UNSUPPORTED
+    with pytest.raises(A.ABCdeZError):
+        A.abcdesmc(A.host.Normal(0, SQ10), A.Model("gauss1d", [3.0, 1.0]), 0.3, None, nparticles=1000, verbose=False, rng=1, fp32_state=True,
+                   max_iters=3, return_state=True)
