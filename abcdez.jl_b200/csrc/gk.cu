@@ -1,16 +1,16 @@
 // gk.cu -- config 3 of BASELINE.json: the g-and-k distribution, 4 parameters, quantile summaries of n
-// (<= 16384, default 10^4) simulated draws.  One dist! evaluation is ~2 * 10^6 arithmetic operations, so a
+// (<= 16384, default 10^4) simulated draws.  One dist! evaluation is ~10^6 arithmetic operations, so a
 // particle is simulated by a whole CTA instead of one thread:
 //   draws      thread t generates the Philox blocks t, t + 256, ... (one Box-Muller pair each in FP64, two in
-//              FP32) and pushes them through
-//                  x = A + B (1 + 0.8 (1 - e^{-g z}) / (1 + e^{-g z})) (1 + z^2)^k z
-//              into shared memory, tracking the extrema of the order-preserving keys on the way;
-//   summaries  the 7 octiles are order statistics x_(ceil(n j / 8)); instead of sorting, a multi-select in KEY
-//              space: one 2048-bin histogram resolves all 7 ranks to a bucket each -- over the window the
-//              distribution's own quantile function predicts for the octiles (~5 keys per bin), or between the
-//              sample's extrema when a rank falls outside it; buckets that are still large are refined 256 ways,
-//              and the <= 64 keys left per octile are ranked directly by one warp -- 2 passes over shared memory
-//              in the usual case;
+//              FP32; two blocks in flight per thread) into shared memory;
+//   summaries  the 7 octiles are order statistics x_(ceil(n j / 8)) of
+//                  x = Q(z) = A + B (1 + 0.8 (1 - e^{-g z}) / (1 + e^{-g z})) (1 + z^2)^k z.
+//              Fast path (n >= 4096, B > 0, k >= 0: Q increasing): select among the z -- per-octile histograms
+//              around Phi^-1(j/8), filled while the normals are drawn -- and push only the ~6 candidates per
+//              octile through Q ("the fast path" below).  Generic path (everything else, and the fallback): all
+//              draws through Q, then a multi-select in KEY space -- one 2048-bin histogram between the extrema
+//              resolves all 7 ranks to a bucket each, buckets that are still large are refined 256 ways, and the
+//              <= 64 keys left per octile are ranked directly by one warp.  Both return the exact order statistics;
 //   distance   sqrt(mean squared octile difference) in FP64.
 // Two registered models, same definition, different arithmetic:
 //   "gk"      FP64 with the library's portable log / exp / sin / cos (common.cuh), i.e. the arithmetic a Julia
@@ -21,7 +21,8 @@
 //             lanes and shorter polynomials; its posterior agrees with "gk" within Monte-Carlo error.
 // The proposal / accept logic around the simulation is abcdesmc_swarm! (src/abcdez_smc.jl:106-153) and
 // abcdemc_swarm! (src/abcdez_mc.jl:5-61) exactly as in sweep.cuh, evaluated redundantly by every thread of the
-// CTA (same Philox streams -> same decisions); thread 0 stores.  Bound: FP64 (FP32) pipe, DESIGN.md section 5.
+// CTA (same Philox streams -> same decisions); thread 0 stores.  Bound: instruction issue on the Box-Muller / Philox
+// chains (FP64 pipe 20 % busy), DESIGN.md section 5.
 #include "sweep.cuh"
 
 namespace abcdez {

@@ -3,6 +3,9 @@
 //   init_kernel       abcde_init!        src/abcdez_init.jl:2-22  (+ prior draws, src/abcdez_smc.jl:242-243)
 //   smc_sweep_kernel  abcdesmc_swarm!    src/abcdez_smc.jl:106-153
 //   mc_sweep_kernel   abcdemc_swarm!     src/abcdez_mc.jl:5-61
+// and, for heavy simulators (M::SPLIT), the same three steps as propose -> queue-driven simulate -> accept launches
+// (smc_propose / mc_propose / init_draw, simulate_queue_kernel, smc_accept / mc_accept / init_finish; second half of this file).
+// Relaxed-parity template switches of the fused kernels: SEG (warp-coherent partner segments), F32 (float theta rows).
 //
 // Jacobi double buffer without the copies.  The reference copies all four state arrays before every
 // sweep (identity.(), src/abcdez_smc.jl:337-340) so that generation g stays read-only while g+1 is
