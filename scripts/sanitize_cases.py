@@ -127,6 +127,16 @@ def _():
         assert gm.nsims == wm.nsims and np.array_equal(gm.C, wm.C), name
 
 
+@case("relaxed-parity modes: FP32 particle state, partner segments, systematic resampling (fused sweep, resampling, result assembly)")
+def _():
+    spec, name, data = C10
+    r = A.abcdesmc(prior_of(spec), A.Model(name, data), 3.0, None, nparticles=1500, rng=4, nsims_max=10**8, verbose=False,
+                   fp32_state=True, partner_segments=True, systematic_resampling=True)
+    assert r.iters > 5 and np.isfinite(r.logZ) and np.array_equal(r.P, r.P.astype(np.float32).astype(np.float64))
+    r1 = A.abcdesmc(prior_of(G1[0]), A.Model(G1[1], G1[2]), 0.3, None, nparticles=1500, rng=4, verbose=False, fp32_state=True)
+    assert abs(math.exp(r1.logZ) / 0.047940112540007955 - 1.0) < 0.3
+
+
 @case("g-and-k CTA-cooperative simulator (FP64 and FP32), multi-select")
 def _():
     data = [1000.0, 2.39384, 2.569082, 2.748052, 3.0, 3.4169, 4.196232, 5.900654]
