@@ -757,6 +757,8 @@ def abcdesmc_batch(runs, *, ctx: Optional[Context] = None, verboseout: bool = Fa
         o.Kmcmc = int(r.get("Kmcmc", 3)); o.Kmcmc_min = float(r.get("Kmcmc_min", 1.0)); o.kernel = _kernel_kind(r.get("ABCk", IndicatorStrict0toEps))
         o.facc_stop = r.get("facc_stop", 0.0); o.facc_min = r.get("facc_min", 0.0); o.facc_tune = r.get("facc_tune", 0.975)
         o.seed = _seed_from(r.get("rng")); o.verboseout = int(verboseout)
+        o.systematic_resampling = int(r.get("systematic_resampling", False)); o.partner_segments = int(r.get("partner_segments", False))
+        o.fp32_state = int(r.get("fp32_state", False))                        # relaxed-parity modes
         P = np.empty((N, d)); W = np.empty(N); Cc = np.empty(N); bl = np.zeros((N, max(B, 1)), dtype=np.uint8)
         h = {k: np.zeros(hist_cap) for k in ("eps", "dmin", "dmax", "logZ", "ess", "facc", "gamma0")}; hK = np.zeros(hist_cap, dtype=np.int32)
         q = res[i]

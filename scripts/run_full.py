@@ -14,6 +14,7 @@ ap.add_argument("--particles-total", type=int, required=True)
 ap.add_argument("--eps", type=float, default=-1.0)
 ap.add_argument("--seed", type=int, default=12345)
 ap.add_argument("--model", default="")
+ap.add_argument("--fp32-state", dest="fp32_state", action="store_true", help="relaxed-parity mode: FP32 particle state")
 ap.add_argument("--max-iters", type=int, default=0, help="safety bound on the SMC iterations (0: none); the reached eps is reported")
 args = ap.parse_args()
 
@@ -42,7 +43,7 @@ if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-r = A.abcdesmc(prior, model, eps_target, None, nparticles=N, rng=args.seed, verbose=False, ctx=ctx, nsims_max=10**15, sync_every=4, profile=True, max_iters=args.max_iters)
+r = A.abcdesmc(prior, model, eps_target, None, nparticles=N, rng=args.seed, verbose=False, ctx=ctx, nsims_max=10**15, sync_every=4, profile=True, max_iters=args.max_iters, fp32_state=args.fp32_state)
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 # posterior moments over the whole population: weighted sums of this rank's block, reduced over the ranks
