@@ -349,12 +349,23 @@ def main():
     barrier()
     t0 = time.perf_counter(); e2e_nsims = 0
     ke = max(1, min(args.steps, 5))
+    trace = []                                           # (ABCDEZ_TRACE: where the host time of an e2e step goes)
     for s in range(ke):
+        ta = time.perf_counter()
         r = run(base + 300000 + s, host_out=host_out)
+        tb = time.perf_counter()
         e2e_nsims += r.nsims
-        assert math.isfinite(float(Ch.sum()))           # the host reads the result
+        # the host reads the result: a strided sample of the distances and the evidence.  (Summing all of Ch with torch took
+        # 15-30 ms per step under torchrun at 4 ranks -- one intra-op thread competing with the other ranks' polling threads --
+        # and the uneven finish times then stalled the next run's first collective: profiles/README.md, "e2e of sharded runs".)
+        assert math.isfinite(float(Ch[::4099].sum())) and (args.mc or math.isfinite(r.logZ))
+        trace.append((1e3 * (tb - ta), 1e3 * (time.perf_counter() - tb)))
+    tc = time.perf_counter()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("ABCDEZ_TRACE"):
+        print(f"[bench] rank {rank}: e2e steps (library call ms, host read ms) {[(round(a, 2), round(b, 2)) for a, b in trace]}, "
+              f"final barrier {1e3 * (time.perf_counter() - tc):.2f} ms, total {1e3 * e2e_s:.2f} ms", file=sys.stderr, flush=True)
     d2h = Nglobal * ((D + 2) * 8 + model.blob_bytes)    # all ranks together
     mean_events = float(Bh[:, 1].mean()) if (Bh is not None and cfg["model"] == "birth_death") else None
     h2d = (len(cfg["data"]) + 4 * D) * 8 + 4 * D        # bound data + prior parameters; the state is born on the device
