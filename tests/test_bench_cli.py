@@ -30,3 +30,17 @@ def test_product_arm_has_no_cpu_fallback():
     assert p.returncode != 0
     assert "no CUDA device" in (p.stdout + p.stderr)
     assert not any(l.startswith("{") for l in p.stdout.splitlines())      # no number without the GPU
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """N > 1: the driver launches the reference arm like the product arm; rank 0 alone runs it on the SAME total
+    population with every host thread (torchrun's OMP_NUM_THREADS=1 is overridden), the other ranks exit 0."""
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29657", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--particles", "10000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["config"]["particles"] == 20000
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) or line["cpu_baseline"]["cores"] > 1 or (os.cpu_count() or 1) == 1
